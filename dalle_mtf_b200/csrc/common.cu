@@ -1,0 +1,102 @@
+#include "common.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace db200 {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(DB200_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return DB200_OK;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static encode_tiled_fn get_encode_fn() {
+  static encode_tiled_fn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<encode_tiled_fn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  encode_tiled_fn fn = get_encode_fn();
+  if (!fn) return set_error(DB200_E_CUDA, "cuTensorMapEncodeTiled driver entry point not available");
+  if (!aligned16(base)) return set_error(DB200_E_ALIGN, "TMA base pointer %p is not 16-byte aligned", base);
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (box[i] == 0 || box[i] > 256) return set_error(DB200_E_INVALID, "TMA box dim %d = %u out of range", i, box[i]);
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    if (strides_bytes[i] % 16 != 0)
+      return set_error(DB200_E_ALIGN, "TMA stride %d = %llu bytes is not a multiple of 16", i,
+                       (unsigned long long)strides_bytes[i]);
+  }
+  if (box[0] * 2 > 128) return set_error(DB200_E_INVALID, "TMA inner box exceeds the 128-byte swizzle span");
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DB200_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return DB200_OK;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
+}  // namespace db200
+
+extern "C" {
+
+const char* db200_last_error(void) { return db200::g_err; }
+int db200_version(void) { return 100; }
+
+int db200_device_check(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return db200::set_error(DB200_E_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+  int major = 0, minor = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  if (major != 10)
+    return db200::set_error(DB200_E_UNSUPPORTED, "device %d is sm_%d%d; libdalle_b200 ships sm_100a code only", dev,
+                            major, minor);
+  return DB200_OK;
+}
+}

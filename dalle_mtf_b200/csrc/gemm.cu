@@ -1,0 +1,473 @@
+// K3/K5/K6/K7/K8 — persistent, warp-specialised bf16 GEMM on tcgen05 for sm_100a.
+//
+//   D[M,N] = A[M,K] * B[K,N],  fp32 accumulation in TMEM, operands staged in shared memory by TMA (128B swizzle).
+//
+//   warp 0   : TMA producer (one elected lane)            smem ring: STAGES x {A 128x64, B BNx64} bf16
+//   warp 1   : MMA issuer  (one elected lane, tcgen05.mma cta_group::1, UMMA 128 x BN x 16)
+//   warp 2   : TMEM allocator / deallocator (2 accumulator stages of BN columns -> epilogue overlaps next tile)
+//   warp 3   : idle
+//   warps 4-7: epilogue (tcgen05.ld, one accumulator row per thread) -> bias / ReLU / residual / CE statistics ...
+//
+// Either operand may be K-major or MN-major in global memory; the tensor maps and the UMMA descriptors absorb the
+// difference, so forward (x*W), dgrad (dy*W^T) and wgrad (x^T*dy) are the same kernel.
+//
+// Reference call sites replaced: every mtf einsum / mtf.layers.dense of src/dalle_mtf/models.py (235-244, 303-311,
+// 317-324, 361-371, 391-395) and their gradients produced by mtf.gradients (src/optimizers.py:34).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace db200 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 256;
+constexpr int GROUP_M = 8;
+constexpr uint32_t SLAB_BYTES = BK * 128;  // one MN-major slab: [BK k-rows][64 bf16] = 8 KiB
+constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KiB
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256: power of two >= 32
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + size_t(STAGES) * STAGE_BYTES + 256 /*barriers*/;
+};
+
+struct GemmParams {
+  int M, N, K;
+  int a_mn, b_mn;
+  int m_tiles, n_tiles, splits, kb_total;
+  int mode, out_f32, relu;
+  float alpha;
+  void* D;
+  long long ldd;
+  const float* bias;
+  const bf16* residual;
+  long long ldr;
+  const bf16* aux;
+  long long ldaux;
+  const int* labels;
+  float* part_max;
+  float* part_sum;
+  float* label_logit;
+  const float* lse;
+  int n_valid;
+};
+
+struct TileCoord {
+  int m_blk, n_blk, kb0, kb1;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  const int mn_tiles = p.m_tiles * p.n_tiles;
+  const int split = tile / mn_tiles;
+  const int mn = tile - split * mn_tiles;
+  const int group_sz = GROUP_M * p.n_tiles;
+  const int group = mn / group_sz;
+  const int first_m = group * GROUP_M;
+  const int gm = min(GROUP_M, p.m_tiles - first_m);
+  const int in_group = mn - group * group_sz;
+  TileCoord t;
+  t.m_blk = first_m + in_group % gm;
+  t.n_blk = in_group / gm;
+  const int per = (p.kb_total + p.splits - 1) / p.splits;
+  t.kb0 = split * per;
+  t.kb1 = min(p.kb_total, t.kb0 + per);
+  return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * A_BYTES;
+  const uint32_t bars = base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t full_bar = bars;                   // STAGES x 8 B
+  const uint32_t empty_bar = bars + 8 * STAGES;     // STAGES x 8 B
+  const uint32_t tfull_bar = bars + 16 * STAGES;    // 2 x 8 B
+  const uint32_t tempty_bar = tfull_bar + 16;       // 2 x 8 B
+  const uint32_t tmem_slot = tempty_bar + 16;       // 4 B
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar + 8 * i, 1);
+      mbar_init(empty_bar + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar + 8 * i, 1);
+      mbar_init(tempty_bar + 8 * i, 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile);
+        const int m0 = t.m_blk * BM, n0 = t.n_blk * BN;
+        for (int kb = t.kb0; kb < t.kb1; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+          const int k0 = kb * BK;
+          const uint32_t a_dst = sA + stage * A_BYTES;
+          const uint32_t b_dst = sB + stage * Cfg::B_BYTES;
+          if (p.a_mn) {
+#pragma unroll
+            for (int s = 0; s < BM / 64; ++s) tma_load_2d(a_dst + s * SLAB_BYTES, &tmA, fb, m0 + 64 * s, k0);
+          } else {
+            tma_load_2d(a_dst, &tmA, fb, k0, m0);
+          }
+          if (p.b_mn) {
+#pragma unroll
+            for (int s = 0; s < BN / 64; ++s) tma_load_2d(b_dst + s * SLAB_BYTES, &tmB, fb, n0 + 64 * s, k0);
+          } else {
+            tma_load_2d(b_dst, &tmB, fb, k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = t.kb0; kb < t.kb1; ++kb) {
+        mbar_wait(full_bar + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = sA + stage * A_BYTES;
+          const uint32_t b_base = sB + stage * Cfg::B_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major: advance 16 elements (32 B) inside the 128 B swizzle row.
+            // MN-major: advance 16 k-rows (2 KiB); 64-wide MN atoms are SLAB_BYTES apart (LBO).
+            const uint64_t adesc = p.a_mn ? umma_smem_desc_sw128(a_base + k * 2048, SLAB_BYTES, 1024)
+                                          : umma_smem_desc_sw128(a_base + k * 32, 0, 1024);
+            const uint64_t bdesc = p.b_mn ? umma_smem_desc_sw128(b_base + k * 2048, SLAB_BYTES, 1024)
+                                          : umma_smem_desc_sw128(b_base + k * 32, 0, 1024);
+            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + 8 * stage);                  // frees the smem slot when these MMAs retire
+          if (kb == t.kb1 - 1) umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int wq = warp - 4;  // == warp % 4 : TMEM lane quarter this warp may access
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, tile);
+      const int row = t.m_blk * BM + wq * 32 + lane;
+      const int n0 = t.n_blk * BN;
+      const bool row_ok = row < p.M;
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + acc * BN + (uint32_t(wq * 32) << 16);
+
+      float run_max = -INFINITY, run_sum = 0.f;  // CE_STATS
+      int label = -1;
+      float row_lse = 0.f;
+      if ((p.mode == DB200_EPI_CE_STATS || p.mode == DB200_EPI_CE_GRAD) && row_ok) {
+        label = p.labels[row];
+        if (p.mode == DB200_EPI_CE_GRAD) row_lse = p.lse[row];
+      }
+
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(t_addr + c * 32, r);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+
+        if (p.mode == DB200_EPI_STORE) {
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col + 8 <= p.N) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float x = v[g * 8 + j] * p.alpha;
+                  if (p.bias) x += __ldg(p.bias + col + j);
+                  if (p.relu) x = fmaxf(x, 0.f);
+                  o[j] = x;
+                }
+                if (p.residual) {
+                  const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + (long long)row * p.ldr + col);
+                  const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
+                               r3 = unpack_bf16x2(rr.w);
+                  o[0] += r0.x; o[1] += r0.y; o[2] += r1.x; o[3] += r1.y;
+                  o[4] += r2.x; o[5] += r2.y; o[6] += r3.x; o[7] += r3.y;
+                }
+                if (p.out_f32) {
+                  float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col;
+                  *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
+                  *reinterpret_cast<float4*>(dp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                } else {
+                  bf16* dp = reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col;
+                  uint4 q;
+                  q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
+                  q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
+                  *reinterpret_cast<uint4*>(dp) = q;
+                }
+              }
+            }
+          }
+        } else if (p.mode == DB200_EPI_ATOMIC) {
+          if (row_ok) {
+            float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(dp + j, v[j] * p.alpha);
+          }
+        } else if (p.mode == DB200_EPI_RELU_BWD) {
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col + 8 <= p.N) {
+                const uint4 aa = *reinterpret_cast<const uint4*>(p.aux + (long long)row * p.ldaux + col);
+                const float2 a0 = unpack_bf16x2(aa.x), a1 = unpack_bf16x2(aa.y), a2 = unpack_bf16x2(aa.z),
+                             a3 = unpack_bf16x2(aa.w);
+                const float am[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = am[j] > 0.f ? v[g * 8 + j] * p.alpha : 0.f;
+                bf16* dp = reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col;
+                uint4 q;
+                q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
+                q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
+                *reinterpret_cast<uint4*>(dp) = q;
+              }
+            }
+          }
+        } else if (p.mode == DB200_EPI_CE_STATS) {
+          if (row_ok) {
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              float x = -INFINITY;
+              if (col < p.n_valid) {
+                x = v[j] + (p.bias ? __ldg(p.bias + col) : 0.f);
+                if (col == label) p.label_logit[row] = x;
+              }
+              v[j] = x;
+              cmax = fmaxf(cmax, x);
+            }
+            if (cmax > -INFINITY) {
+              const float new_max = fmaxf(run_max, cmax);
+              float s = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) s += __expf(v[j] - new_max);  // exp(-inf) = 0 for masked columns
+              run_sum = run_sum * __expf(run_max - new_max) + s;          // run_max = -inf -> factor 0
+              run_max = new_max;
+            }
+          }
+        } else {  // DB200_EPI_CE_GRAD
+          if (row_ok) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int col = col0 + g * 8;
+              if (col + 8 <= p.N) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int cc = col + j;
+                  float gval = 0.f;
+                  if (cc < p.n_valid) {
+                    const float x = v[g * 8 + j] + (p.bias ? __ldg(p.bias + cc) : 0.f);
+                    gval = (__expf(x - row_lse) - (cc == label ? 1.f : 0.f)) * p.alpha;
+                  }
+                  o[j] = gval;
+                }
+                bf16* dp = reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col;
+                uint4 q;
+                q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
+                q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
+                *reinterpret_cast<uint4*>(dp) = q;
+              }
+            }
+          }
+        }
+      }
+      if (p.mode == DB200_EPI_CE_STATS && row_ok) {
+        p.part_max[(long long)row * p.n_tiles + t.n_blk] = run_max;
+        p.part_sum[(long long)row * p.n_tiles + t.n_blk] = run_sum;
+      }
+      // release the accumulator stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN>
+static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DB200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles * p.splits;
+  const int grid = total < sm_count() ? total : sm_count();
+  gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace db200
+
+using namespace db200;
+
+extern "C" int db200_gemm_ce_tiles(int N) { return (N + 255) / 256; }
+
+extern "C" int db200_gemm_bf16(db200_stream_t stream_, const void* A, int a_mn_major, int64_t lda, const void* B,
+                               int b_mn_major, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
+                               const db200_gemm_epilogue* epi) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(epi != nullptr, DB200_E_INVALID, "gemm: epilogue descriptor is NULL");
+  DB200_REQUIRE(M > 0 && N > 0 && K > 0, DB200_E_INVALID, "gemm: M,N,K must be positive (got %d,%d,%d)", M, N, K);
+  DB200_REQUIRE(A && B, DB200_E_INVALID, "gemm: NULL operand");
+  DB200_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, DB200_E_ALIGN,
+                "gemm: lda/ldb must be multiples of 8 elements (16 B) for TMA (got %lld, %lld)", (long long)lda,
+                (long long)ldb);
+  DB200_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K), DB200_E_INVALID,
+                "gemm: leading dimension smaller than the contiguous extent");
+  const int mode = epi->mode;
+  DB200_REQUIRE(mode >= DB200_EPI_STORE && mode <= DB200_EPI_CE_GRAD, DB200_E_INVALID, "gemm: unknown epilogue %d",
+                mode);
+  if (mode != DB200_EPI_CE_STATS) {
+    DB200_REQUIRE(D != nullptr && aligned16(D), DB200_E_ALIGN, "gemm: D must be non-NULL and 16-byte aligned");
+    DB200_REQUIRE(ldd >= N, DB200_E_INVALID, "gemm: ldd < N");
+  }
+  if (mode == DB200_EPI_STORE || mode == DB200_EPI_RELU_BWD || mode == DB200_EPI_CE_GRAD) {
+    DB200_REQUIRE(N % 8 == 0 && ldd % 8 == 0, DB200_E_ALIGN,
+                  "gemm: vectorised store epilogues need N and ldd to be multiples of 8 (got N=%d ldd=%lld)", N,
+                  (long long)ldd);
+  }
+  if (mode == DB200_EPI_STORE && epi->residual)
+    DB200_REQUIRE(aligned16(epi->residual) && epi->ldr % 8 == 0 && epi->ldr >= N, DB200_E_ALIGN,
+                  "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
+  if (mode == DB200_EPI_RELU_BWD)
+    DB200_REQUIRE(epi->aux && aligned16(epi->aux) && epi->ldaux % 8 == 0 && epi->ldaux >= N, DB200_E_ALIGN,
+                  "gemm: RELU_BWD needs an aligned aux tensor");
+  if (mode == DB200_EPI_CE_STATS)
+    DB200_REQUIRE(epi->labels && epi->part_max && epi->part_sum && epi->label_logit && epi->n_valid > 0 &&
+                      epi->n_valid <= N,
+                  DB200_E_INVALID, "gemm: CE_STATS needs labels/part_max/part_sum/label_logit and 0 < n_valid <= N");
+  if (mode == DB200_EPI_CE_GRAD)
+    DB200_REQUIRE(epi->labels && epi->lse && epi->n_valid > 0 && epi->n_valid <= N, DB200_E_INVALID,
+                  "gemm: CE_GRAD needs labels/lse and 0 < n_valid <= N");
+  int splits = 1;
+  const int kb_total = (K + BK - 1) / BK;
+  if (mode == DB200_EPI_ATOMIC) {
+    splits = epi->split_k;
+    if (splits <= 0) {  // auto: fill the machine, keep >= 4 k-blocks per split
+      const int tiles = ((M + BM - 1) / BM) * ((N + 255) / 256);
+      splits = sm_count() / (tiles > 0 ? tiles : 1);
+      if (splits > kb_total / 4) splits = kb_total / 4;
+      if (splits < 1) splits = 1;
+    }
+    if (splits > kb_total) splits = kb_total;
+    // every split must own at least one k-block
+    const int per = (kb_total + splits - 1) / splits;
+    splits = (kb_total + per - 1) / per;
+  } else {
+    DB200_REQUIRE(epi->split_k <= 1, DB200_E_INVALID, "gemm: split_k > 1 is only valid with DB200_EPI_ATOMIC");
+  }
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = a_mn_major ? 1 : 0;
+  p.b_mn = b_mn_major ? 1 : 0;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.splits = splits;
+  p.kb_total = kb_total;
+  p.mode = mode;
+  p.out_f32 = epi->out_f32;
+  p.relu = epi->relu;
+  p.alpha = epi->alpha;
+  p.D = D;
+  p.ldd = ldd;
+  p.bias = epi->bias;
+  p.residual = reinterpret_cast<const bf16*>(epi->residual);
+  p.ldr = epi->ldr;
+  p.aux = reinterpret_cast<const bf16*>(epi->aux);
+  p.ldaux = epi->ldaux;
+  p.labels = epi->labels;
+  p.part_max = epi->part_max;
+  p.part_sum = epi->part_sum;
+  p.label_logit = epi->label_logit;
+  p.lse = epi->lse;
+  p.n_valid = epi->n_valid;
+
+  // tile width: 256 unless that leaves most SMs idle (CE epilogues are defined on 256-wide tiles)
+  int bn = 256;
+  if (mode != DB200_EPI_CE_STATS && mode != DB200_EPI_CE_GRAD) {
+    const int tiles256 = p.m_tiles * ((N + 255) / 256) * splits;
+    if (N <= 128 || tiles256 * 2 <= sm_count()) bn = 128;
+  }
+  p.n_tiles = (N + bn - 1) / bn;
+
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (p.a_mn) rc = make_tmap_2d(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  else        rc = make_tmap_2d(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM);
+  if (rc != DB200_OK) return rc;
+  if (p.b_mn) rc = make_tmap_2d(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
+  else        rc = make_tmap_2d(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, (uint32_t)bn);
+  if (rc != DB200_OK) return rc;
+
+  if (bn == 256) return launch_gemm<256>(stream, tmA, tmB, p);
+  return launch_gemm<128>(stream, tmA, tmB, p);
+}

@@ -1,0 +1,268 @@
+"""Tensor-level wrappers over the C ABI (one Python function per exported kernel family).
+
+Every function enqueues on torch's current CUDA stream and returns without synchronising.  Tensors are only
+containers for device memory here; no torch arithmetic happens on the product path.
+"""
+import ctypes
+
+import torch
+
+from . import lib as L
+from .lib import GemmEpilogue, ConvDesc, check, ptr, stream_ptr
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+I32 = torch.int32
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise L.DB200Error(f"{name}: tensor must live on a CUDA device (no CPU fallback)")
+    if t.dtype != dtype:
+        raise L.DB200Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if t.dim() > 0 and t.stride(-1) != 1:
+        raise L.DB200Error(f"{name}: innermost dimension must be contiguous")
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, ldd=None, mode=L.EPI_STORE,
+         alpha=1.0, bias=None, relu=False, residual=None, aux=None, split_k=1, labels=None, part_max=None,
+         part_sum=None, label_logit=None, lse=None, n_valid=0):
+    """D[M,N] = A[M,K] @ B[K,N] on tcgen05.  a_mn / b_mn: operand is stored with M (resp. N) contiguous.
+
+    a: [M,K] (k-major) or [K,M] (mn-major);  b: [N,K] (k-major) or [K,N] (mn-major).
+    """
+    L.require_device()
+    _chk(a, BF16, "gemm A")
+    _chk(b, BF16, "gemm B")
+    lda = lda if lda is not None else a.stride(0)
+    ldb = ldb if ldb is not None else b.stride(0)
+    e = GemmEpilogue()
+    e.mode = mode
+    e.out_f32 = 1 if (out is not None and out.dtype == F32) else 0
+    e.relu = 1 if relu else 0
+    e.split_k = split_k
+    e.alpha = alpha
+    _chk(bias, F32, "gemm bias")
+    e.bias = ptr(bias)
+    _chk(residual, BF16, "gemm residual")
+    e.residual = ptr(residual)
+    e.ldr = residual.stride(0) if residual is not None else 0
+    _chk(aux, BF16, "gemm aux")
+    e.aux = ptr(aux)
+    e.ldaux = aux.stride(0) if aux is not None else 0
+    _chk(labels, I32, "gemm labels")
+    e.labels = ptr(labels)
+    e.part_max, e.part_sum, e.label_logit, e.lse = ptr(part_max), ptr(part_sum), ptr(label_logit), ptr(lse)
+    e.n_valid = n_valid
+    if out is not None:
+        if mode == L.EPI_ATOMIC:
+            _chk(out, F32, "gemm D (atomic)")
+        ldd = ldd if ldd is not None else out.stride(0)
+    else:
+        ldd = 0
+    check(L.load().db200_gemm_bf16(stream_ptr(), ptr(a), int(a_mn), lda, ptr(b), int(b_mn), ldb, ptr(out), ldd,
+                                   M, N, K, ctypes.byref(e)), "db200_gemm_bf16")
+    return out
+
+
+def linear_fwd(x, w, out, bias=None, relu=False, residual=None):
+    """out[T,N] = act(x[T,K] @ w[K,N] + bias) + residual      (forward: A k-major, B mn-major)."""
+    T, K = x.shape
+    N = w.shape[1]
+    return gemm(x, w, out, T, N, K, a_mn=False, b_mn=True, bias=bias, relu=relu, residual=residual)
+
+
+def linear_dgrad(dy, w, out, relu_mask_of=None):
+    """out[T,K] = dy[T,N] @ w[K,N]^T  (optionally masked by relu_mask_of > 0)."""
+    T, N = dy.shape
+    K = w.shape[0]
+    if relu_mask_of is not None:
+        return gemm(dy, w, out, T, K, N, a_mn=False, b_mn=False, mode=L.EPI_RELU_BWD, aux=relu_mask_of)
+    return gemm(dy, w, out, T, K, N, a_mn=False, b_mn=False)
+
+
+def linear_wgrad(x, dy, dw, N=None):
+    """dw[K,N] (f32) += x[T,K]^T @ dy[T,N]      (both operands mn-major, split-K + red.add)."""
+    T, K = x.shape
+    N = N if N is not None else dy.shape[1]
+    return gemm(x, dy, dw, K, N, T, a_mn=True, b_mn=True, mode=L.EPI_ATOMIC, split_k=0)
+
+
+def ce_tiles(N):
+    return L.load().db200_gemm_ce_tiles(N)
+
+
+def ce_finish(part_max, part_sum, label_logit, lse, loss_rows, loss_sum):
+    L.require_device()
+    M, n_tiles = part_max.shape
+    check(L.load().db200_ce_finish(stream_ptr(), ptr(part_max), ptr(part_sum), ptr(label_logit), ptr(lse),
+                                   ptr(loss_rows), ptr(loss_sum), M, n_tiles), "db200_ce_finish")
+
+
+# ----------------------------------------------------------------------------------------------- row ops
+def embed_fwd(ids, wte, wpe, out):
+    L.require_device()
+    _chk(ids, I32, "ids"); _chk(wte, BF16, "wte"); _chk(wpe, BF16, "wpe"); _chk(out, BF16, "out")
+    B, S = ids.shape
+    V, d = wte.shape
+    check(L.load().db200_embed_fwd(stream_ptr(), ptr(ids), ptr(wte), ptr(wpe), ptr(out), B, S, d, V), "embed_fwd")
+    return out
+
+
+def embed_bwd(ids, dx, dwte, dwpe):
+    L.require_device()
+    _chk(ids, I32, "ids"); _chk(dx, BF16, "dx"); _chk(dwte, F32, "dwte"); _chk(dwpe, F32, "dwpe")
+    B, S = ids.shape
+    V, d = dwte.shape
+    check(L.load().db200_embed_bwd(stream_ptr(), ptr(ids), ptr(dx), ptr(dwte), ptr(dwpe), B, S, d, V), "embed_bwd")
+
+
+def layernorm_fwd(x, g, b, y, mean, rstd, eps=1e-5):
+    L.require_device()
+    _chk(x, BF16, "x"); _chk(y, BF16, "y"); _chk(g, F32, "g"); _chk(b, F32, "b")
+    _chk(mean, F32, "mean"); _chk(rstd, F32, "rstd")
+    rows, d = x.shape
+    check(L.load().db200_layernorm_fwd(stream_ptr(), ptr(x), ptr(g), ptr(b), ptr(y), ptr(mean), ptr(rstd), rows, d,
+                                       eps), "layernorm_fwd")
+    return y
+
+
+def layernorm_bwd(dy, x, g, mean, rstd, dres, dx, dg, db):
+    L.require_device()
+    _chk(dy, BF16, "dy"); _chk(x, BF16, "x"); _chk(dres, BF16, "dres"); _chk(dx, BF16, "dx")
+    _chk(g, F32, "g"); _chk(dg, F32, "dg"); _chk(db, F32, "db")
+    rows, d = x.shape
+    check(L.load().db200_layernorm_bwd(stream_ptr(), ptr(dy), ptr(x), ptr(g), ptr(mean), ptr(rstd), ptr(dres),
+                                       ptr(dx), ptr(dg), ptr(db), rows, d), "layernorm_bwd")
+    return dx
+
+
+def colsum(x, out_accum, rows=None, cols=None):
+    L.require_device()
+    _chk(x, BF16, "x"); _chk(out_accum, F32, "out_accum")
+    rows = rows if rows is not None else x.shape[0]
+    cols = cols if cols is not None else x.shape[1]
+    check(L.load().db200_colsum_bf16(stream_ptr(), ptr(x), x.stride(0), rows, cols, ptr(out_accum)), "colsum")
+
+
+def cast_f32_to_bf16(src, dst):
+    L.require_device()
+    _chk(src, F32, "src"); _chk(dst, BF16, "dst")
+    check(L.load().db200_cast_f32_to_bf16(stream_ptr(), ptr(src), ptr(dst), src.numel()), "cast_f32_to_bf16")
+    return dst
+
+
+def cast_bf16_to_f32(src, dst):
+    L.require_device()
+    _chk(src, BF16, "src"); _chk(dst, F32, "dst")
+    check(L.load().db200_cast_bf16_to_f32(stream_ptr(), ptr(src), ptr(dst), src.numel()), "cast_bf16_to_f32")
+    return dst
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def attn_fwd(qkv, out, lse, B, S, H, dh, scale=1.0):
+    L.require_device()
+    _chk(qkv, BF16, "qkv"); _chk(out, BF16, "out"); _chk(lse, F32, "lse")
+    check(L.load().db200_attn_causal_fwd(stream_ptr(), ptr(qkv), ptr(out), ptr(lse), B, S, H, dh, scale),
+          "attn_causal_fwd")
+    return out
+
+
+def attn_bwd(qkv, out, dout, lse, dq_accum, delta, dqkv, B, S, H, dh, scale=1.0):
+    L.require_device()
+    _chk(qkv, BF16, "qkv"); _chk(out, BF16, "out"); _chk(dout, BF16, "dout"); _chk(dqkv, BF16, "dqkv")
+    _chk(lse, F32, "lse"); _chk(dq_accum, F32, "dq_accum"); _chk(delta, F32, "delta")
+    check(L.load().db200_attn_causal_bwd(stream_ptr(), ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dq_accum),
+                                         ptr(delta), ptr(dqkv), B, S, H, dh, scale), "attn_causal_bwd")
+    return dqkv
+
+
+# ----------------------------------------------------------------------------------------------- optimiser
+def sqnorm(g, out_accum):
+    L.require_device()
+    _chk(g, F32, "g"); _chk(out_accum, F32, "out_accum")
+    check(L.load().db200_sqnorm_f32(stream_ptr(), ptr(g), g.numel(), ptr(out_accum)), "sqnorm")
+
+
+def adam_step(p, m, v, g, p_bf16, lr, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0, gnorm_sq=None,
+              clip=0.0, grad_scale=1.0, bias_correction=False, step=0):
+    L.require_device()
+    for t, n in ((p, "p"), (m, "m"), (v, "v"), (g, "g")):
+        _chk(t, F32, n)
+    _chk(p_bf16, BF16, "p_bf16")
+    check(L.load().db200_adam_step(stream_ptr(), ptr(p), ptr(m), ptr(v), ptr(g), ptr(p_bf16), p.numel(), lr, beta1,
+                                   beta2, eps, weight_decay, ptr(gnorm_sq), clip, grad_scale, int(bias_correction),
+                                   int(step)), "adam_step")
+
+
+# ----------------------------------------------------------------------------------------------- VAE ops
+def conv_desc(N, H, W, Cin, Cout, KH, KW, stride, transposed=False, act_f32=True, relu_in=False):
+    c = ConvDesc()
+    c.N, c.H, c.W, c.Cin, c.Cout = N, H, W, Cin, Cout
+    c.KH, c.KW, c.stride = KH, KW, stride
+    if transposed:
+        c.Ho, c.Wo = H * stride, W * stride
+    else:
+        c.Ho, c.Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
+    c.transposed = int(transposed)
+    c.act_f32 = int(act_f32)
+    c.relu_in = int(relu_in)
+    return c
+
+
+def conv2d_fwd(c, x, w, bias, residual, y):
+    L.require_device()
+    check(L.load().db200_conv2d_fwd(stream_ptr(), ctypes.byref(c), ptr(x), ptr(w), ptr(bias), ptr(residual),
+                                    ptr(y)), "conv2d_fwd")
+    return y
+
+
+def conv2d_dgrad(c, dy, w, x_mask, dres, dx):
+    L.require_device()
+    check(L.load().db200_conv2d_dgrad(stream_ptr(), ctypes.byref(c), ptr(dy), ptr(w), ptr(x_mask), ptr(dres),
+                                      ptr(dx)), "conv2d_dgrad")
+    return dx
+
+
+def conv2d_wgrad(c, x, dy, dw, dbias):
+    L.require_device()
+    check(L.load().db200_conv2d_wgrad(stream_ptr(), ctypes.byref(c), ptr(x), ptr(dy), ptr(dw), ptr(dbias)),
+          "conv2d_wgrad")
+
+
+def rowmatmul(a, b, out, rows, K, N, b_transposed=False, accumulate=False):
+    L.require_device()
+    check(L.load().db200_rowmatmul_f32(stream_ptr(), ptr(a), ptr(b), ptr(out), rows, K, N, int(b_transposed),
+                                       int(accumulate)), "rowmatmul")
+    return out
+
+
+def rowmatmul_tn(a, b, out_accum, rows, M, N):
+    L.require_device()
+    check(L.load().db200_rowmatmul_tn_f32(stream_ptr(), ptr(a), ptr(b), ptr(out_accum), rows, M, N), "rowmatmul_tn")
+
+
+def gumbel_softmax_fwd(logits, u, y_soft, y_out, idx, rows, K, tau, hard):
+    L.require_device()
+    check(L.load().db200_gumbel_softmax_fwd(stream_ptr(), ptr(logits), ptr(u), ptr(y_soft), ptr(y_out), ptr(idx),
+                                            rows, K, tau, int(hard)), "gumbel_softmax_fwd")
+
+
+def gumbel_softmax_bwd(y_soft, dy, dlogits, rows, K, tau):
+    L.require_device()
+    check(L.load().db200_gumbel_softmax_bwd(stream_ptr(), ptr(y_soft), ptr(dy), ptr(dlogits), rows, K, tau),
+          "gumbel_softmax_bwd")
+
+
+def argmax_rows(x, idx, rows, K):
+    L.require_device()
+    check(L.load().db200_argmax_rows_f32(stream_ptr(), ptr(x), ptr(idx), rows, K), "argmax_rows")
+
+
+def mse_fwd_bwd(pred, target, dpred, loss_accum, scale):
+    L.require_device()
+    check(L.load().db200_mse_fwd_bwd(stream_ptr(), ptr(pred), ptr(target), ptr(dpred), ptr(loss_accum),
+                                     pred.numel(), scale), "mse_fwd_bwd")
