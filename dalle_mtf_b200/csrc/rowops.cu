@@ -79,6 +79,14 @@ __global__ void embed_bwd_wpe_kernel(const bf16* __restrict__ dx, float* __restr
   for (int j = 0; j < 8; ++j) dst[j] += acc[j];
 }
 
+// labels[b][t] = ids[b][t+1] for t < S-1, labels[b][S-1] = eos      (src/dalle_mtf/models.py:407-410)
+__global__ void shift_labels_kernel(const int* __restrict__ ids, int* __restrict__ labels, int B, int S, int eos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * S) return;
+  const int t = i % S;
+  labels[i] = (t == S - 1) ? eos : ids[i + 1];
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // One warp per row; the row lives in registers (NCH 16-byte chunks per lane, d = NCH * 256).
 template <int NCH>
@@ -321,6 +329,14 @@ extern "C" int db200_embed_bwd(db200_stream_t stream_, const int32_t* ids, const
   const int total_pe = S * (d / 8);
   embed_bwd_wpe_kernel<<<(total_pe + 127) / 128, 128, 0, stream>>>((const bf16*)dx, dwpe, B, S, d);
   return check_launch("embed_bwd_wpe_kernel");
+}
+
+extern "C" int db200_shift_labels(db200_stream_t stream_, const int32_t* ids, int32_t* labels, int B, int S,
+                                  int eos_id) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(B > 0 && S > 0 && ids && labels, DB200_E_INVALID, "shift_labels: bad arguments");
+  shift_labels_kernel<<<(B * S + 255) / 256, 256, 0, stream>>>(ids, labels, B, S, eos_id);
+  return check_launch("shift_labels_kernel");
 }
 
 extern "C" int db200_layernorm_fwd(db200_stream_t stream_, const void* x, const float* g, const float* b, void* y,

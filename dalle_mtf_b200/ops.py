@@ -120,6 +120,14 @@ def embed_bwd(ids, dx, dwte, dwpe):
     check(L.load().db200_embed_bwd(stream_ptr(), ptr(ids), ptr(dx), ptr(dwte), ptr(dwpe), B, S, d, V), "embed_bwd")
 
 
+def shift_labels(ids, labels, eos_id):
+    L.require_device()
+    _chk(ids, I32, "ids"); _chk(labels, I32, "labels")
+    B, S = ids.shape
+    check(L.load().db200_shift_labels(stream_ptr(), ptr(ids), ptr(labels), B, S, eos_id), "shift_labels")
+    return labels
+
+
 def layernorm_fwd(x, g, b, y, mean, rstd, eps=1e-5):
     L.require_device()
     _chk(x, BF16, "x"); _chk(y, BF16, "y"); _chk(g, F32, "g"); _chk(b, F32, "b")

@@ -47,6 +47,10 @@ int db200_embed_fwd(db200_stream_t stream, const int32_t* ids, const void* wte_b
 int db200_embed_bwd(db200_stream_t stream, const int32_t* ids, const void* dx_bf16, float* dwte, float* dwpe, int B,
                     int S, int d, int V);
 
+/* label shift: labels[b][t] = ids[b][t+1], labels[b][S-1] = eos_id.  Replaces the pad + gather at
+ * src/dalle_mtf/models.py:407-410 (pad op: src/dalle_mtf/ops.py:6-68). */
+int db200_shift_labels(db200_stream_t stream, const int32_t* ids, int32_t* labels, int B, int S, int eos_id);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * K2  LayerNorm.   Replaces DALLE.layer_norm + norm():  src/dalle_mtf/models.py:373-389, src/dalle_mtf/layers.py:30-33
  *     y = (x - mean) * rsqrt(mean((x-mean)^2) + eps) * g + b      (biased variance, fp32 statistics)
