@@ -1,0 +1,506 @@
+// K11 — discrete-VAE convolutions as im2col-free, shared-memory-staged direct convolutions (CUDA cores, fp32
+// accumulate).  One generic "gather-GEMM" kernel covers conv / conv-transpose forward and both dgrads, one generic
+// "outer-product" kernel covers both wgrads; the host describes each case with a tap list.
+//
+//   gather-GEMM:   y[pix, n] = epi( sum_taps sum_k  x[src(pix, tap), k] * w[tap][k][n] )
+//                  64 pixels x 64 channels per CTA, K staged through smem in chunks of 16, 4x4 outputs per thread.
+//   outer-product: dw[tap][a][b] += sum_pix p[srcP(pix,tap), a] * q[srcQ(pix,tap), b]   (split over pixels, red.add)
+//
+// Reference: tf.layers.conv2d / conv2d_transpose call sites src/vae_tf/models.py:95-109, 139-155 (NHWC, HWIO,
+// padding SAME); codebook matmuls src/vae_tf/models.py:118,127 reuse the same kernels with a 1x1 geometry.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace db200 {
+
+constexpr int MAX_TAPS = 16;
+
+struct Tap {
+  int dy, dx;       // source pixel = (oy*in_stride + dy, ox*in_stride + dx)
+  long long w_off;  // element offset of this tap's [K][N] slab in the weight tensor
+};
+
+struct ConvGemmParams {
+  int NB, OH, OW;          // enumeration grid of output pixels (M = NB*OH*OW)
+  int out_H, out_W;        // spatial dims of the output tensor
+  int out_stride, oa, ob;  // output pixel = (oy*out_stride + oa, ox*out_stride + ob)
+  int in_H, in_W, in_stride;
+  int K, Nn;               // channels contracted / produced
+  int ntaps;
+  Tap taps[MAX_TAPS];
+  long long w_k_stride, w_n_stride;
+  const void* x;
+  const float* w;
+  const float* bias;
+  const void* residual;  // same layout/dtype as y
+  const void* mask;      // same layout/dtype as y: y *= (mask > 0)
+  void* y;
+  int relu;
+};
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p);
+template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void stf(T* p, float v);
+template <> __device__ __forceinline__ void stf<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void stf<bf16>(bf16* p, float v) { *p = __float2bfloat16(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_gemm_kernel(const ConvGemmParams p) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long M = (long long)p.NB * p.OH * p.OW;
+  const long long m0 = (long long)blockIdx.x * 64;
+  const int n0 = blockIdx.y * 64;
+  const T* x = reinterpret_cast<const T*>(p.x);
+
+  // A loader: this thread always stages pixel (tid >> 2), channels ((tid & 3) * 4 .. +3) of the current K chunk
+  const int a_pix = tid >> 2, a_k = (tid & 3) * 4;
+  const long long am = m0 + a_pix;
+  int a_n = 0, a_oy = 0, a_ox = 0;
+  const bool a_ok = am < M;
+  if (a_ok) {
+    a_ox = (int)(am % p.OW);
+    a_oy = (int)((am / p.OW) % p.OH);
+    a_n = (int)(am / ((long long)p.OW * p.OH));
+  }
+  const bool n_contig = (p.w_n_stride == 1);
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int t = 0; t < p.ntaps; ++t) {
+    const int iy = a_oy * p.in_stride + p.taps[t].dy, ix = a_ox * p.in_stride + p.taps[t].dx;
+    const bool src_ok = a_ok && iy >= 0 && iy < p.in_H && ix >= 0 && ix < p.in_W;
+    const T* src = x + (((long long)a_n * p.in_H + iy) * p.in_W + ix) * p.K;
+    const float* wt = p.w + p.taps[t].w_off;
+    for (int k0 = 0; k0 < p.K; k0 += 16) {
+      // ---- stage A (zero-filled outside the image / beyond K)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + a_k + j;
+        As[a_k + j][a_pix] = (src_ok && k < p.K) ? ldf<T>(src + k) : 0.f;
+      }
+      // ---- stage B
+      if (n_contig) {
+        const int bk = tid >> 4, bn = (tid & 15) * 4;
+        const int k = k0 + bk;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int n = n0 + bn + j;
+          Bs[bk][bn + j] = (k < p.K && n < p.Nn) ? wt[(long long)k * p.w_k_stride + n] : 0.f;
+        }
+      } else {
+        const int bn = tid >> 2, bk = (tid & 3) * 4;
+        const int n = n0 + bn;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + bk + j;
+          Bs[bk + j][bn] = (k < p.K && n < p.Nn) ? wt[(long long)k * p.w_k_stride + (long long)n * p.w_n_stride] : 0.f;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  // ---- epilogue
+  T* y = reinterpret_cast<T*>(p.y);
+  const T* res = reinterpret_cast<const T*>(p.residual);
+  const T* msk = reinterpret_cast<const T*>(p.mask);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+    const int ox = (int)(m % p.OW);
+    const int oy = (int)((m / p.OW) % p.OH);
+    const int n = (int)(m / ((long long)p.OW * p.OH));
+    const long long o =
+        (((long long)n * p.out_H + (oy * p.out_stride + p.oa)) * p.out_W + (ox * p.out_stride + p.ob)) * p.Nn;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c >= p.Nn) continue;
+      float v = acc[i][j];
+      if (p.bias) v += p.bias[c];
+      if (p.relu) v = fmaxf(v, 0.f);
+      if (msk) v = ldf<T>(msk + o + c) > 0.f ? v : 0.f;
+      if (res) v += ldf<T>(res + o + c);
+      stf<T>(y + o + c, v);
+    }
+  }
+}
+
+struct WgradTap {
+  int pdy, pdx, qdy, qdx;
+  long long w_off;
+};
+struct ConvWgradParams {
+  int NB, OH, OW;  // enumeration grid (contracted)
+  int pH, pW, pC, p_stride;
+  int qH, qW, qC, q_stride;
+  int ntaps, splits;
+  WgradTap taps[MAX_TAPS];
+  long long a_stride, b_stride;
+  const void* P;
+  const void* Q;
+  float* dw;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(const ConvWgradParams p) {
+  __shared__ float Ps[16][64 + 4];
+  __shared__ float Qs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int a0 = blockIdx.x * 64, b0 = blockIdx.y * 64;
+  const int t = blockIdx.z % p.ntaps, split = blockIdx.z / p.ntaps;
+  const long long M = (long long)p.NB * p.OH * p.OW;
+  const long long per = ((M + p.splits - 1) / p.splits + 15) / 16 * 16;
+  const long long mbeg = split * per, mend = (mbeg + per < M) ? mbeg + per : M;
+  const T* P = reinterpret_cast<const T*>(p.P);
+  const T* Q = reinterpret_cast<const T*>(p.Q);
+  const WgradTap tap = p.taps[t];
+  const int l_pix = tid >> 4, l_c = (tid & 15) * 4;  // loader: pixel l_pix of the chunk, channels l_c..l_c+3
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (long long mm = mbeg; mm < mend; mm += 16) {
+    const long long m = mm + l_pix;
+    bool pok = false, qok = false;
+    const T *psrc = P, *qsrc = Q;
+    if (m < mend) {
+      const int ox = (int)(m % p.OW);
+      const int oy = (int)((m / p.OW) % p.OH);
+      const int n = (int)(m / ((long long)p.OW * p.OH));
+      const int py = oy * p.p_stride + tap.pdy, px = ox * p.p_stride + tap.pdx;
+      const int qy = oy * p.q_stride + tap.qdy, qx = ox * p.q_stride + tap.qdx;
+      pok = py >= 0 && py < p.pH && px >= 0 && px < p.pW;
+      qok = qy >= 0 && qy < p.qH && qx >= 0 && qx < p.qW;
+      psrc = P + (((long long)n * p.pH + py) * p.pW + px) * p.pC;
+      qsrc = Q + (((long long)n * p.qH + qy) * p.qW + qx) * p.qC;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int a = a0 + l_c + j, b = b0 + l_c + j;
+      Ps[l_pix][l_c + j] = (pok && a < p.pC) ? ldf<T>(psrc + a) : 0.f;
+      Qs[l_pix][l_c + j] = (qok && b < p.qC) ? ldf<T>(qsrc + b) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&Ps[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Qs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* dw = p.dw + tap.w_off;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int a = a0 + ty * 4 + i;
+    if (a >= p.pC) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int b = b0 + tx * 4 + j;
+      if (b >= p.qC) continue;
+      atomicAdd(dw + (long long)a * p.a_stride + (long long)b * p.b_stride, acc[i][j]);
+    }
+  }
+}
+
+// column sums of a [rows][C] activation matrix (bias gradients), T = float | bf16
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_act_kernel(const T* __restrict__ x, long long rows, int C,
+                                                          float* __restrict__ out) {
+  // block: 32 columns x 8 row-lanes
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float acc = 0.f;
+  if (c < C)
+    for (long long r = (long long)blockIdx.y * 8 + ry; r < rows; r += (long long)gridDim.y * 8)
+      acc += ldf<T>(x + r * C + c);
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][cx];
+    atomicAdd(out + c, s);
+  }
+}
+
+static int launch_gemm(cudaStream_t stream, const ConvGemmParams& p, bool act_f32) {
+  const long long M = (long long)p.NB * p.OH * p.OW;
+  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((p.Nn + 63) / 64));
+  if (act_f32) conv_gemm_kernel<float><<<grid, 256, 0, stream>>>(p);
+  else         conv_gemm_kernel<bf16><<<grid, 256, 0, stream>>>(p);
+  return check_launch("conv_gemm_kernel");
+}
+
+static int launch_wgrad(cudaStream_t stream, ConvWgradParams& p, bool act_f32) {
+  const long long M = (long long)p.NB * p.OH * p.OW;
+  const int tiles = ((p.pC + 63) / 64) * ((p.qC + 63) / 64) * p.ntaps;
+  int splits = (sm_count() * 4 + tiles - 1) / tiles;
+  const long long max_splits = (M + 255) / 256;  // at least 256 pixels per split
+  if (splits > max_splits) splits = (int)max_splits;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  dim3 grid((p.pC + 63) / 64, (p.qC + 63) / 64, p.ntaps * splits);
+  if (act_f32) conv_wgrad_kernel<float><<<grid, 256, 0, stream>>>(p);
+  else         conv_wgrad_kernel<bf16><<<grid, 256, 0, stream>>>(p);
+  return check_launch("conv_wgrad_kernel");
+}
+
+static int pad_before(int in, int out, int k, int s) {
+  int total = (out - 1) * s + k - in;
+  if (total < 0) total = 0;
+  return total / 2;  // TF SAME: the odd pixel goes after
+}
+
+static int validate(const db200_conv_desc* c, const char* who) {
+  DB200_REQUIRE(c != nullptr, DB200_E_INVALID, "%s: NULL descriptor", who);
+  DB200_REQUIRE(c->N > 0 && c->H > 0 && c->W > 0 && c->Cin > 0 && c->Cout > 0 && c->Ho > 0 && c->Wo > 0,
+                DB200_E_INVALID, "%s: non-positive dimension", who);
+  DB200_REQUIRE(c->KH > 0 && c->KW > 0 && c->KH * c->KW <= MAX_TAPS, DB200_E_UNSUPPORTED,
+                "%s: kernel %dx%d has more than %d taps", who, c->KH, c->KW, MAX_TAPS);
+  DB200_REQUIRE(c->stride == 1 || c->stride == 2, DB200_E_UNSUPPORTED, "%s: stride %d not in {1,2}", who, c->stride);
+  if (c->transposed) {
+    DB200_REQUIRE(c->KH == 4 && c->KW == 4 && c->stride == 2 && c->Ho == 2 * c->H && c->Wo == 2 * c->W,
+                  DB200_E_UNSUPPORTED, "%s: conv2d_transpose is implemented for k=4, s=2, SAME only", who);
+  } else {
+    DB200_REQUIRE(c->Ho == (c->H + c->stride - 1) / c->stride && c->Wo == (c->W + c->stride - 1) / c->stride,
+                  DB200_E_INVALID, "%s: Ho/Wo do not match SAME padding", who);
+  }
+  return DB200_OK;
+}
+
+}  // namespace db200
+
+using namespace db200;
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int db200_conv2d_fwd(db200_stream_t stream_, const db200_conv_desc* c, const void* x, const float* w,
+                                const float* bias, const void* residual, void* y) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = validate(c, "conv2d_fwd");
+  if (rc != DB200_OK) return rc;
+  DB200_REQUIRE(x && w && y, DB200_E_INVALID, "conv2d_fwd: NULL pointer");
+  ConvGemmParams p{};
+  p.x = x; p.w = w; p.bias = bias; p.residual = residual; p.mask = nullptr; p.y = y;
+  p.relu = c->relu;
+  p.K = c->Cin; p.Nn = c->Cout;
+  p.in_H = c->H; p.in_W = c->W;
+  p.out_H = c->Ho; p.out_W = c->Wo;
+  if (!c->transposed) {
+    // y[oy,ox] = sum_{kh,kw} x[oy*s + kh - pt, ox*s + kw - pl] * w[kh][kw][ci][co]
+    const int pt = pad_before(c->H, c->Ho, c->KH, c->stride), pl = pad_before(c->W, c->Wo, c->KW, c->stride);
+    p.NB = c->N; p.OH = c->Ho; p.OW = c->Wo;
+    p.out_stride = 1; p.oa = 0; p.ob = 0; p.in_stride = c->stride;
+    p.ntaps = c->KH * c->KW;
+    for (int kh = 0; kh < c->KH; ++kh)
+      for (int kw = 0; kw < c->KW; ++kw) {
+        Tap& t = p.taps[kh * c->KW + kw];
+        t.dy = kh - pt; t.dx = kw - pl;
+        t.w_off = (long long)(kh * c->KW + kw) * c->Cin * c->Cout;
+      }
+    p.w_k_stride = c->Cout; p.w_n_stride = 1;
+    return launch_gemm(stream, p, c->act_f32 != 0);
+  }
+  // conv2d_transpose(k=4,s=2,SAME), kernel [kh][kw][cout][cin]:  y[2i-1+kh, 2j-1+kw, co] += x[i,j,ci] * w[kh][kw][co][ci]
+  // one launch per output parity (a,b); each uses the 2x2 taps that land on that parity.
+  p.NB = c->N; p.OH = c->H; p.OW = c->W;
+  p.out_stride = 2; p.in_stride = 1;
+  p.w_k_stride = 1; p.w_n_stride = c->Cin;
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      p.oa = a; p.ob = b; p.ntaps = 0;
+      for (int kh = 0; kh < 4; ++kh) {
+        if (((a + 1 - kh) & 1) != 0) continue;
+        for (int kw = 0; kw < 4; ++kw) {
+          if (((b + 1 - kw) & 1) != 0) continue;
+          Tap& t = p.taps[p.ntaps++];
+          t.dy = (a + 1 - kh) / 2; t.dx = (b + 1 - kw) / 2;  // exact: the numerators are even
+          t.w_off = (long long)(kh * 4 + kw) * c->Cout * c->Cin;
+        }
+      }
+      rc = launch_gemm(stream, p, c->act_f32 != 0);
+      if (rc != DB200_OK) return rc;
+    }
+  return DB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dgrad: dx = d(loss)/d(x) given dy; optional ReLU mask (dx *= x_mask > 0) and residual-gradient add
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int db200_conv2d_dgrad(db200_stream_t stream_, const db200_conv_desc* c, const void* dy, const float* w,
+                                  const void* x_mask, const void* dres, void* dx) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = validate(c, "conv2d_dgrad");
+  if (rc != DB200_OK) return rc;
+  DB200_REQUIRE(dy && w && dx, DB200_E_INVALID, "conv2d_dgrad: NULL pointer");
+  ConvGemmParams p{};
+  p.x = dy; p.w = w; p.bias = nullptr; p.residual = dres; p.mask = x_mask; p.y = dx; p.relu = 0;
+  p.K = c->Cout; p.Nn = c->Cin;
+  p.in_H = c->Ho; p.in_W = c->Wo;   // the tensor being gathered is dy
+  p.out_H = c->H; p.out_W = c->W;   // the tensor being produced is dx
+  if (!c->transposed) {
+    const int pt = pad_before(c->H, c->Ho, c->KH, c->stride), pl = pad_before(c->W, c->Wo, c->KW, c->stride);
+    // forward: iy = oy*s + kh - pt  =>  dx[iy] += dy[oy] * w[kh][kw][ci][co]
+    p.w_k_stride = 1; p.w_n_stride = c->Cout;  // B(k = co, n = ci) = w[tap][ci][co]
+    if (c->stride == 1) {
+      p.NB = c->N; p.OH = c->H; p.OW = c->W;
+      p.out_stride = 1; p.oa = 0; p.ob = 0; p.in_stride = 1;
+      p.ntaps = c->KH * c->KW;
+      for (int kh = 0; kh < c->KH; ++kh)
+        for (int kw = 0; kw < c->KW; ++kw) {
+          Tap& t = p.taps[kh * c->KW + kw];
+          t.dy = pt - kh; t.dx = pl - kw;  // oy = iy + pt - kh
+          t.w_off = (long long)(kh * c->KW + kw) * c->Cin * c->Cout;
+        }
+      return launch_gemm(stream, p, c->act_f32 != 0);
+    }
+    // stride 2: input pixel iy = 2*i + a receives from taps with (a + pt - kh) even; oy = i + (a + pt - kh)/2
+    DB200_REQUIRE(c->H % 2 == 0 && c->W % 2 == 0, DB200_E_UNSUPPORTED, "conv2d_dgrad: stride 2 needs even H, W");
+    p.NB = c->N; p.OH = c->H / 2; p.OW = c->W / 2;
+    p.out_stride = 2; p.in_stride = 1;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        p.oa = a; p.ob = b; p.ntaps = 0;
+        for (int kh = 0; kh < c->KH; ++kh) {
+          if (((a + pt - kh) & 1) != 0) continue;
+          for (int kw = 0; kw < c->KW; ++kw) {
+            if (((b + pl - kw) & 1) != 0) continue;
+            DB200_REQUIRE(p.ntaps < MAX_TAPS, DB200_E_UNSUPPORTED, "conv2d_dgrad: too many taps");
+            Tap& t = p.taps[p.ntaps++];
+            // floor division of a possibly negative even number
+            t.dy = (a + pt - kh) / 2; t.dx = (b + pl - kw) / 2;
+            t.w_off = (long long)(kh * c->KW + kw) * c->Cin * c->Cout;
+          }
+        }
+        rc = launch_gemm(stream, p, c->act_f32 != 0);
+        if (rc != DB200_OK) return rc;
+      }
+    return DB200_OK;
+  }
+  // transposed forward y[2i-1+kh] += x[i]*w[kh][kw][co][ci]  =>  dx[i,ci] = sum dy[2i-1+kh, 2j-1+kw, co] * w[..][co][ci]
+  p.NB = c->N; p.OH = c->H; p.OW = c->W;
+  p.out_stride = 1; p.oa = 0; p.ob = 0; p.in_stride = 2;
+  p.ntaps = 16;
+  for (int kh = 0; kh < 4; ++kh)
+    for (int kw = 0; kw < 4; ++kw) {
+      Tap& t = p.taps[kh * 4 + kw];
+      t.dy = kh - 1; t.dx = kw - 1;
+      t.w_off = (long long)(kh * 4 + kw) * c->Cout * c->Cin;
+    }
+  p.w_k_stride = c->Cin; p.w_n_stride = 1;  // B(k = co, n = ci) = w[tap][co][ci]
+  return launch_gemm(stream, p, c->act_f32 != 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad (+ bias grad): accumulate into dw / dbias
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int db200_conv2d_wgrad(db200_stream_t stream_, const db200_conv_desc* c, const void* x, const void* dy,
+                                  float* dw, float* dbias) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int rc = validate(c, "conv2d_wgrad");
+  if (rc != DB200_OK) return rc;
+  DB200_REQUIRE(x && dy && dw, DB200_E_INVALID, "conv2d_wgrad: NULL pointer");
+  ConvWgradParams p{};
+  p.P = x; p.Q = dy; p.dw = dw;
+  p.pH = c->H; p.pW = c->W; p.pC = c->Cin;
+  p.qH = c->Ho; p.qW = c->Wo; p.qC = c->Cout;
+  p.ntaps = c->KH * c->KW;
+  if (!c->transposed) {
+    const int pt = pad_before(c->H, c->Ho, c->KH, c->stride), pl = pad_before(c->W, c->Wo, c->KW, c->stride);
+    p.NB = c->N; p.OH = c->Ho; p.OW = c->Wo;  // contract over output pixels
+    p.p_stride = c->stride; p.q_stride = 1;
+    for (int kh = 0; kh < c->KH; ++kh)
+      for (int kw = 0; kw < c->KW; ++kw) {
+        WgradTap& t = p.taps[kh * c->KW + kw];
+        t.pdy = kh - pt; t.pdx = kw - pl; t.qdy = 0; t.qdx = 0;
+        t.w_off = (long long)(kh * c->KW + kw) * c->Cin * c->Cout;
+      }
+    p.a_stride = c->Cout; p.b_stride = 1;  // dw[tap][ci][co]
+  } else {
+    p.NB = c->N; p.OH = c->H; p.OW = c->W;  // contract over input (low-res) pixels
+    p.p_stride = 1; p.q_stride = 2;
+    for (int kh = 0; kh < 4; ++kh)
+      for (int kw = 0; kw < 4; ++kw) {
+        WgradTap& t = p.taps[kh * 4 + kw];
+        t.pdy = 0; t.pdx = 0; t.qdy = kh - 1; t.qdx = kw - 1;
+        t.w_off = (long long)(kh * 4 + kw) * c->Cout * c->Cin;
+      }
+    p.a_stride = 1; p.b_stride = c->Cin;  // dw[tap][co][ci]
+  }
+  rc = launch_wgrad(stream, p, c->act_f32 != 0);
+  if (rc != DB200_OK) return rc;
+  if (dbias) {
+    const long long rows = (long long)c->N * c->Ho * c->Wo;
+    dim3 grid((c->Cout + 31) / 32, (unsigned)((rows + 255) / 256 < 512 ? (rows + 255) / 256 : 512));
+    if (c->act_f32) colsum_act_kernel<float><<<grid, 256, 0, stream>>>((const float*)dy, rows, c->Cout, dbias);
+    else            colsum_act_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)dy, rows, c->Cout, dbias);
+    return check_launch("colsum_act_kernel");
+  }
+  return DB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small fp32 matmuls (codebook): the same kernels with a 1x1 geometry
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int db200_rowmatmul_f32(db200_stream_t stream_, const float* a, const float* b, float* out, int rows, int K,
+                                   int N, int b_transposed, int accumulate) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(a && b && out && rows > 0 && K > 0 && N > 0, DB200_E_INVALID, "rowmatmul: bad arguments");
+  ConvGemmParams p{};
+  p.NB = rows; p.OH = 1; p.OW = 1; p.out_H = 1; p.out_W = 1; p.out_stride = 1; p.in_H = 1; p.in_W = 1; p.in_stride = 1;
+  p.K = K; p.Nn = N; p.ntaps = 1;
+  p.taps[0].dy = 0; p.taps[0].dx = 0; p.taps[0].w_off = 0;
+  if (b_transposed) { p.w_k_stride = 1; p.w_n_stride = K; }  // b stored [N][K]
+  else              { p.w_k_stride = N; p.w_n_stride = 1; }  // b stored [K][N]
+  p.x = a; p.w = b; p.y = out;
+  p.residual = accumulate ? out : nullptr;
+  return launch_gemm(stream, p, true);
+}
+
+extern "C" int db200_rowmatmul_tn_f32(db200_stream_t stream_, const float* a, const float* b, float* out_accum,
+                                      int rows, int M, int N) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(a && b && out_accum && rows > 0 && M > 0 && N > 0, DB200_E_INVALID, "rowmatmul_tn: bad arguments");
+  ConvWgradParams p{};
+  p.NB = rows; p.OH = 1; p.OW = 1;
+  p.pH = 1; p.pW = 1; p.pC = M; p.p_stride = 1;
+  p.qH = 1; p.qW = 1; p.qC = N; p.q_stride = 1;
+  p.ntaps = 1;
+  p.taps[0] = WgradTap{0, 0, 0, 0, 0};
+  p.a_stride = N; p.b_stride = 1;
+  p.P = a; p.Q = b; p.dw = out_accum;
+  return launch_wgrad(stream, p, true);
+}

@@ -35,7 +35,7 @@ class GemmEpilogue(ctypes.Structure):
 class ConvDesc(ctypes.Structure):
     """Mirror of ``struct db200_conv_desc``."""
     _fields_ = [(n, ctypes.c_int32) for n in
-                ("N", "H", "W", "Cin", "Ho", "Wo", "Cout", "KH", "KW", "stride", "transposed", "act_f32", "relu_in",
+                ("N", "H", "W", "Cin", "Ho", "Wo", "Cout", "KH", "KW", "stride", "transposed", "act_f32", "relu",
                  "reserved")]
 
 

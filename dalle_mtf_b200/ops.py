@@ -207,7 +207,7 @@ def adam_step(p, m, v, g, p_bf16, lr, beta1=0.9, beta2=0.999, eps=1e-6, weight_d
 
 
 # ----------------------------------------------------------------------------------------------- VAE ops
-def conv_desc(N, H, W, Cin, Cout, KH, KW, stride, transposed=False, act_f32=True, relu_in=False):
+def conv_desc(N, H, W, Cin, Cout, KH, KW, stride, transposed=False, act_f32=True, relu=False):
     c = ConvDesc()
     c.N, c.H, c.W, c.Cin, c.Cout = N, H, W, Cin, Cout
     c.KH, c.KW, c.stride = KH, KW, stride
@@ -217,7 +217,7 @@ def conv_desc(N, H, W, Cin, Cout, KH, KW, stride, transposed=False, act_f32=True
         c.Ho, c.Wo = (H + stride - 1) // stride, (W + stride - 1) // stride
     c.transposed = int(transposed)
     c.act_f32 = int(act_f32)
-    c.relu_in = int(relu_in)
+    c.relu = int(relu)
     return c
 
 

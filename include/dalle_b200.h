@@ -150,7 +150,7 @@ int db200_adam_step(db200_stream_t stream, float* p, float* m, float* v, const f
 /* ------------------------------------------------------------------------------------------------------------------
  * K11  discrete-VAE convolutions, NHWC activations / HWIO kernels like tf.layers.conv2d
  *     (src/vae_tf/models.py:95-109, 139-155).  Shared-memory-staged direct convolutions (no im2col buffer).
- *     conv2d:            y = conv(x, w[kh][kw][cin][cout], stride, SAME) + bias  [relu_in: relu applied to x on load]
+ *     conv2d:            y = conv(x, w[kh][kw][cin][cout], stride, SAME) + bias  [relu: ReLU on the output]
  *                        [+ residual]                                     x: [N][H][W][Cin]  y: [N][Ho][Wo][Cout]
  *     conv2d_transpose:  tf.layers.conv2d_transpose(k=4, s=2, SAME), kernel [kh][kw][cout][cin]
  *     *_dgrad / *_wgrad: gradients w.r.t. input / kernel+bias (dw, dbias accumulate in f32).
@@ -162,7 +162,7 @@ typedef struct db200_conv_desc {
   int32_t KH, KW, stride; /* SAME padding: pad_top = max((Ho-1)*stride + KH - H, 0) / 2 */
   int32_t transposed;     /* 1 -> conv2d_transpose geometry (x is the low-res tensor [N][H][W][Cin]) */
   int32_t act_f32;        /* 1 -> activations are float, 0 -> bf16 */
-  int32_t relu_in;        /* apply relu to x while loading (fuses the residual block's activation) */
+  int32_t relu;           /* fwd: apply ReLU to the output (fuses the residual block's activation, models.py:102) */
   int32_t reserved;
 } db200_conv_desc;
 
