@@ -1,0 +1,323 @@
+"""Discrete-VAE engine (host side) on the sm_100a kernels: encoder / Gumbel-softmax quantiser / decoder, forward and
+backward as explicit kernel sequences, flat fp32 parameter / gradient / Adam buffers.
+
+Mirrors src/vae_tf/models.py:46-184 (DiscreteVAE), src/vae_tf/layers.py:4-25 and the optimiser wiring of
+src/model_fns_tf.py:40-66.  Parameter names are the reference's TF variable names under scope ``vae/``
+(SURVEY.md Appendix B): kernels HWIO, transposed-conv kernels [kh,kw,out,in], codebook [n_hid, K].
+Activations are NHWC, fp32 or bf16 (use_bf16, src/model_fns_tf.py:48-53); the codebook matmuls, Gumbel-softmax and
+the loss are always fp32 (src/vae_tf/models.py:115-116,157-158).
+"""
+import math
+
+import torch
+
+from . import lib as L
+from . import ops
+from .dalle_engine import ParamLayout
+
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+
+
+class VaeEngine:
+    def __init__(self, num_tokens, image_size, convblocks, input_channels=3, use_bf16=False, recompute_grad=False,
+                 stack_factor=1, device="cuda"):
+        L.require_device()
+        assert math.log2(stack_factor).is_integer()                      # src/vae_tf/models.py:78
+        if stack_factor != 1:
+            raise L.DB200Error("stack_factor > 1 (space_to_depth) is not wired in the B200 engine yet")
+        self.K = int(num_tokens)
+        self.H = self.W = int(image_size)
+        self.convblocks = [(int(s), int(c)) for s, c in convblocks]
+        self.C = int(input_channels)
+        self.use_bf16 = bool(use_bf16)
+        self.recompute_grad = bool(recompute_grad)  # accepted; activations are simply kept (they fit in 180 GB)
+        self.device = torch.device(device)
+        self.act = BF16 if self.use_bf16 else F32
+        if self.H % (2 ** len(self.convblocks)) != 0:
+            raise L.DB200Error("image_size must be divisible by 2**len(convblocks)")
+        self.n_hid = self.convblocks[-1][1]
+        self.hw = self.H // (2 ** len(self.convblocks))
+        self.image_seq_len = self.hw * self.hw                           # src/model_fns.py:68
+
+        lay = ParamLayout()
+        # ---- network description: list of layers with geometry
+        self.enc, self.dec = [], []
+        cin, res = self.C, self.H
+        for b, (stack, ch) in enumerate(self.convblocks):
+            for i in range(stack):
+                pre = f"encoder/block_{b}/layer_{i}/"
+                if i == 0:
+                    lay.add(pre + "conv_downsample/kernel", (4, 4, cin, ch)); lay.add(pre + "conv_downsample/bias", (ch,))
+                    self.enc.append(("down", pre + "conv_downsample", cin, ch, res))
+                    res //= 2
+                else:
+                    for nm in ("conv_in", "conv_out"):
+                        lay.add(pre + nm + "/kernel", (3, 3, ch, ch)); lay.add(pre + nm + "/bias", (ch,))
+                    self.enc.append(("res", pre, ch, ch, res))
+            cin = ch
+        lay.add("codebook/codebook", (self.n_hid, self.K))
+        for b, (stack, ch) in enumerate(reversed(self.convblocks)):
+            for i in range(stack):
+                pre = f"decoder/block_{b}/layer_{i}/"
+                if i == 0:
+                    lay.add(pre + "conv_upsample/kernel", (4, 4, ch, cin)); lay.add(pre + "conv_upsample/bias", (ch,))
+                    self.dec.append(("up", pre + "conv_upsample", cin, ch, res))
+                    res *= 2
+                else:
+                    for nm in ("conv_in", "conv_out"):
+                        lay.add(pre + nm + "/kernel", (3, 3, ch, ch)); lay.add(pre + nm + "/bias", (ch,))
+                    self.dec.append(("res", pre, ch, ch, res))
+            cin = ch
+        lay.add("decoder/conv2d/kernel", (1, 1, cin, self.C)); lay.add("decoder/conv2d/bias", (self.C,))
+        self.dec_out_cin = cin
+        self.layout = lay
+        n = lay.size + 64
+        self.n_params_padded = lay.size
+        self.aux_off = lay.size
+        dev = self.device
+        self.master = torch.zeros(n, dtype=F32, device=dev)
+        self.grads = torch.zeros(n, dtype=F32, device=dev)
+        self.adam_m = torch.zeros(n, dtype=F32, device=dev)
+        self.adam_v = torch.zeros(n, dtype=F32, device=dev)
+        self._B = None
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def P(self, name):
+        return self.layout.view(self.master, name)
+
+    def G(self, name):
+        return self.layout.view(self.grads, name)
+
+    def n_params(self):
+        return sum(math.prod(shape) for _, shape in self.layout.entries.values())
+
+    def load_params(self, named):
+        self.master.zero_()
+        for name in self.layout.order:
+            dst = self.P(name)
+            t = named[name].to(device=self.device, dtype=F32)
+            if tuple(t.shape) != tuple(dst.shape):
+                raise L.DB200Error(f"load_params: {name}: expected {tuple(dst.shape)}, got {tuple(t.shape)}")
+            dst.copy_(t)
+
+    def export_params(self, source=None):
+        flat = self.master if source is None else source
+        return {n: self.layout.view(flat, n).detach().float().cpu().clone() for n in self.layout.order}
+
+    def init_params(self, seed=0):
+        """glorot_uniform kernels / zero biases (tf.layers defaults ‡), drawn on the device."""
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        self.master.zero_()
+        for name in self.layout.order:
+            _, shape = self.layout.entries[name]
+            if name.endswith("/bias"):
+                continue
+            if len(shape) == 4:
+                rf = shape[0] * shape[1]
+                fan_in, fan_out = rf * shape[2], rf * shape[3]
+            else:
+                fan_in, fan_out = shape
+            limit = math.sqrt(6.0 / (fan_in + fan_out))
+            self.P(name).copy_((torch.rand(shape, generator=g, device=self.device) * 2 - 1) * limit)
+
+    # ------------------------------------------------------------------------------------------ buffers
+    def _alloc(self, B):
+        if self._B == B:
+            return
+        dev, act = self.device, self.act
+        e = lambda *shape, dtype=act: torch.empty(*shape, dtype=dtype, device=dev)
+        self._B = B
+        rows = B * self.hw * self.hw
+        b = {"x_in": e(B, self.H, self.W, self.C), "enc": [], "dec": []}
+        for kind, _, cin, ch, res in self.enc:
+            if kind == "down":
+                b["enc"].append({"out": e(B, res // 2, res // 2, ch)})
+            else:
+                b["enc"].append({"t": e(B, res, res, ch), "out": e(B, res, res, ch)})
+        b.update({
+            "enc_f32": e(rows, self.n_hid, dtype=F32), "logits": e(rows, self.K, dtype=F32),
+            "y_soft": e(rows, self.K, dtype=F32), "y_out": e(rows, self.K, dtype=F32), "idx": e(rows, dtype=I32),
+            "z_f32": e(rows, self.n_hid, dtype=F32), "z": e(B, self.hw, self.hw, self.n_hid),
+        })
+        for kind, _, cin, ch, res in self.dec:
+            if kind == "up":
+                b["dec"].append({"out": e(B, res * 2, res * 2, ch)})
+            else:
+                b["dec"].append({"t": e(B, res, res, ch), "out": e(B, res, res, ch)})
+        b.update({
+            "recon_act": e(B, self.H, self.W, self.C), "recon": e(B, self.H, self.W, self.C, dtype=F32),
+            "drecon": e(B, self.H, self.W, self.C, dtype=F32), "drecon_act": e(B, self.H, self.W, self.C),
+            "dy": e(rows, self.K, dtype=F32), "dlogits": e(rows, self.K, dtype=F32),
+            "dz_f32": e(rows, self.n_hid, dtype=F32), "denc_f32": e(rows, self.n_hid, dtype=F32),
+        })
+        # gradient scratch: two buffers per distinct activation shape
+        shapes = {}
+        for lst in (b["enc"], b["dec"]):
+            for d in lst:
+                shapes[tuple(d["out"].shape)] = None
+        shapes[(B, self.hw, self.hw, self.n_hid)] = None
+        b["gscratch"] = {s: [e(*s), e(*s)] for s in shapes}
+        self._b = b
+
+    def _desc(self, B, res, cin, cout, k, stride, transposed=False, relu=False):
+        return ops.conv_desc(B, res, res, cin, cout, k, k, stride, transposed=transposed, act_f32=not self.use_bf16,
+                             relu=relu)
+
+    def _to_act(self, src_f32, dst_act):
+        if self.use_bf16:
+            ops.cast_f32_to_bf16(src_f32, dst_act)
+            return dst_act
+        return src_f32
+
+    def _to_f32(self, src_act, dst_f32):
+        if self.use_bf16:
+            ops.cast_bf16_to_f32(src_act, dst_f32)
+            return dst_f32
+        return src_act
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _res_fwd(self, B, pre, ch, res, x, sv):
+        """x + conv_out(relu(conv_in(x)))   (src/vae_tf/models.py:99-109 / 143-153)."""
+        ops.conv2d_fwd(self._desc(B, res, ch, ch, 3, 1, relu=True), x, self.P(pre + "conv_in/kernel"),
+                       self.P(pre + "conv_in/bias"), None, sv["t"])
+        ops.conv2d_fwd(self._desc(B, res, ch, ch, 3, 1), sv["t"], self.P(pre + "conv_out/kernel"),
+                       self.P(pre + "conv_out/bias"), x, sv["out"])
+        return sv["out"]
+
+    def encode_logits(self, img):
+        """DiscreteVAE.encoder (src/vae_tf/models.py:81-120): img fp32 NHWC [B,H,W,C] -> fp32 logits [B*h*w, K]."""
+        B = img.shape[0]
+        self._alloc(B)
+        b = self._b
+        x = self._to_act(img, b["x_in"])
+        self._x0 = x
+        for (kind, name, cin, ch, res), sv in zip(self.enc, b["enc"]):
+            if kind == "down":
+                ops.conv2d_fwd(self._desc(B, res, cin, ch, 4, 2), x, self.P(name + "/kernel"), self.P(name + "/bias"),
+                               None, sv["out"])
+                x = sv["out"]
+            else:
+                x = self._res_fwd(B, name, ch, res, x, sv)
+        rows = B * self.hw * self.hw
+        xf = self._to_f32(x.view(rows, self.n_hid), b["enc_f32"])
+        self._enc_f32 = xf
+        ops.rowmatmul(xf, self.P("codebook/codebook"), b["logits"], rows, self.n_hid, self.K)
+        return b["logits"]
+
+    def encode_tokens(self, img):
+        """src/model_fns.py:72-77: argmax over the K codes (first maximum), int32 [B, image_seq_len]."""
+        logits = self.encode_logits(img)
+        rows = logits.shape[0]
+        ops.argmax_rows(logits, self._b["idx"], rows, self.K)
+        return self._b["idx"].view(img.shape[0], self.image_seq_len)
+
+    def forward(self, img, u, temperature=1.0, hard=True, loss_accum=None):
+        """DiscreteVAE.forward(return_recon_loss=True) (src/vae_tf/models.py:165-184).  u: fp32 uniform noise
+        [B*h*w, K] in [1e-9, 1) or None (no noise).  Adds sum((img-out)^2)/numel into loss_accum; returns recon."""
+        B = img.shape[0]
+        logits = self.encode_logits(img)
+        b = self._b
+        rows = B * self.hw * self.hw
+        self._tau = float(temperature)
+        ops.gumbel_softmax_fwd(logits, u, b["y_soft"], b["y_out"], b["idx"], rows, self.K, self._tau, hard)
+        ops.rowmatmul(b["y_out"], self.P("codebook/codebook"), b["z_f32"], rows, self.K, self.n_hid,
+                      b_transposed=True)                                                     # models.py:127
+        x = self._to_act(b["z_f32"], b["z"].view(rows, self.n_hid)).view(B, self.hw, self.hw, self.n_hid)
+        self._z = x
+        for (kind, name, cin, ch, res), sv in zip(self.dec, b["dec"]):
+            if kind == "up":
+                ops.conv2d_fwd(self._desc(B, res, cin, ch, 4, 2, transposed=True), x, self.P(name + "/kernel"),
+                               self.P(name + "/bias"), None, sv["out"])
+                x = sv["out"]
+            else:
+                x = self._res_fwd(B, name, ch, res, x, sv)
+        self._dec_last = x
+        ops.conv2d_fwd(self._desc(B, self.H, self.dec_out_cin, self.C, 1, 1), x, self.P("decoder/conv2d/kernel"),
+                       self.P("decoder/conv2d/bias"), None, b["recon_act"])                   # models.py:155
+        recon = self._to_f32(b["recon_act"], b["recon"])
+        self._img = img
+        if loss_accum is None:
+            loss_accum = self.grads[self.aux_off:self.aux_off + 1]
+        n = img.numel()
+        self._loss_scale = 1.0 / n
+        ops.mse_fwd_bwd(recon, img, b["drecon"], loss_accum, 1.0 / n)                          # layers.py:24-25
+        return recon
+
+    # ------------------------------------------------------------------------------------------ backward
+    def _res_bwd(self, B, pre, ch, res, x_in, sv, dx, scratch):
+        """Backward of x_out = x_in + conv_out(t), t = relu(conv_in(x_in)); dx is overwritten with d(x_in)."""
+        d_out = self._desc(B, res, ch, ch, 3, 1)
+        ops.conv2d_wgrad(d_out, sv["t"], dx, self.G(pre + "conv_out/kernel"), self.G(pre + "conv_out/bias"))
+        dt = scratch
+        ops.conv2d_dgrad(d_out, dx, self.P(pre + "conv_out/kernel"), sv["t"], None, dt)      # masked by t > 0
+        ops.conv2d_wgrad(d_out, x_in, dt, self.G(pre + "conv_in/kernel"), self.G(pre + "conv_in/bias"))
+        # d(x_in) = dgrad(conv_in)(dt) + dx: read dx as the residual and write the result over dt's partner
+        ops.conv2d_dgrad(d_out, dt, self.P(pre + "conv_in/kernel"), None, dx, dx)
+        return dx
+
+    def backward(self, grad_scale=1.0):
+        """Back-propagates d(loss) * grad_scale; gradients ACCUMULATE into self.grads."""
+        b = self._b
+        B = self._img.shape[0]
+        rows = B * self.hw * self.hw
+        if grad_scale != 1.0:
+            raise L.DB200Error("VaeEngine.backward: fold grad_scale into the Adam step (grad_scale argument there)")
+        dx = self._to_act(b["drecon"], b["drecon_act"])
+        d1 = self._desc(B, self.H, self.dec_out_cin, self.C, 1, 1)
+        ops.conv2d_wgrad(d1, self._dec_last, dx, self.G("decoder/conv2d/kernel"), self.G("decoder/conv2d/bias"))
+        gs = b["gscratch"][tuple(self._dec_last.shape)]
+        ops.conv2d_dgrad(d1, dx, self.P("decoder/conv2d/kernel"), None, None, gs[0])
+        dx = gs[0]
+        # decoder, reversed
+        inputs = [self._z] + [sv["out"] for sv in b["dec"][:-1]]
+        for (kind, name, cin, ch, res), sv, x_in in reversed(list(zip(self.dec, b["dec"], inputs))):
+            if kind == "up":
+                dsc = self._desc(B, res, cin, ch, 4, 2, transposed=True)
+                ops.conv2d_wgrad(dsc, x_in, dx, self.G(name + "/kernel"), self.G(name + "/bias"))
+                nxt = b["gscratch"][tuple(x_in.shape)][0]
+                ops.conv2d_dgrad(dsc, dx, self.P(name + "/kernel"), None, None, nxt)
+                dx = nxt
+            else:
+                pair = b["gscratch"][tuple(x_in.shape)]
+                scratch = pair[1] if dx is pair[0] else pair[0]
+                dx = self._res_bwd(B, name, ch, res, x_in, sv, dx, scratch)
+        # quantiser
+        dz = self._to_f32(dx.view(rows, self.n_hid), b["dz_f32"])
+        cb = self.P("codebook/codebook")
+        ops.rowmatmul_tn(dz, b["y_out"], self.G("codebook/codebook"), rows, self.n_hid, self.K)   # d codebook (decode)
+        ops.rowmatmul(dz, cb, b["dy"], rows, self.n_hid, self.K)                                  # dy = dz @ C
+        ops.gumbel_softmax_bwd(b["y_soft"], b["dy"], b["dlogits"], rows, self.K, self._tau)       # straight-through
+        ops.rowmatmul_tn(self._enc_f32, b["dlogits"], self.G("codebook/codebook"), rows, self.n_hid, self.K)
+        ops.rowmatmul(b["dlogits"], cb, b["denc_f32"], rows, self.K, self.n_hid, b_transposed=True)
+        pair = b["gscratch"][(B, self.hw, self.hw, self.n_hid)]
+        dx = self._to_act(b["denc_f32"], pair[0].view(rows, self.n_hid)).view(B, self.hw, self.hw, self.n_hid)
+        if not self.use_bf16:
+            dx = b["denc_f32"].view(B, self.hw, self.hw, self.n_hid)
+        # encoder, reversed
+        inputs = [self._x0] + [sv["out"] for sv in b["enc"][:-1]]
+        for li, ((kind, name, cin, ch, res), sv, x_in) in reversed(list(enumerate(zip(self.enc, b["enc"], inputs)))):
+            if kind == "down":
+                dsc = self._desc(B, res, cin, ch, 4, 2)
+                ops.conv2d_wgrad(dsc, x_in, dx, self.G(name + "/kernel"), self.G(name + "/bias"))
+                if li > 0:  # the gradient w.r.t. the image itself is never needed
+                    nxt = b["gscratch"][tuple(x_in.shape)][0]
+                    ops.conv2d_dgrad(dsc, dx, self.P(name + "/kernel"), None, None, nxt)
+                    dx = nxt
+            else:
+                pair = b["gscratch"][tuple(x_in.shape)]
+                if dx is not pair[0] and dx is not pair[1]:  # fp32 path: dx is denc_f32 viewed; move into a pair slot
+                    pair[0].copy_(dx)
+                    dx = pair[0]
+                scratch = pair[1] if dx is pair[0] else pair[0]
+                dx = self._res_bwd(B, name, ch, res, x_in, sv, dx, scratch)
+
+    # ------------------------------------------------------------------------------------------ optimiser
+    def zero_grads(self):
+        self.grads.zero_()
+
+    def optimizer_step(self, lr, step, grad_scale=1.0, beta1=0.9, beta2=0.999, eps=1e-8):
+        """tf.train.AdamOptimizer (bias-corrected, no clipping), src/model_fns_tf.py:58-66.  `step` = t >= 1.
+        grad_scale = 1/world_size turns the all-reduced SUM into CrossShardOptimizer's mean."""
+        n = self.n_params_padded
+        ops.adam_step(self.master[:n], self.adam_m[:n], self.adam_v[:n], self.grads[:n], None, lr, beta1, beta2, eps,
+                      0.0, None, 0.0, grad_scale, True, step)
