@@ -1,0 +1,266 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the DALL-E data-parallel training step (the north-star hot path) on N B200s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3              # N=1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W                # N>1, one rank per GPU over NCCL
+    python bench.py --impl reference ...                         # the CPU restatement of the reference on host cores
+
+Workload (config.workload): configs/dalle_example_b200.json = BASELINE.json configs[1]: n_embd 512, 6 layers, 4 heads,
+sequence 256 text + 1024 image tokens (dataset.image_size 256 through the 3-stage vae_example tokenizer), bf16,
+32 sequences per GPU (weak scaling: global batch = 32 * N).  A "step" = VAE-encode the images to token ids, assemble
+text|image tokens, forward, backward, bucketed gradient all-reduce, clip-by-global-norm + Adam.
+
+One JSON line on rank 0:
+  value        whole-job tokens/s with the step's inputs (images, captions) already resident in HBM
+  e2e          same through the public API (dalle_model_fn's train_op) with PINNED HOST inputs: the H2D copy of
+               the images / captions and a D2H read of the loss are inside the timed region, every step
+  roofline     the dominant kernel (tcgen05 GEMM, all launches of a step): algorithmic 2*M*N*K FLOPs / CUDA-event
+               time of those launches, against MEASURED_PEAKS.json's sustained bf16 figure
+  cpu_baseline the oracle (CPU port of the reference math, "reference-faithful" variant: one-hot embedding / CE,
+               materialised attention) timed on the box's host cores on a bounded sample of the same workload
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PER_GPU_BATCH = 32
+METRIC = "tokens_per_sec"
+UNIT = "tokens/s"
+
+
+def load_params(n_gpus):
+    from dalle_mtf_b200.utils import fetch_model_params
+    p = fetch_model_params(os.path.join(ROOT, "configs", "dalle_example_b200.json"))
+    p["vae_params"] = fetch_model_params(os.path.join(ROOT, "configs", p["vae_model"] + ".json"))
+    p["train_batch_size"] = PER_GPU_BATCH * n_gpus
+    p["mesh_shape"] = f"data:{n_gpus}"
+    p["vae_random_init"] = True        # no pretrained VAE checkpoint in a throughput run (random-init weights)
+    p["padding_id"] = 50257
+    p["model_path"] = None
+    return p
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_step_rate(steps, warmup, seqs, label):
+    """Times the oracle's reference-faithful fp32 training step (fwd + bwd + clip + Adam) on the host cores.
+    Returns tokens/s.  This is the ONLY place bench.py executes oracle/ (as the CPU baseline, never as product)."""
+    from oracle import dalle as O
+    from oracle import optim as OO
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.DalleConfig(512, 6, 4, 50258, 512, 256, 1024)
+    params = O.init_params(cfg, 0)
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v = {k: torch.zeros_like(v_) for k, v_ in params.items()}
+    g = torch.Generator().manual_seed(1234)
+    hp = {"lr": 1e-3, "train_steps": 100000}
+    times = []
+    for it in range(warmup + steps):
+        tokens = torch.randint(0, cfg.total_tokens - 1, (seqs, cfg.seq_len), generator=g)
+        t0 = time.perf_counter()
+        leaves = {k: p.clone().requires_grad_(True) for k, p in params.items()}
+        loss, _, _ = O.forward(leaves, tokens, cfg, bf16=False, faithful=True)
+        loss.backward()
+        grads = {k: p.grad for k, p in leaves.items()}
+        params, m, v, _, _ = OO.dalle_train_step(params, m, v, grads, 3000 + it, hp)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return seqs * cfg.seq_len / mean, mean * 1e3, cores, f"{label}: {seqs} sequences x 1280 tokens per step, fp32, " \
+        f"fwd+bwd+clip+Adam, reference-faithful graph (one-hot embedding/CE, materialised [S,S] attention)"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    seqs = 2
+    value, ms, cores, sample = cpu_reference_step_rate(args.steps, min(args.warmup, 1), seqs, "bounded sample")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "dalle_example_b200 (n_embd=512 n_layers=6 n_heads=4 seq=256+1024)", "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "mesh-tensorflow/TF 2.4 cannot be installed here (Python 3.12, no network): the oracle port of the "
+                "reference math stands in for the reference's CPU path",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    from dalle_mtf_b200 import lib as L
+    from dalle_mtf_b200 import ops
+    from dalle_mtf_b200.dist import DataParallel
+    from dalle_mtf_b200.input_fns import dalle_input_fn
+    from dalle_mtf_b200.model_fns import TRAIN, dalle_model_fn
+
+    dp = DataParallel().init()
+    if dp.world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={dp.world}: launch with torch.distributed.run")
+    L.require_device()
+    device = torch.device("cuda", torch.cuda.current_device())
+    params = load_params(args.gpus)
+    params["_dp"] = dp
+    it = iter(dalle_input_fn(params))
+    host_batches = [next(it) for _ in range(4)]                 # pinned host memory
+    dev_batches = [(f.to(device), l.to(device)) for f, l in host_batches]   # 4 x 25 MB of images: rotated every step
+    spec = dalle_model_fn(host_batches[0][0], host_batches[0][1], TRAIN, params)
+    spec.global_step = 3000   # past the linear warm-up so the update is not a no-op (lr(0) = 0)
+    tokens_per_step = spec.tokens_per_step
+    sampler = ClockSampler(dp.local_rank)
+
+    def timed(batches, steps, read_loss):
+        dp.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            f, l = batches[i % len(batches)]
+            loss = spec.train_op(f, l)
+            if read_loss:
+                _ = float(loss.item())          # D2H read of the step's result, every step
+        e1.record()
+        torch.cuda.synchronize(); dp.barrier()
+        return dp.max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- device-resident inputs: `value`
+    timed(dev_batches, args.warmup, False)
+    sampler.start()
+    ops.GEMM_PROFILE = []
+    n0 = L.launch_count()
+    ms_total = timed(dev_batches, args.steps, False)
+    launches = L.launch_count() - n0
+    prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
+    clocks = sampler.stop()
+    ms_per_step = ms_total / args.steps
+    value = tokens_per_step * 1000.0 / ms_per_step
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    gemm_flops = sum(f for _, _, f in prof)
+    peak_tf, _, peak_kind = measured_peaks()
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    loss_now = float(spec.loss_sum.item()) * spec.loss_scale
+
+    # ---- host inputs through the public API: `e2e`
+    timed(host_batches, 2, True)
+    ms_e2e = timed(host_batches, args.steps, True) / args.steps
+    f0, l0 = host_batches[0]
+    h2d = f0.numel() * f0.element_size() + l0.numel() * l0.element_size()
+
+    line = None
+    if dp.rank == 0:
+        d, Lyr, S, V = 512, 6, 1280, 50771
+        f_tok = 3 * (Lyr * (24 * d * d + 2 * S * d) + 2 * d * V)     # BASELINE.md §4 training FLOPs per token
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "dalle_example_b200: n_embd=512 n_layers=6 n_heads=4 seq=256+1024 (image_size 256 "
+                                   "-> 3-stage vae_example tokenizer -> 1024 image tokens), V=50771",
+                       "global_batch": PER_GPU_BATCH * args.gpus, "per_gpu_batch": PER_GPU_BATCH, "seq_len": S,
+                       "parallelism": f"dp{args.gpus}", "step": "vae-encode + fwd + bwd + allreduce + clip + adam",
+                       "l2": "inputs rotate over 4 batches; each step streams several GB of activations (>> 126 MB L2)"},
+            "tokens_per_sec_per_gpu": value / args.gpus,
+            "model_flops_fraction": (value / args.gpus) * f_tok / (peak_tf * 1e12),
+            "loss": loss_now,
+            "e2e": {"value": tokens_per_step * 1000.0 / ms_e2e, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "gemm_tc_kernel (tcgen05, all launches of the step)", "bound": "tensor",
+                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                         "peak_kind": f"bf16_tflops_sustained ({peak_kind})", "traffic": None,
+                         "launches_per_step": len(prof) / args.steps, "share_of_step": gemm_ms / ms_total},
+        }
+        if args.gpus == 1 and not args.no_cpu_baseline:
+            v, ms, cores, sample = cpu_reference_step_rate(2, 1, 2, "bounded sample")
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "ms_per_step": ms}
+        print(json.dumps(line), flush=True)
+    dp.barrier()
+    dp.shutdown()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -15,7 +15,10 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
+static unsigned long long g_launches = 0;  // kernels launched through this library (bench.py reports the delta)
+
 int check_launch(const char* what) {
+  __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_error(DB200_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return DB200_OK;
@@ -86,6 +89,7 @@ extern "C" {
 
 const char* db200_last_error(void) { return db200::g_err; }
 int db200_version(void) { return 100; }
+unsigned long long db200_launch_count(void) { return __atomic_load_n(&db200::g_launches, __ATOMIC_RELAXED); }
 
 int db200_device_check(void) {
   int dev = 0;

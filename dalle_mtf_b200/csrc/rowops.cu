@@ -87,6 +87,16 @@ __global__ void shift_labels_kernel(const int* __restrict__ ids, int* __restrict
   labels[i] = (t == S - 1) ? eos : ids[i + 1];
 }
 
+// tokens[b][:] = concat(text[b][:Tt], image_idx[b][:Ti] + offset)       (src/model_fns.py:117-122)
+__global__ void assemble_tokens_kernel(const int* __restrict__ text, const int* __restrict__ img, int* __restrict__ out,
+                                       int B, int Tt, int Ti, int offset) {
+  const int S = Tt + Ti;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * S) return;
+  const int b = i / S, t = i - b * S;
+  out[i] = t < Tt ? text[b * Tt + t] : img[b * Ti + (t - Tt)] + offset;
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm
 // One warp per row; the row lives in registers (NCH 16-byte chunks per lane, d = NCH * 256).
 template <int NCH>
@@ -337,6 +347,18 @@ extern "C" int db200_shift_labels(db200_stream_t stream_, const int32_t* ids, in
   DB200_REQUIRE(B > 0 && S > 0 && ids && labels, DB200_E_INVALID, "shift_labels: bad arguments");
   shift_labels_kernel<<<(B * S + 255) / 256, 256, 0, stream>>>(ids, labels, B, S, eos_id);
   return check_launch("shift_labels_kernel");
+}
+
+extern "C" int db200_assemble_tokens(db200_stream_t stream_, const int32_t* text_ids, const int32_t* image_idx,
+                                     int32_t* tokens, int B, int text_len, int image_len, int image_offset) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(B > 0 && text_len >= 0 && image_len >= 0 && text_len + image_len > 0 && tokens &&
+                    (text_len == 0 || text_ids) && (image_len == 0 || image_idx),
+                DB200_E_INVALID, "assemble_tokens: bad arguments");
+  const int n = B * (text_len + image_len);
+  assemble_tokens_kernel<<<(n + 255) / 256, 256, 0, stream>>>(text_ids, image_idx, tokens, B, text_len, image_len,
+                                                            image_offset);
+  return check_launch("assemble_tokens_kernel");
 }
 
 extern "C" int db200_layernorm_fwd(db200_stream_t stream_, const void* x, const float* g, const float* b, void* y,

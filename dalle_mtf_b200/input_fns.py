@@ -1,0 +1,72 @@
+"""Input contract of src/input_fns.py, served from synthetic data.
+
+The reference's tf.data pipelines (JPEG decode, centre-crop + resize, TFRecord parsing, shuffle/batch/prefetch) are
+host I/O outside the hot path ("next" row N2).  What the step functions rely on is the OUTPUT
+contract, reproduced here exactly:
+  * images: float32 NHWC [B, size, size, n_channels], (uint8 - 127.5) / 127.5               (input_fns.py:15-21)
+  * captions: int32 [B, text_seq_len], truncated / right-padded with params["padding_id"]   (input_fns.py:32-38)
+  * vae_input_fn yields (image, image); dalle_input_fn yields (image, caption)              (input_fns.py:64,41-52)
+Each data-parallel rank generates only ITS shard of the global batch (seed 1234 + rank); the reference instead
+broadcasts the full batch to every core (train_dalle.py:69).
+Batches are produced in pinned host memory so the step's host->device copy is asynchronous.
+"""
+import os
+
+import torch
+
+PADDING_ID = 50257  # <|padding|> appended to the GPT-2 vocabulary (src/data/tokenizer_utils.py:7-14, train_dalle.py:49)
+
+
+def _local_batch(params, eval):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    gb = params["eval_batch_size" if eval else "train_batch_size"]
+    if gb % world != 0:
+        raise ValueError(f"batch size {gb} not divisible by the data-parallel size {world}")
+    return gb // world
+
+
+def _pin(t):
+    return t.pin_memory() if torch.cuda.is_available() else t
+
+
+def synthetic_images(batch, size, channels, generator):
+    """CIFAR-10-shaped stand-in: uint8 uniform[0,255] then the reference normalisation (input_fns.py:20)."""
+    u8 = torch.randint(0, 256, (batch, size, size, channels), generator=generator, dtype=torch.uint8)
+    return (u8.to(torch.float32) - 127.5) / 127.5
+
+
+def synthetic_captions(batch, text_seq_len, padding_id, generator, vocab=50257, min_len=5, max_len=64):
+    """Random-caption stand-in for create_random_dataset (src/data/create_tfrecords.py:59-97) + truncate_or_pad_label."""
+    ids = torch.full((batch, text_seq_len), padding_id, dtype=torch.int32)
+    lens = torch.randint(min_len, max_len + 1, (batch,), generator=generator)
+    for b in range(batch):
+        n = min(int(lens[b]), text_seq_len)
+        ids[b, :n] = torch.randint(0, vocab, (n,), generator=generator, dtype=torch.int32)
+    return ids
+
+
+def vae_input_fn(params, eval=False):
+    """src/input_fns.py:69-104."""
+    rank = int(os.environ.get("RANK", "0"))
+    g = torch.Generator().manual_seed(1234 + rank + (10_000 if eval else 0))
+    B = _local_batch(params, eval)
+    size = params["dataset"]["image_size"]
+    ch = params.get("n_channels") or 3
+    while True:
+        img = _pin(synthetic_images(B, size, ch, g))
+        yield img, img
+
+
+def dalle_input_fn(params, eval=False):
+    """src/input_fns.py:106-120."""
+    rank = int(os.environ.get("RANK", "0"))
+    g = torch.Generator().manual_seed(1234 + rank + (10_000 if eval else 0))
+    B = _local_batch(params, eval)
+    size = params["dataset"]["image_size"]
+    ch = params.get("n_channels") or 3
+    pad = params.get("padding_id")
+    pad = PADDING_ID if pad is None else pad
+    while True:
+        img = _pin(synthetic_images(B, size, ch, g))
+        cap = _pin(synthetic_captions(B, params["text_seq_len"], pad, g, vocab=min(50257, params["text_vocab_size"])))
+        yield img, cap

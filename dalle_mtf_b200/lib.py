@@ -45,6 +45,7 @@ _SIGNATURES = {
     "db200_device_check": [],
     "db200_embed_fwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int],
     "db200_embed_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int],
+    "db200_assemble_tokens": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int],
     "db200_shift_labels": [c_vp, c_vp, c_vp, c_int, c_int, c_int],
     "db200_layernorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32],
     "db200_layernorm_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int],
@@ -70,7 +71,7 @@ _SIGNATURES = {
     "db200_argmax_rows_f32": [c_vp, c_vp, c_vp, c_int, c_int],
     "db200_mse_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_f32],
 }
-EXPORTED_SYMBOLS = ["db200_last_error"] + sorted(_SIGNATURES)
+EXPORTED_SYMBOLS = ["db200_last_error", "db200_launch_count"] + sorted(_SIGNATURES)
 
 _lib = None
 MISSING_SYMBOLS = []
@@ -92,6 +93,8 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.db200_last_error.restype = ctypes.c_char_p
     lib.db200_last_error.argtypes = []
+    lib.db200_launch_count.restype = ctypes.c_ulonglong
+    lib.db200_launch_count.argtypes = []
     for name, argtypes in _SIGNATURES.items():
         try:
             fn = getattr(lib, name)
@@ -122,6 +125,10 @@ def require_device():
         raise DB200Error("CUDA device required: dalle_mtf_b200 has no CPU fallback")
     check(load().db200_device_check(), "db200_device_check")
     _device_ok = True
+
+
+def launch_count():
+    return int(load().db200_launch_count())
 
 
 def stream_ptr():

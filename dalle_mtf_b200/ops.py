@@ -27,6 +27,11 @@ def _chk(t, dtype, name):
 
 
 # ----------------------------------------------------------------------------------------------- GEMM
+# bench.py sets GEMM_PROFILE to a list to time every tcgen05 GEMM launch with CUDA events on the launching stream:
+# entries are (start_event, end_event, algorithmic_flops).
+GEMM_PROFILE = None
+
+
 def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, ldd=None, mode=L.EPI_STORE,
          alpha=1.0, bias=None, relu=False, residual=None, aux=None, split_k=1, labels=None, part_max=None,
          part_sum=None, label_logit=None, lse=None, n_valid=0):
@@ -63,8 +68,15 @@ def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, ldd=
         ldd = ldd if ldd is not None else out.stride(0)
     else:
         ldd = 0
+    prof = GEMM_PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(L.load().db200_gemm_bf16(stream_ptr(), ptr(a), int(a_mn), lda, ptr(b), int(b_mn), ldb, ptr(out), ldd,
                                    M, N, K, ctypes.byref(e)), "db200_gemm_bf16")
+    if prof is not None:
+        ev1.record()
+        prof.append((ev0, ev1, 2.0 * M * N * K))
     return out
 
 
@@ -118,6 +130,16 @@ def embed_bwd(ids, dx, dwte, dwpe):
     B, S = ids.shape
     V, d = dwte.shape
     check(L.load().db200_embed_bwd(stream_ptr(), ptr(ids), ptr(dx), ptr(dwte), ptr(dwpe), B, S, d, V), "embed_bwd")
+
+
+def assemble_tokens(text_ids, image_idx, tokens, image_offset):
+    L.require_device()
+    _chk(text_ids, I32, "text_ids"); _chk(image_idx, I32, "image_idx"); _chk(tokens, I32, "tokens")
+    B, Tt = text_ids.shape
+    Ti = image_idx.shape[1]
+    check(L.load().db200_assemble_tokens(stream_ptr(), ptr(text_ids), ptr(image_idx), ptr(tokens), B, Tt, Ti,
+                                         image_offset), "assemble_tokens")
+    return tokens
 
 
 def shift_labels(ids, labels, eos_id):

@@ -34,6 +34,8 @@ typedef void* db200_stream_t;
 
 const char* db200_last_error(void);
 int db200_version(void);
+/* number of kernels this library has launched in this process (monotonic; used for bench.py's gpu_launches) */
+unsigned long long db200_launch_count(void);
 /* 0 if the current CUDA device is compute capability 10.x (sm_100a cubins can run), else DB200_E_UNSUPPORTED. */
 int db200_device_check(void);
 
@@ -46,6 +48,11 @@ int db200_embed_fwd(db200_stream_t stream, const int32_t* ids, const void* wte_b
                     void* out_bf16, int B, int S, int d, int V);
 int db200_embed_bwd(db200_stream_t stream, const int32_t* ids, const void* dx_bf16, float* dwte, float* dwpe, int B,
                     int S, int d, int V);
+
+/* T0 token assembly: tokens[b] = concat(text_ids[b], image_idx[b] + image_offset).  Replaces tf.concat at
+ * src/model_fns.py:117-122 (image_offset = text_vocab_size). */
+int db200_assemble_tokens(db200_stream_t stream, const int32_t* text_ids, const int32_t* image_idx, int32_t* tokens,
+                          int B, int text_len, int image_len, int image_offset);
 
 /* label shift: labels[b][t] = ids[b][t+1], labels[b][S-1] = eos_id.  Replaces the pad + gather at
  * src/dalle_mtf/models.py:407-410 (pad op: src/dalle_mtf/ops.py:6-68). */

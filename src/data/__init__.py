@@ -1,0 +1,1 @@
+from dalle_mtf_b200.tokenizer import get_tokenizer  # noqa: F401
