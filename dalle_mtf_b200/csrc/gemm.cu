@@ -6,7 +6,8 @@
 //   warp 1   : MMA issuer  (one elected lane, tcgen05.mma cta_group::1, UMMA 128 x BN x 16)
 //   warp 2   : TMEM allocator / deallocator (2 accumulator stages of BN columns -> epilogue overlaps next tile)
 //   warp 3   : idle
-//   warps 4-7: epilogue (tcgen05.ld, one accumulator row per thread) -> bias / ReLU / residual / CE statistics ...
+//   warps 4-11: epilogue (tcgen05.ld; each accumulator row is split between two threads) -> bias / ReLU /
+//               residual / split-K reduction / cross-entropy statistics and gradient
 //
 // Either operand may be K-major or MN-major in global memory; the tensor maps and the UMMA descriptors absorb the
 // difference, so forward (x*W), dgrad (dy*W^T) and wgrad (x^T*dy) are the same kernel.
@@ -20,7 +21,7 @@ namespace db200 {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int GROUP_M = 8;
 constexpr uint32_t SLAB_BYTES = BK * 128;  // one MN-major slab: [BK k-rows][64 bf16] = 8 KiB
 constexpr uint32_t A_BYTES = BM * BK * 2;  // 16 KiB
@@ -53,6 +54,7 @@ struct GemmParams {
   float* label_logit;
   const float* lse;
   int n_valid;
+  int n_parts;  // CE_STATS: partials per row = 2 * n_tiles (one per half tile)
 };
 
 struct TileCoord {
@@ -75,6 +77,225 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
   t.kb0 = split * per;
   t.kb1 = min(p.kb_total, t.kb0 + per);
   return t;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// epilogues.  One thread = one accumulator row x (BN/2) columns, processed in 32-column chunks straight out of TMEM.
+// All tcgen05.ld are executed by the whole warp (they are .sync.aligned); predicates only guard the global accesses.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void load8(const float* p, float* o) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+__device__ __forceinline__ void store8_bf16(bf16* dp, const float* o) {
+  uint4 q;
+  q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
+  q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
+  *reinterpret_cast<uint4*>(dp) = q;
+}
+__device__ __forceinline__ void load8_bf16(const bf16* sp, float* o) {
+  const uint4 rr = *reinterpret_cast<const uint4*>(sp);
+  const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z), r3 = unpack_bf16x2(rr.w);
+  o[0] = r0.x; o[1] = r0.y; o[2] = r1.x; o[3] = r1.y; o[4] = r2.x; o[5] = r2.y; o[6] = r3.x; o[7] = r3.y;
+}
+
+template <int CH>
+__device__ __forceinline__ void epi_store(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase) {
+#pragma unroll 1
+  for (int c = 0; c < CH; ++c) {
+    const int col0 = cbase + c * 32;
+    if (col0 >= p.N) break;  // warp-uniform
+    uint32_t r[32];
+    tmem_ld_x32(t_addr + c * 32, r);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = col0 + g * 8;
+      if (col + 8 > p.N) break;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
+      if (p.bias) {
+        float b[8];
+        load8(p.bias + col, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += b[j];
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+      }
+      if (p.residual) {
+        float rr[8];
+        load8_bf16(p.residual + (long long)row * p.ldr + col, rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += rr[j];
+      }
+      if (p.out_f32) {
+        float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col;
+        *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(dp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      } else {
+        store8_bf16(reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col, o);
+      }
+    }
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void epi_atomic(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase) {
+#pragma unroll 1
+  for (int c = 0; c < CH; ++c) {
+    const int col0 = cbase + c * 32;
+    if (col0 >= p.N) break;
+    uint32_t r[32];
+    tmem_ld_x32(t_addr + c * 32, r);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+    float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
+    if (col0 + 32 <= p.N && (p.ldd & 3) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)  // REDG.E.ADD.F32x4: one vector reduction per 16 bytes
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + j),
+                     "f"(__uint_as_float(r[j]) * p.alpha), "f"(__uint_as_float(r[j + 1]) * p.alpha),
+                     "f"(__uint_as_float(r[j + 2]) * p.alpha), "f"(__uint_as_float(r[j + 3]) * p.alpha)
+                     : "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) atomicAdd(dp + j, __uint_as_float(r[j]) * p.alpha);
+    }
+  }
+}
+
+template <int CH>
+__device__ __forceinline__ void epi_relu_bwd(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase) {
+#pragma unroll 1
+  for (int c = 0; c < CH; ++c) {
+    const int col0 = cbase + c * 32;
+    if (col0 >= p.N) break;
+    uint32_t r[32];
+    tmem_ld_x32(t_addr + c * 32, r);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = col0 + g * 8;
+      if (col + 8 > p.N) break;
+      float am[8], o[8];
+      load8_bf16(p.aux + (long long)row * p.ldaux + col, am);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = am[j] > 0.f ? __uint_as_float(r[g * 8 + j]) * p.alpha : 0.f;
+      store8_bf16(reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col, o);
+    }
+  }
+}
+
+// per (row, half-tile): running max and sum exp of (acc + bias) over the valid vocabulary columns; label logit
+template <int CH>
+__device__ __forceinline__ void epi_ce_stats(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase,
+                                             int part_idx) {
+  float run_max = -INFINITY, run_sum = 0.f;
+  const int label = row_ok ? p.labels[row] : -1;
+#pragma unroll 1
+  for (int c = 0; c < CH; ++c) {
+    const int col0 = cbase + c * 32;
+    if (col0 >= p.N) break;
+    uint32_t r[32];
+    tmem_ld_x32(t_addr + c * 32, r);
+    tmem_ld_wait();
+    if (!row_ok || col0 >= p.n_valid) continue;
+    float v[32];
+    if (col0 + 32 <= p.n_valid) {  // interior chunk (warp-uniform): no per-element masking
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (p.bias) load8(p.bias + col0 + g * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[g * 8 + j] = __uint_as_float(r[g * 8 + j]) + b[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + j;
+        v[j] = col < p.n_valid ? __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + col) : 0.f) : -INFINITY;
+      }
+    }
+    if (label >= col0 && label < col0 + 32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j == label) p.label_logit[row] = v[j];
+    }
+    float cmax = v[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, v[j]);
+    const float new_max = fmaxf(run_max, cmax);  // finite: at least one valid column in this chunk
+    const float m2 = new_max * kLog2e;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      s0 += fast_exp2(fmaf(v[j], kLog2e, -m2));
+      s1 += fast_exp2(fmaf(v[j + 1], kLog2e, -m2));
+    }
+    run_sum = run_sum * fast_exp2((run_max - new_max) * kLog2e) + (s0 + s1);
+    run_max = new_max;
+  }
+  if (row_ok) {
+    p.part_max[(long long)row * p.n_parts + part_idx] = run_max;
+    p.part_sum[(long long)row * p.n_parts + part_idx] = run_sum;
+  }
+}
+
+// dlogits = alpha * (softmax - onehot), zero in the padded vocabulary columns
+template <int CH>
+__device__ __forceinline__ void epi_ce_grad(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase) {
+  const int label = row_ok ? p.labels[row] : -1;
+  const float l2 = row_ok ? p.lse[row] * kLog2e : 0.f;
+#pragma unroll 1
+  for (int c = 0; c < CH; ++c) {
+    const int col0 = cbase + c * 32;
+    if (col0 >= p.N) break;
+    uint32_t r[32];
+    tmem_ld_x32(t_addr + c * 32, r);
+    tmem_ld_wait();
+    if (!row_ok) continue;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int col = col0 + g * 8;
+      if (col + 8 > p.N) break;
+      float o[8];
+      if (col + 8 <= p.n_valid) {
+        float b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (p.bias) load8(p.bias + col, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = fast_exp2(fmaf(__uint_as_float(r[g * 8 + j]) + b[j], kLog2e, -l2)) * p.alpha;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int cc = col + j;
+          o[j] = cc < p.n_valid
+                     ? fast_exp2(fmaf(__uint_as_float(r[g * 8 + j]) + (p.bias ? __ldg(p.bias + cc) : 0.f), kLog2e, -l2)) *
+                           p.alpha
+                     : 0.f;
+        }
+      }
+      if (label >= col && label < col + 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (col + j == label) o[j] -= p.alpha;
+      }
+      store8_bf16(reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col, o);
+    }
+  }
 }
 
 template <int BN>
@@ -110,7 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar + 8 * i, 1);
-      mbar_init(tempty_bar + 8 * i, 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar + 8 * i, 8);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -186,153 +407,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int wq = warp - 4;  // == warp % 4 : TMEM lane quarter this warp may access
+    // ------------------------------------------------------------------ epilogue: 8 warps
+    // warp w may only touch TMEM lanes 32*(w%4)..+31, so warps 4-7 take the left half of the tile's columns and
+    // warps 8-11 the right half: every accumulator row is finished by two threads.
+    const int ew = warp - 4;
+    const int wq = ew & 3;
+    const int half = ew >> 2;
+    constexpr int CH = BN / 64;  // 32-column chunks per half
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
       const int row = t.m_blk * BM + wq * 32 + lane;
-      const int n0 = t.n_blk * BN;
       const bool row_ok = row < p.M;
+      const int cbase = t.n_blk * BN + half * (BN / 2);
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + acc * BN + (uint32_t(wq * 32) << 16);
-
-      float run_max = -INFINITY, run_sum = 0.f;  // CE_STATS
-      int label = -1;
-      float row_lse = 0.f;
-      if ((p.mode == DB200_EPI_CE_STATS || p.mode == DB200_EPI_CE_GRAD) && row_ok) {
-        label = p.labels[row];
-        if (p.mode == DB200_EPI_CE_GRAD) row_lse = p.lse[row];
-      }
-
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = n0 + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_x32(t_addr + c * 32, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-
-        if (p.mode == DB200_EPI_STORE) {
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              if (col + 8 <= p.N) {
-                float o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float x = v[g * 8 + j] * p.alpha;
-                  if (p.bias) x += __ldg(p.bias + col + j);
-                  if (p.relu) x = fmaxf(x, 0.f);
-                  o[j] = x;
-                }
-                if (p.residual) {
-                  const uint4 rr = *reinterpret_cast<const uint4*>(p.residual + (long long)row * p.ldr + col);
-                  const float2 r0 = unpack_bf16x2(rr.x), r1 = unpack_bf16x2(rr.y), r2 = unpack_bf16x2(rr.z),
-                               r3 = unpack_bf16x2(rr.w);
-                  o[0] += r0.x; o[1] += r0.y; o[2] += r1.x; o[3] += r1.y;
-                  o[4] += r2.x; o[5] += r2.y; o[6] += r3.x; o[7] += r3.y;
-                }
-                if (p.out_f32) {
-                  float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col;
-                  *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
-                  *reinterpret_cast<float4*>(dp + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                } else {
-                  bf16* dp = reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col;
-                  uint4 q;
-                  q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
-                  q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
-                  *reinterpret_cast<uint4*>(dp) = q;
-                }
-              }
-            }
-          }
-        } else if (p.mode == DB200_EPI_ATOMIC) {
-          if (row_ok) {
-            float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) atomicAdd(dp + j, v[j] * p.alpha);
-          }
-        } else if (p.mode == DB200_EPI_RELU_BWD) {
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              if (col + 8 <= p.N) {
-                const uint4 aa = *reinterpret_cast<const uint4*>(p.aux + (long long)row * p.ldaux + col);
-                const float2 a0 = unpack_bf16x2(aa.x), a1 = unpack_bf16x2(aa.y), a2 = unpack_bf16x2(aa.z),
-                             a3 = unpack_bf16x2(aa.w);
-                const float am[8] = {a0.x, a0.y, a1.x, a1.y, a2.x, a2.y, a3.x, a3.y};
-                float o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = am[j] > 0.f ? v[g * 8 + j] * p.alpha : 0.f;
-                bf16* dp = reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col;
-                uint4 q;
-                q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
-                q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
-                *reinterpret_cast<uint4*>(dp) = q;
-              }
-            }
-          }
-        } else if (p.mode == DB200_EPI_CE_STATS) {
-          if (row_ok) {
-            float cmax = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = col0 + j;
-              float x = -INFINITY;
-              if (col < p.n_valid) {
-                x = v[j] + (p.bias ? __ldg(p.bias + col) : 0.f);
-                if (col == label) p.label_logit[row] = x;
-              }
-              v[j] = x;
-              cmax = fmaxf(cmax, x);
-            }
-            if (cmax > -INFINITY) {
-              const float new_max = fmaxf(run_max, cmax);
-              float s = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) s += __expf(v[j] - new_max);  // exp(-inf) = 0 for masked columns
-              run_sum = run_sum * __expf(run_max - new_max) + s;          // run_max = -inf -> factor 0
-              run_max = new_max;
-            }
-          }
-        } else {  // DB200_EPI_CE_GRAD
-          if (row_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int col = col0 + g * 8;
-              if (col + 8 <= p.N) {
-                float o[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const int cc = col + j;
-                  float gval = 0.f;
-                  if (cc < p.n_valid) {
-                    const float x = v[g * 8 + j] + (p.bias ? __ldg(p.bias + cc) : 0.f);
-                    gval = (__expf(x - row_lse) - (cc == label ? 1.f : 0.f)) * p.alpha;
-                  }
-                  o[j] = gval;
-                }
-                bf16* dp = reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col;
-                uint4 q;
-                q.x = pack_bf16x2(o[0], o[1]); q.y = pack_bf16x2(o[2], o[3]);
-                q.z = pack_bf16x2(o[4], o[5]); q.w = pack_bf16x2(o[6], o[7]);
-                *reinterpret_cast<uint4*>(dp) = q;
-              }
-            }
-          }
-        }
-      }
-      if (p.mode == DB200_EPI_CE_STATS && row_ok) {
-        p.part_max[(long long)row * p.n_tiles + t.n_blk] = run_max;
-        p.part_sum[(long long)row * p.n_tiles + t.n_blk] = run_sum;
+      const uint32_t t_addr = tmem_base + acc * BN + half * (BN / 2) + (uint32_t(wq * 32) << 16);
+      switch (p.mode) {
+        case DB200_EPI_STORE:    epi_store<CH>(p, t_addr, row, row_ok, cbase); break;
+        case DB200_EPI_ATOMIC:   epi_atomic<CH>(p, t_addr, row, row_ok, cbase); break;
+        case DB200_EPI_RELU_BWD: epi_relu_bwd<CH>(p, t_addr, row, row_ok, cbase); break;
+        case DB200_EPI_CE_STATS: epi_ce_stats<CH>(p, t_addr, row, row_ok, cbase, t.n_blk * 2 + half); break;
+        default:                 epi_ce_grad<CH>(p, t_addr, row, row_ok, cbase); break;
       }
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
@@ -369,7 +465,7 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
 
 using namespace db200;
 
-extern "C" int db200_gemm_ce_tiles(int N) { return (N + 255) / 256; }
+extern "C" int db200_gemm_ce_tiles(int N) { return 2 * ((N + 255) / 256); }
 
 extern "C" int db200_gemm_bf16(db200_stream_t stream_, const void* A, int a_mn_major, int64_t lda, const void* B,
                                int b_mn_major, int64_t ldb, void* D, int64_t ldd, int M, int N, int K,
@@ -395,6 +491,7 @@ extern "C" int db200_gemm_bf16(db200_stream_t stream_, const void* A, int a_mn_m
                   "gemm: vectorised store epilogues need N and ldd to be multiples of 8 (got N=%d ldd=%lld)", N,
                   (long long)ldd);
   }
+  DB200_REQUIRE(aligned16(epi->bias), DB200_E_ALIGN, "gemm: bias must be 16-byte aligned");
   if (mode == DB200_EPI_STORE && epi->residual)
     DB200_REQUIRE(aligned16(epi->residual) && epi->ldr % 8 == 0 && epi->ldr >= N, DB200_E_ALIGN,
                   "gemm: residual must be 16-byte aligned with ldr %% 8 == 0");
@@ -458,6 +555,7 @@ extern "C" int db200_gemm_bf16(db200_stream_t stream_, const void* A, int a_mn_m
     if (N <= 128 || tiles256 * 2 <= sm_count()) bn = 128;
   }
   p.n_tiles = (N + bn - 1) / bn;
+  p.n_parts = 2 * p.n_tiles;
 
   CUtensorMap tmA, tmB;
   int rc;

@@ -65,6 +65,7 @@ def load_vae_model(params, device):
     convblocks = vae_params.get("convblocks") or [(3, 64), (3, 128), (3, 256)]
     vae = VaeEngine(num_tokens=vae_params["num_tokens"], image_size=D, convblocks=convblocks,
                     input_channels=vae_params.get("input_channels") or 3,
+                    use_bf16=bool(vae_params.get("use_bf16")),   # bf16 -> tcgen05 implicit-GEMM convolutions
                     stack_factor=vae_params.get("stack_factor") or 1, device=device)
     ckpt = params.get("vae_checkpoint_path")
     if ckpt is None:

@@ -250,6 +250,20 @@ def conv2d_fwd(c, x, w, bias, residual, y):
     return y
 
 
+def conv2d_fwd_tc(c, x, w_bf16, bias, residual, y):
+    """tcgen05 implicit-GEMM forward (bf16 activations / kernel).  Raises if the shape is not supported."""
+    L.require_device()
+    _chk(x, BF16, "x"); _chk(w_bf16, BF16, "w"); _chk(y, BF16, "y"); _chk(residual, BF16, "residual")
+    check(L.load().db200_conv2d_fwd_tc(stream_ptr(), ctypes.byref(c), ptr(x), ptr(w_bf16), ptr(bias), ptr(residual),
+                                       ptr(y)), "conv2d_fwd_tc")
+    return y
+
+
+def conv_tc_supported(c):
+    return (not c.transposed and not c.act_f32 and c.Cin % 64 == 0 and c.Cout % 8 == 0 and c.KH * c.KW <= 16 and
+            (c.stride == 1 or (c.stride == 2 and c.H % 2 == 0 and c.W % 2 == 0)))
+
+
 def conv2d_dgrad(c, dy, w, x_mask, dres, dx):
     L.require_device()
     check(L.load().db200_conv2d_dgrad(stream_ptr(), ctypes.byref(c), ptr(dy), ptr(w), ptr(x_mask), ptr(dres),

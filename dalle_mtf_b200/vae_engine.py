@@ -79,6 +79,8 @@ class VaeEngine:
         self.grads = torch.zeros(n, dtype=F32, device=dev)
         self.adam_m = torch.zeros(n, dtype=F32, device=dev)
         self.adam_v = torch.zeros(n, dtype=F32, device=dev)
+        # bf16 copy of the kernels for the tensor-core convolutions (use_bf16 only)
+        self.shadow = torch.zeros(n, dtype=BF16, device=dev) if self.use_bf16 else None
         self._B = None
 
     # ------------------------------------------------------------------------------------------ parameters
@@ -91,6 +93,21 @@ class VaeEngine:
     def n_params(self):
         return sum(math.prod(shape) for _, shape in self.layout.entries.values())
 
+    def W16(self, name):
+        return self.layout.view(self.shadow, name)
+
+    def refresh_shadow(self):
+        if self.shadow is not None:
+            ops.cast_f32_to_bf16(self.master[:self.n_params_padded], self.shadow[:self.n_params_padded])
+
+    def _conv_fwd(self, dsc, x, name, residual, y):
+        """One forward convolution: tcgen05 implicit GEMM when the layer qualifies (bf16, Cin % 64 == 0), else the
+        shared-memory-staged direct kernel (first layer with 3 input channels, transposed convs, fp32 mode)."""
+        if self.use_bf16 and ops.conv_tc_supported(dsc):
+            return ops.conv2d_fwd_tc(dsc, x, self.W16(name + "/kernel").view(-1, dsc.Cout), self.P(name + "/bias"),
+                                     residual, y)
+        return ops.conv2d_fwd(dsc, x, self.P(name + "/kernel"), self.P(name + "/bias"), residual, y)
+
     def load_params(self, named):
         self.master.zero_()
         for name in self.layout.order:
@@ -99,6 +116,7 @@ class VaeEngine:
             if tuple(t.shape) != tuple(dst.shape):
                 raise L.DB200Error(f"load_params: {name}: expected {tuple(dst.shape)}, got {tuple(t.shape)}")
             dst.copy_(t)
+        self.refresh_shadow()
 
     def export_params(self, source=None):
         flat = self.master if source is None else source
@@ -119,6 +137,7 @@ class VaeEngine:
                 fan_in, fan_out = shape
             limit = math.sqrt(6.0 / (fan_in + fan_out))
             self.P(name).copy_((torch.rand(shape, generator=g, device=self.device) * 2 - 1) * limit)
+        self.refresh_shadow()
 
     # ------------------------------------------------------------------------------------------ buffers
     def _alloc(self, B):
@@ -178,10 +197,8 @@ class VaeEngine:
     # ------------------------------------------------------------------------------------------ forward
     def _res_fwd(self, B, pre, ch, res, x, sv):
         """x + conv_out(relu(conv_in(x)))   (src/vae_tf/models.py:99-109 / 143-153)."""
-        ops.conv2d_fwd(self._desc(B, res, ch, ch, 3, 1, relu=True), x, self.P(pre + "conv_in/kernel"),
-                       self.P(pre + "conv_in/bias"), None, sv["t"])
-        ops.conv2d_fwd(self._desc(B, res, ch, ch, 3, 1), sv["t"], self.P(pre + "conv_out/kernel"),
-                       self.P(pre + "conv_out/bias"), x, sv["out"])
+        self._conv_fwd(self._desc(B, res, ch, ch, 3, 1, relu=True), x, pre + "conv_in", None, sv["t"])
+        self._conv_fwd(self._desc(B, res, ch, ch, 3, 1), sv["t"], pre + "conv_out", x, sv["out"])
         return sv["out"]
 
     def encode_logits(self, img):
@@ -193,8 +210,7 @@ class VaeEngine:
         self._x0 = x
         for (kind, name, cin, ch, res), sv in zip(self.enc, b["enc"]):
             if kind == "down":
-                ops.conv2d_fwd(self._desc(B, res, cin, ch, 4, 2), x, self.P(name + "/kernel"), self.P(name + "/bias"),
-                               None, sv["out"])
+                self._conv_fwd(self._desc(B, res, cin, ch, 4, 2), x, name, None, sv["out"])
                 x = sv["out"]
             else:
                 x = self._res_fwd(B, name, ch, res, x, sv)
@@ -319,5 +335,6 @@ class VaeEngine:
         """tf.train.AdamOptimizer (bias-corrected, no clipping), src/model_fns_tf.py:58-66.  `step` = t >= 1.
         grad_scale = 1/world_size turns the all-reduced SUM into CrossShardOptimizer's mean."""
         n = self.n_params_padded
-        ops.adam_step(self.master[:n], self.adam_m[:n], self.adam_v[:n], self.grads[:n], None, lr, beta1, beta2, eps,
-                      0.0, None, 0.0, grad_scale, True, step)
+        ops.adam_step(self.master[:n], self.adam_m[:n], self.adam_v[:n], self.grads[:n],
+                      None if self.shadow is None else self.shadow[:n], lr, beta1, beta2, eps, 0.0, None, 0.0,
+                      grad_scale, True, step)

@@ -175,6 +175,11 @@ typedef struct db200_conv_desc {
 
 int db200_conv2d_fwd(db200_stream_t stream, const db200_conv_desc* c, const void* x, const float* w,
                      const float* bias_or_null, const void* residual_or_null, void* y);
+/* Tensor-core forward (tcgen05 implicit GEMM, 4-D TMA boxes per filter tap, no im2col): bf16 NHWC activations,
+ * bf16 HWIO kernel, f32 bias, optional bf16 residual; needs Cin % 64 == 0, Cout % 8 == 0, stride 1 or 2 (even H, W).
+ * Returns DB200_E_UNSUPPORTED otherwise (callers choose the direct kernel explicitly; there is no silent fallback). */
+int db200_conv2d_fwd_tc(db200_stream_t stream, const db200_conv_desc* c, const void* x_bf16, const void* w_bf16,
+                        const float* bias_or_null, const void* residual_bf16_or_null, void* y_bf16);
 int db200_conv2d_dgrad(db200_stream_t stream, const db200_conv_desc* c, const void* dy, const float* w,
                        const void* x_for_relu_mask_or_null, const void* dres_or_null, void* dx);
 int db200_conv2d_wgrad(db200_stream_t stream, const db200_conv_desc* c, const void* x, const void* dy, float* dw,

@@ -64,6 +64,47 @@ def conv_case(N, H, Cin, Cout, k, stride, transposed, seed, bf16=False):
     check(tag + " dbias", dbd, br.grad, 1e-4 if bf16 else 1e-5)
 
 
+def conv_tc_case(N, H, Cin, Cout, k, stride, relu, with_res, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, H, H, Cin, generator=g).to(torch.bfloat16)
+    w = (torch.randn(k, k, Cin, Cout, generator=g) * (1.0 / (k * k * Cin) ** 0.5)).to(torch.bfloat16)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    y = OV.conv2d_same(x.float(), w.float(), bias, stride)
+    if relu:
+        y = torch.relu(y)
+    res = None
+    if with_res:
+        res = torch.randn(y.shape, generator=g).to(torch.bfloat16)
+        y = y + res.float()
+    c = ops.conv_desc(N, H, H, Cin, Cout, k, k, stride, act_f32=False, relu=relu)
+    yd = torch.zeros(y.shape, dtype=torch.bfloat16, device=DEV)
+    ops.conv2d_fwd_tc(c, x.to(DEV), w.to(DEV).view(-1, Cout), bias.to(DEV), None if res is None else res.to(DEV), yd)
+    torch.cuda.synchronize()
+    check(f"conv_tc N={N} H={H} Cin={Cin} Cout={Cout} k={k} s={stride} relu={int(relu)} res={int(with_res)}", yd, y, 1e-2)
+
+
+def tokenizer_case(size, B, seed):
+    """bf16 tensor-core tokenizer vs the fp32 oracle: logits error and token match rate (near-ties may flip)."""
+    cb = [[3, 64], [3, 128], [3, 256]]
+    p = OV.init_params(cb, 512, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    img = (torch.randint(0, 256, (B, size, size, 3), generator=g).float() - 127.5) / 127.5
+    logits = OV.encoder(p, img, cb)
+    tok_ref = logits.argmax(-1).reshape(B, -1)
+    eng = VaeEngine(512, size, cb, use_bf16=True)
+    eng.load_params(p)
+    tok = eng.encode_tokens(img.to(DEV)).cpu().long()
+    torch.cuda.synchronize()
+    check(f"tokenizer(bf16 tc) size={size} B={B} logits", eng._b["logits"], logits.reshape(-1, 512), 3e-2)
+    match = (tok == tok_ref).float().mean().item()
+    top2 = logits.reshape(-1, 512).topk(2, -1).values
+    margin = (top2[:, 0] - top2[:, 1])
+    mism = (tok.flatten() != tok_ref.flatten())
+    print(f"      token match rate vs fp32 oracle: {match:.4f}; median top1-top2 margin all={margin.median():.4f} "
+          f"mismatched={margin[mism].median().item() if mism.any() else float('nan'):.5f}")
+    OKS.append(match > 0.9)
+
+
 def engine_case(convblocks, K, size, B, hard, tau, use_bf16, seed):
     g = torch.Generator().manual_seed(seed)
     p = OV.init_params(convblocks, K, seed=seed)
@@ -118,6 +159,14 @@ def main():
     conv_case(2, 8, 16, 3, 1, 1, False, 6)       # 1x1 output conv
     conv_case(2, 8, 32, 32, 3, 1, False, 7, bf16=True)
     conv_case(2, 8, 32, 16, 4, 2, True, 8, bf16=True)
+    conv_tc_case(2, 16, 64, 64, 3, 1, True, False, 20)
+    conv_tc_case(2, 16, 128, 128, 3, 1, False, True, 21)
+    conv_tc_case(3, 12, 64, 128, 3, 1, False, False, 22)     # ragged: 12 = 8 + 4 (TMA OOB + epilogue bounds)
+    conv_tc_case(2, 16, 64, 128, 4, 2, False, False, 23)     # stride 2 via parity views
+    conv_tc_case(5, 8, 128, 256, 4, 2, False, False, 24)     # 4x4 output: tile spans images
+    conv_tc_case(2, 4, 256, 256, 3, 1, True, True, 25)
+    conv_tc_case(1, 32, 256, 64, 3, 1, False, False, 26)
+    tokenizer_case(64, 4, 30)
     engine_case([[2, 32], [2, 64]], 64, 16, 4, True, 1.0, False, 10)
     engine_case([[2, 32], [2, 64]], 64, 16, 4, False, 0.5, False, 11)
     engine_case([[3, 64], [3, 128], [3, 256]], 512, 32, 8, True, 1.0, False, 12)   # vae_example geometry
