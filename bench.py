@@ -108,12 +108,35 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def usable_cores():
+    """Host cores this process may actually use: scheduler affinity, capped by the cgroup CPU quota if there is one
+    (os.cpu_count() reports the whole machine inside a container and oversubscribing it is far slower)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(int(txt[0]) / int(txt[1]))))
+            else:
+                q = int(txt[0])
+                per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
 def cpu_reference_step_rate(steps, warmup, seqs, label):
     """Times the oracle's reference-faithful fp32 training step (fwd + bwd + clip + Adam) on the host cores.
     Returns tokens/s.  This is the ONLY place bench.py executes oracle/ (as the CPU baseline, never as product)."""
     from oracle import dalle as O
     from oracle import optim as OO
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     cfg = O.DalleConfig(512, 6, 4, 50258, 512, 256, 1024)
     params = O.init_params(cfg, 0)

@@ -25,6 +25,8 @@ def get_tokenizer(tokenizer_type=None, from_pretrained=True, add_padding_token=T
             tok = GPT2TokenizerFast.from_pretrained("gpt2", local_files_only=True)
             if add_padding_token:
                 tok.add_special_tokens({"pad_token": "<|padding|>"})
+            if len(tok) != 50258:   # an empty / partial local cache is not the GPT-2 vocabulary
+                return _PaddingOnlyTokenizer()
             return tok
         except Exception:  # no local cache / no network
             return _PaddingOnlyTokenizer()

@@ -157,7 +157,7 @@ def forward(params, tokens, cfg: DalleConfig, bf16=False, quirks: Quirks = None,
     # --- to_logits (models.py:391-395): LN -> dense -> cast fp32
     hf = _r(layer_norm(x, W("to_logits/layer_norm/g"), W("to_logits/layer_norm/b"), q_.ln_eps), bf16)
     logits = hf @ W("to_logits/linear_out/kernel") + W("to_logits/linear_out/bias")
-    logits = logits.to(torch.float32)
+    logits = logits.to(torch.promote_types(logits.dtype, torch.float32))  # models.py:395 (fp64 kept for FD tests)
     # --- loss (models.py:407-411, 348-359)
     labels = shift_labels(tokens, cfg.eos_token_id)
     if faithful:
