@@ -238,8 +238,16 @@ def main():
     clocks = sampler.stop()
     ms_per_step = ms_total / args.steps
     value = tokens_per_step * 1000.0 / ms_per_step
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-    gemm_flops = sum(f for _, _, f in prof)
+    gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
+    gemm_flops = sum(f for _, _, f, _ in prof)
+    if os.environ.get("DB200_BENCH_VERBOSE") and dp.rank == 0:
+        agg = {}
+        for a, b, f, tag in prof:
+            e = agg.setdefault(tag, [0, 0.0, 0.0])
+            e[0] += 1; e[1] += a.elapsed_time(b); e[2] += f
+        for tag, (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print(f"  gemm M={tag[0]:6d} N={tag[1]:6d} K={tag[2]:6d} mode={tag[3]} a_mn={tag[4]} b_mn={tag[5]}: n/step={n / args.steps:5.1f} "
+                  f"ms/step={ms / args.steps:7.3f} {fl / ms / 1e9:7.1f} TFLOP/s", file=sys.stderr)
     peak_tf, _, peak_kind = measured_peaks()
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     loss_now = float(spec.loss_sum.item()) * spec.loss_scale

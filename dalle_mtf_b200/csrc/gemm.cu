@@ -32,7 +32,8 @@ struct GemmCfg {
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256: power of two >= 32
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + size_t(STAGES) * STAGE_BYTES + 256 /*barriers*/;
+  static constexpr size_t SMEM_BYTES =
+      1024 /*align slack*/ + size_t(STAGES) * STAGE_BYTES + 256 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
 };
 
 struct GemmParams {
@@ -106,48 +107,145 @@ __device__ __forceinline__ void load8_bf16(const bf16* sp, float* o) {
   o[0] = r0.x; o[1] = r0.y; o[2] = r1.x; o[3] = r1.y; o[4] = r2.x; o[5] = r2.y; o[6] = r3.x; o[7] = r3.y;
 }
 
+// Coalesced epilogue I/O.  A thread owns one accumulator ROW, so touching global memory directly would make every
+// warp-level access hit 32 different rows with 16 bytes each (partial sectors -> L2 read-modify-write: ncu showed
+// 1.5-2 GB of DRAM reads for a 4.1 GB write, even with 64-byte segments).  Each epilogue warp therefore owns a 4 KiB
+// smem buffer holding a [32 rows][128 B] block (16-byte slots XOR-swizzled by row: conflict-free both ways); global
+// traffic is 8 instructions of 4 rows x 128 contiguous bytes = whole cache lines, for outputs AND for the
+// residual / ReLU-mask operands.
+constexpr uint32_t STG_BYTES = 32 * 128;  // per epilogue warp
+
+__device__ __forceinline__ uint32_t stg_addr(uint32_t stg, int row, int slot) {
+  return stg + row * 128 + (((slot ^ row) & 7) << 4);
+}
+__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4u(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)
+               : "memory");
+  return v;
+}
+// this lane's row: 32 bf16 values -> slots [4h, 4h+4)
+__device__ __forceinline__ void stage_put_bf16(uint32_t stg, int lane, int h, const float* o) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float* v = o + g * 8;
+    st_shared_v4u(stg_addr(stg, lane, h * 4 + g), pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                  pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+__device__ __forceinline__ void stage_get_bf16(uint32_t stg, int lane, int h, float* o) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint4 q = ld_shared_v4u(stg_addr(stg, lane, h * 4 + g));
+    const float2 a = unpack_bf16x2(q.x), b = unpack_bf16x2(q.y), c = unpack_bf16x2(q.z), d = unpack_bf16x2(q.w);
+    float* v = o + g * 8;
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  }
+}
+// this lane's row: 32 fp32 values -> all 8 slots
+__device__ __forceinline__ void stage_put_f32(uint32_t stg, int lane, const float* o) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    st_shared_v4u(stg_addr(stg, lane, g), __float_as_uint(o[g * 4]), __float_as_uint(o[g * 4 + 1]),
+                  __float_as_uint(o[g * 4 + 2]), __float_as_uint(o[g * 4 + 3]));
+}
+// smem block -> global rows [row0, row0+32) x 128 bytes starting at element column col0 (ESZ bytes per element)
+template <int ESZ>
+__device__ __forceinline__ void stage_flush(uint32_t stg, void* D, long long ldd, int row0, int col0, int M, int N,
+                                            int lane) {
+  constexpr int EPS = 16 / ESZ;  // elements per 16-byte slot
+  __syncwarp();
+  const int slot = lane & 7, rsub = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    const uint4 v = ld_shared_v4u(stg_addr(stg, r, slot));
+    const int row = row0 + r, col = col0 + slot * EPS;
+    if (row < M && col + EPS <= N)
+      *reinterpret_cast<uint4*>(reinterpret_cast<char*>(D) + ((long long)row * ldd + col) * ESZ) = v;
+  }
+  __syncwarp();
+}
+// global bf16 rows -> smem block (zero where out of range)
+__device__ __forceinline__ void stage_fetch_bf16(uint32_t stg, const bf16* src, long long ld, int row0, int col0, int M,
+                                                 int N, int lane) {
+  const int slot = lane & 7, rsub = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    const int row = row0 + r, col = col0 + slot * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < M && col + 8 <= N) v = __ldg(reinterpret_cast<const uint4*>(src + (long long)row * ld + col));
+    st_shared_v4u(stg_addr(stg, r, slot), v.x, v.y, v.z, v.w);
+  }
+  __syncwarp();
+}
+
 template <int CH>
-__device__ __forceinline__ void epi_store(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase) {
+__device__ __forceinline__ void epi_store(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase,
+                                          uint32_t stg, int row0, int lane) {
+  static_assert(CH % 2 == 0, "epilogue works on pairs of 32-column chunks");
 #pragma unroll 1
-  for (int c = 0; c < CH; ++c) {
-    const int col0 = cbase + c * 32;
-    if (col0 >= p.N) break;  // warp-uniform
-    uint32_t r[32];
-    tmem_ld_x32(t_addr + c * 32, r);
-    tmem_ld_wait();
-    if (!row_ok) continue;
+  for (int pc = 0; pc < CH / 2; ++pc) {
+    const int colp = cbase + pc * 64;
+    if (colp >= p.N) break;  // warp-uniform
+    if (p.residual) stage_fetch_bf16(stg, p.residual, p.ldr, row0, colp, p.M, p.N, lane);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int col = col0 + g * 8;
-      if (col + 8 > p.N) break;
-      float o[8];
+    for (int h = 0; h < 2; ++h) {
+      const int col0 = colp + h * 32;
+      uint32_t r[32];
+      tmem_ld_x32(t_addr + (pc * 2 + h) * 32, r);
+      tmem_ld_wait();
+      float o[32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = __uint_as_float(r[g * 8 + j]) * p.alpha;
-      if (p.bias) {
-        float b[8];
-        load8(p.bias + col, b);
+      for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]) * p.alpha;
+      if (p.bias && col0 + 32 <= p.N) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += b[j];
+        for (int g = 0; g < 4; ++g) {
+          float b[8];
+          load8(p.bias + col0 + g * 8, b);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[g * 8 + j] += b[j];
+        }
+      } else if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.N) o[j] += __ldg(p.bias + col0 + j);
       }
       if (p.relu) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+        for (int j = 0; j < 32; ++j) o[j] = fmaxf(o[j], 0.f);
       }
       if (p.residual) {
-        float rr[8];
-        load8_bf16(p.residual + (long long)row * p.ldr + col, rr);
+        float rr[32];
+        stage_get_bf16(stg, lane, h, rr);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] += rr[j];
+        for (int j = 0; j < 32; ++j) o[j] += rr[j];
       }
-      if (p.out_f32) {
-        float* dp = reinterpret_cast<float*>(p.D) + (long long)row * p.ldd + col;
-        *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(dp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      if (p.out_f32) {  // 32 fp32 columns are a whole 128-byte line: flush per chunk
+        if (p.residual) __syncwarp();
+        // (fp32 output with a residual shares the buffer: the residual of chunk h was consumed above)
+        if (p.residual && h == 0) {  // keep chunk 1's residual: spill it to registers before overwriting
+          float keep[32];
+          stage_get_bf16(stg, lane, 1, keep);
+          stage_put_f32(stg, lane, o);
+          stage_flush<4>(stg, p.D, p.ldd, row0, col0, p.M, p.N, lane);
+          stage_put_bf16(stg, lane, 1, keep);
+          __syncwarp();
+        } else {
+          stage_put_f32(stg, lane, o);
+          stage_flush<4>(stg, p.D, p.ldd, row0, col0, p.M, p.N, lane);
+        }
       } else {
-        store8_bf16(reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col, o);
+        stage_put_bf16(stg, lane, h, o);
       }
     }
+    if (!p.out_f32) stage_flush<2>(stg, p.D, p.ldd, row0, colp, p.M, p.N, lane);
   }
+  (void)row; (void)row_ok;
 }
 
 template <int CH>
@@ -177,26 +275,27 @@ __device__ __forceinline__ void epi_atomic(const GemmParams& p, uint32_t t_addr,
 }
 
 template <int CH>
-__device__ __forceinline__ void epi_relu_bwd(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase) {
+__device__ __forceinline__ void epi_relu_bwd(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase,
+                                             uint32_t stg, int row0, int lane) {
 #pragma unroll 1
-  for (int c = 0; c < CH; ++c) {
-    const int col0 = cbase + c * 32;
-    if (col0 >= p.N) break;
-    uint32_t r[32];
-    tmem_ld_x32(t_addr + c * 32, r);
-    tmem_ld_wait();
-    if (!row_ok) continue;
+  for (int pc = 0; pc < CH / 2; ++pc) {
+    const int colp = cbase + pc * 64;
+    if (colp >= p.N) break;
+    stage_fetch_bf16(stg, p.aux, p.ldaux, row0, colp, p.M, p.N, lane);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int col = col0 + g * 8;
-      if (col + 8 > p.N) break;
-      float am[8], o[8];
-      load8_bf16(p.aux + (long long)row * p.ldaux + col, am);
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[32];
+      tmem_ld_x32(t_addr + (pc * 2 + h) * 32, r);
+      tmem_ld_wait();
+      float am[32], o[32];
+      stage_get_bf16(stg, lane, h, am);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = am[j] > 0.f ? __uint_as_float(r[g * 8 + j]) * p.alpha : 0.f;
-      store8_bf16(reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col, o);
+      for (int j = 0; j < 32; ++j) o[j] = am[j] > 0.f ? __uint_as_float(r[j]) * p.alpha : 0.f;
+      stage_put_bf16(stg, lane, h, o);  // in place: this lane overwrites the slots it just read
     }
+    stage_flush<2>(stg, p.D, p.ldd, row0, colp, p.M, p.N, lane);
   }
+  (void)row; (void)row_ok;
 }
 
 // per (row, half-tile): running max and sum exp of (acc + bias) over the valid vocabulary columns; label logit
@@ -256,45 +355,51 @@ __device__ __forceinline__ void epi_ce_stats(const GemmParams& p, uint32_t t_add
 
 // dlogits = alpha * (softmax - onehot), zero in the padded vocabulary columns
 template <int CH>
-__device__ __forceinline__ void epi_ce_grad(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase) {
+__device__ __forceinline__ void epi_ce_grad(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase,
+                                            uint32_t stg, int row0, int lane) {
   const int label = row_ok ? p.labels[row] : -1;
   const float l2 = row_ok ? p.lse[row] * kLog2e : 0.f;
 #pragma unroll 1
-  for (int c = 0; c < CH; ++c) {
-    const int col0 = cbase + c * 32;
-    if (col0 >= p.N) break;
-    uint32_t r[32];
-    tmem_ld_x32(t_addr + c * 32, r);
-    tmem_ld_wait();
-    if (!row_ok) continue;
+  for (int pc = 0; pc < CH / 2; ++pc) {
+    const int colp = cbase + pc * 64;
+    if (colp >= p.N) break;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const int col = col0 + g * 8;
-      if (col + 8 > p.N) break;
-      float o[8];
-      if (col + 8 <= p.n_valid) {
-        float b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (p.bias) load8(p.bias + col, b);
+    for (int h = 0; h < 2; ++h) {
+      const int col0 = colp + h * 32;
+      uint32_t r[32];
+      tmem_ld_x32(t_addr + (pc * 2 + h) * 32, r);
+      tmem_ld_wait();
+      float o[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = fast_exp2(fmaf(__uint_as_float(r[g * 8 + j]) + b[j], kLog2e, -l2)) * p.alpha;
-      } else {
+      for (int j = 0; j < 32; ++j) o[j] = 0.f;
+      if (row_ok && col0 < p.n_valid) {
+        if (col0 + 32 <= p.n_valid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int cc = col + j;
-          o[j] = cc < p.n_valid
-                     ? fast_exp2(fmaf(__uint_as_float(r[g * 8 + j]) + (p.bias ? __ldg(p.bias + cc) : 0.f), kLog2e, -l2)) *
-                           p.alpha
-                     : 0.f;
+          for (int g = 0; g < 4; ++g) {
+            float b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (p.bias) load8(p.bias + col0 + g * 8, b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[g * 8 + j] = fast_exp2(fmaf(__uint_as_float(r[g * 8 + j]) + b[j], kLog2e, -l2)) * p.alpha;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int cc = col0 + j;
+            if (cc < p.n_valid)
+              o[j] = fast_exp2(fmaf(__uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + cc) : 0.f), kLog2e, -l2)) *
+                     p.alpha;
+          }
+        }
+        if (label >= col0 && label < col0 + 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j == label) o[j] -= p.alpha;
         }
       }
-      if (label >= col && label < col + 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (col + j == label) o[j] -= p.alpha;
-      }
-      store8_bf16(reinterpret_cast<bf16*>(p.D) + (long long)row * p.ldd + col, o);
+      stage_put_bf16(stg, lane, h, o);
     }
+    stage_flush<2>(stg, p.D, p.ldd, row0, colp, p.M, p.N, lane);
   }
 }
 
@@ -314,6 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tfull_bar = bars + 16 * STAGES;    // 2 x 8 B
   const uint32_t tempty_bar = tfull_bar + 16;       // 2 x 8 B
   const uint32_t tmem_slot = tempty_bar + 16;       // 4 B
+  const uint32_t stg_base = bars + 256;             // 8 x STG_BYTES, 16-byte aligned
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
@@ -414,21 +520,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int wq = ew & 3;
     const int half = ew >> 2;
     constexpr int CH = BN / 64;  // 32-column chunks per half
+    const uint32_t stg = stg_base + ew * STG_BYTES;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const TileCoord t = decode_tile(p, tile);
-      const int row = t.m_blk * BM + wq * 32 + lane;
+      const int row0 = t.m_blk * BM + wq * 32;
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const int cbase = t.n_blk * BN + half * (BN / 2);
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + half * (BN / 2) + (uint32_t(wq * 32) << 16);
       switch (p.mode) {
-        case DB200_EPI_STORE:    epi_store<CH>(p, t_addr, row, row_ok, cbase); break;
+        case DB200_EPI_STORE:    epi_store<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
         case DB200_EPI_ATOMIC:   epi_atomic<CH>(p, t_addr, row, row_ok, cbase); break;
-        case DB200_EPI_RELU_BWD: epi_relu_bwd<CH>(p, t_addr, row, row_ok, cbase); break;
+        case DB200_EPI_RELU_BWD: epi_relu_bwd<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
         case DB200_EPI_CE_STATS: epi_ce_stats<CH>(p, t_addr, row, row_ok, cbase, t.n_blk * 2 + half); break;
-        default:                 epi_ce_grad<CH>(p, t_addr, row, row_ok, cbase); break;
+        default:                 epi_ce_grad<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
       }
       // release the accumulator stage back to the MMA warp
       tc_fence_before();

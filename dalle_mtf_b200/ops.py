@@ -76,7 +76,7 @@ def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, ldd=
                                    M, N, K, ctypes.byref(e)), "db200_gemm_bf16")
     if prof is not None:
         ev1.record()
-        prof.append((ev0, ev1, 2.0 * M * N * K))
+        prof.append((ev0, ev1, 2.0 * M * N * K, (M, N, K, mode, int(a_mn), int(b_mn))))
     return out
 
 
