@@ -8,8 +8,8 @@
 // Layout: qkv bf16 [B][S][3][H][dh] (the fused q|k|v projection output), out / dout bf16 [B][S][H][dh],
 //         lse f32 [B][H][S] (natural log of sum exp(scale*s)), dqkv like qkv.
 //
-// Design (all three kernels): 128 threads; thread t owns TMEM lane t (= one query row of the 128-row tile, or one
-// key row of the dK/dV accumulators).  Operand tiles are brought by TMA as [rows][64] bf16 sub-tiles with the
+// Design (all three kernels): 256 threads; threads t and t+128 share TMEM lane t (= one query row of the 128-row tile,
+// or one key row of the dK/dV accumulators) and each handle half of its columns.  Operand tiles are brought by TMA as [rows][64] bf16 sub-tiles with the
 // 128-byte swizzle, which serves both as a K-major UMMA operand (K = head dim) and as an MN-major one (K = rows), so
 // Q, K, V, dO are each loaded once and used for every product they appear in.  P / dS are written by the softmax
 // threads straight into the same swizzled layout and consumed by the next tcgen05.mma.
@@ -45,15 +45,17 @@ struct FwdCfg {
   static constexpr uint32_t Q_BYTES = 128 * DH * 2;
   static constexpr uint32_t KV_BYTES = BNK * DH * 2;
   static constexpr uint32_t P_BYTES = 128 * BNK * 2;
-  static constexpr size_t SMEM = 1024 + Q_BYTES + 2 * KV_BYTES + P_BYTES + 128;
+  static constexpr size_t SMEM = 1024 + Q_BYTES + 2 * KV_BYTES + P_BYTES + 64 + 2 * 128 * 4 + 64;
 };
 
 template <int DH>
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(256, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                 bf16* __restrict__ out, float* __restrict__ lse_out, int S, int H, float scale) {
   using C = FwdCfg<DH>;
   constexpr int BNK = C::BNK;
+  constexpr int HC = BNK / 2;  // key columns of S handled by one thread (two threads share a query row)
+  constexpr int HD = DH / 2;   // output columns accumulated by one thread
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -62,9 +64,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16, bar_s = bars + 24, bar_o = bars + 32;
   const uint32_t tmem_slot = bars + 40;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* xch = reinterpret_cast<float*>(smem_raw + (bars + 64 - raw));  // [2][128] row-max exchange
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int qb = gridDim.x - 1 - blockIdx.x;  // heavy (late) query blocks first
+  const int rowi = tid & 127, half = tid >> 7;  // TMEM lane (query row in the tile), column half
+  const int qb = gridDim.x - 1 - blockIdx.x;    // heavy (late) query blocks first
   const int h = blockIdx.y, b = blockIdx.z;
   const int q0 = qb * 128;
   const int kv_len = min(S, q0 + 128);
@@ -82,7 +86,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tO = tmem + 128;
-  const uint32_t lane_off = uint32_t(warp * 32) << 16;
+  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, C::Q_BYTES);
@@ -96,18 +100,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, BNK, 0, 0);  // S = Q K^T : both K-major (K = dh)
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);   // O = P V   : A K-major (K = keys), B MN-major
 
-  const int qi = q0 + tid;  // this thread's query index
+  const int qi = q0 + rowi;  // this thread's query index
   const float c1 = scale * LOG2E;
-  float m_run = -INFINITY, l_run = 0.f;
-  float o_acc[DH];
+  float m_run = -INFINITY, l_run = 0.f;  // l_run: partial sum over this thread's key columns
+  float o_acc[HD];
 #pragma unroll
-  for (int e = 0; e < DH; ++e) o_acc[e] = 0.f;
+  for (int e = 0; e < HD; ++e) o_acc[e] = 0.f;
 
   mbar_wait(bar_q, 0);
 
   for (int j = 0; j < n_kv; ++j) {
     const uint32_t ph = j & 1;
-    // ---- S = Q K_j^T
     if (tid == 0) {
       mbar_wait(bar_k, ph);
       tc_fence_after();
@@ -125,55 +128,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_expect_tx(bar_k, C::KV_BYTES);
       tma_load_tile<DH>(sK, BNK * 128, &tmKV, bar_k, 1 * H + h, (j + 1) * BNK, b);
     }
-    // ---- softmax on this thread's row
-    const int k0 = j * BNK;
-    const bool need_mask = (k0 + BNK - 1) > q0;  // block reaches past the first query row of the tile
+    // ---- softmax: this thread's half of the row, kept in registers
+    const int k0 = j * BNK + half * HC;
+    const bool need_mask = (j * BNK + BNK - 1) > q0;
+    float sv[HC];
     float mx = -INFINITY;
-#pragma unroll 1
-    for (int c = 0; c < BNK / 32; ++c) {
+#pragma unroll
+    for (int c = 0; c < HC / 32; ++c) {
       uint32_t r[32];
-      tmem_ld_x32(tS + lane_off + c * 32, r);
+      tmem_ld_x32(tS + lane_off + half * HC + c * 32, r);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
         float s = __uint_as_float(r[i]);
         if (need_mask && (k0 + c * 32 + i) > qi) s = -INFINITY;
+        sv[c * 32 + i] = s;
         mx = fmaxf(mx, s);
       }
     }
-    const float m_new = fmaxf(m_run, mx);  // finite: key 0 is visible to every row and is in block 0
+    xch[half * 128 + rowi] = mx;
+    tc_fence_before();
+    __syncthreads();  // (1) both halves' maxima visible; every thread has finished reading S from TMEM
+    const float m_new = fmaxf(m_run, fmaxf(mx, xch[(half ^ 1) * 128 + rowi]));  // finite: key 0 is always visible
     const float alpha = exp2f((m_run - m_new) * c1);
     const float mc = m_new * c1;
     float lsum = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < BNK / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(tS + lane_off + c * 32, r);
-      tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < HC / 32; ++c) {
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        float s0 = __uint_as_float(r[i]), s1 = __uint_as_float(r[i + 1]);
-        float p0 = exp2f(s0 * c1 - mc), p1 = exp2f(s1 * c1 - mc);
-        if (need_mask) {
-          if ((k0 + c * 32 + i) > qi) p0 = 0.f;
-          if ((k0 + c * 32 + i + 1) > qi) p1 = 0.f;
-        }
+        const float p0 = exp2f(sv[c * 32 + i] * c1 - mc), p1 = exp2f(sv[c * 32 + i + 1] * c1 - mc);  // exp2(-inf) = 0
         lsum += p0 + p1;
         pk[i >> 1] = pack_bf16x2(p0, p1);
       }
-      // columns [c*32, c*32+32) of the P tile -> sub-tile (c*32)/64, 4 x 16-byte chunks
-      const uint32_t sub = sP + ((c * 32) / 64) * (128 * 128);
-      const int cc = (c * 32) % 64;
+      const int col = half * HC + c * 32;  // column inside the [128][BNK] P tile
+      const uint32_t sub = sP + (col / 64) * (128 * 128);
+      const int cc = col % 64;
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        st_shared_v4(sub + sw128_offset(tid, cc + g * 8), pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+        st_shared_v4(sub + sw128_offset(rowi, cc + g * 8), pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
     }
     l_run = l_run * alpha + lsum;
     m_run = m_new;
     fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to tcgen05.mma (async proxy)
-    tc_fence_before();
-    __syncthreads();
+    __syncthreads();           // (2) P complete
     // ---- O_j = P V_j  (fresh accumulator; the running output lives in registers)
     if (tid == 0) {
       mbar_wait(bar_v, ph);
@@ -187,7 +186,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       umma_commit(bar_o);
     }
 #pragma unroll
-    for (int e = 0; e < DH; ++e) o_acc[e] *= alpha;
+    for (int e = 0; e < HD; ++e) o_acc[e] *= alpha;
     mbar_wait(bar_o, ph);
     tc_fence_after();
     if (tid == 0 && j + 1 < n_kv) {
@@ -195,26 +194,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tma_load_tile<DH>(sV, BNK * 128, &tmKV, bar_v, 2 * H + h, (j + 1) * BNK, b);
     }
 #pragma unroll
-    for (int c = 0; c < DH / 32; ++c) {
+    for (int c = 0; c < HD / 32; ++c) {
       uint32_t r[32];
-      tmem_ld_x32(tO + lane_off + c * 32, r);
+      tmem_ld_x32(tO + lane_off + half * HD + c * 32, r);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(r[i]);
     }
-    // the next iteration's MMAs overwrite S / O in TMEM only after its own __syncthreads / barrier waits, but the
-    // S MMA is issued by thread 0 right away: make sure every thread finished reading S (done above, before the
-    // __syncthreads) and O (order it with a fence + barrier here).
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();  // (3) O consumed before the next iteration's MMAs overwrite S / O; xch reusable
     tc_fence_after();
   }
 
+  // combine the two halves' partial row sums
+  xch[half * 128 + rowi] = l_run;
+  __syncthreads();
+  const float l_tot = l_run + xch[(half ^ 1) * 128 + rowi];
   if (qi < S) {
-    const float inv = 1.f / l_run;
-    bf16* op = out + (((long long)b * S + qi) * H + h) * DH;
+    const float inv = 1.f / l_tot;
+    bf16* op = out + (((long long)b * S + qi) * H + h) * DH + half * HD;
 #pragma unroll
-    for (int e = 0; e < DH; e += 8) {
+    for (int e = 0; e < HD; e += 8) {
       uint4 q;
       q.x = pack_bf16x2(o_acc[e] * inv, o_acc[e + 1] * inv);
       q.y = pack_bf16x2(o_acc[e + 2] * inv, o_acc[e + 3] * inv);
@@ -222,7 +222,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       q.w = pack_bf16x2(o_acc[e + 6] * inv, o_acc[e + 7] * inv);
       *reinterpret_cast<uint4*>(op + e) = q;
     }
-    lse_out[((long long)b * H + h) * S + qi] = m_run * scale + logf(l_run);
+    if (half == 0) lse_out[((long long)b * H + h) * S + qi] = m_run * scale + logf(l_tot);
   }
   tc_fence_before();
   __syncthreads();
@@ -266,31 +266,33 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __rest
 //   ds = p * (dp - delta) * scale
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bwd_make_p_ds(uint32_t tS, uint32_t tdP, uint32_t lane_off, uint32_t sP, uint32_t sdS,
-                                              bool write_p, int tid, int qi, int k0, bool need_mask, bool row_ok,
-                                              float lse_l2, float delta, float c1, float scale) {
+                                              bool write_p, int rowi, int half, int qi, int k0, bool need_mask,
+                                              bool row_ok, float lse_l2, float delta, float c1, float scale) {
+  // two threads share a query row: `half` selects key columns [64*half, 64*half + 64) = sub-tile `half`
 #pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
+    const int col0 = half * 64 + c * 32;
     uint32_t rs[32], rd[32];
-    tmem_ld_x32(tS + lane_off + c * 32, rs);
-    tmem_ld_x32(tdP + lane_off + c * 32, rd);
+    tmem_ld_x32(tS + lane_off + col0, rs);
+    tmem_ld_x32(tdP + lane_off + col0, rd);
     tmem_ld_wait();
     uint32_t pk[16], dk[16];
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       float p0 = exp2f(__uint_as_float(rs[i]) * c1 - lse_l2);
       float p1 = exp2f(__uint_as_float(rs[i + 1]) * c1 - lse_l2);
-      if (!row_ok || (need_mask && (k0 + c * 32 + i) > qi)) p0 = 0.f;
-      if (!row_ok || (need_mask && (k0 + c * 32 + i + 1) > qi)) p1 = 0.f;
+      if (!row_ok || (need_mask && (k0 + col0 + i) > qi)) p0 = 0.f;
+      if (!row_ok || (need_mask && (k0 + col0 + i + 1) > qi)) p1 = 0.f;
       const float d0 = p0 * (__uint_as_float(rd[i]) - delta) * scale;
       const float d1 = p1 * (__uint_as_float(rd[i + 1]) - delta) * scale;
       pk[i >> 1] = pack_bf16x2(p0, p1);
       dk[i >> 1] = pack_bf16x2(d0, d1);
     }
-    const uint32_t sub_off = ((c * 32) / 64) * (128 * 128);
-    const int cc = (c * 32) % 64;
+    const uint32_t sub_off = half * (128 * 128);
+    const int cc = c * 32;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      const uint32_t off = sub_off + sw128_offset(tid, cc + g * 8);
+      const uint32_t off = sub_off + sw128_offset(rowi, cc + g * 8);
       if (write_p) st_shared_v4(sP + off, pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
       st_shared_v4(sdS + off, dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
     }
@@ -311,7 +313,7 @@ struct BwdCfg {
 };
 
 template <int DH>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                      const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S,
                      int H, float scale) {
@@ -328,6 +330,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int rowi = tid & 127, half = tid >> 7;
   const int jb = blockIdx.x;  // kv block (block 0 has the most work and is scheduled first)
   const int h = blockIdx.y, b = blockIdx.z;
   const int k0 = jb * 128;
@@ -345,7 +348,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 256 + DH;
-  const uint32_t lane_off = uint32_t(warp * 32) << 16;
+  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
 
   if (tid == 0) {
     mbar_expect_tx(bar_kv, 2 * C::TILE);
@@ -365,7 +368,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   for (int ib = jb; ib < n_q; ++ib, ++it) {
     const uint32_t ph = it & 1;
     const int q0 = ib * 128;
-    const int qi = q0 + tid;
+    const int qi = q0 + rowi;
     const bool row_ok = qi < S;
     float lse_l2 = 0.f, dl = 0.f;
     if (row_ok) {
@@ -392,8 +395,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
     mbar_wait(bar_a, ph);
     tc_fence_after();
-    bwd_make_p_ds(tS, tdP, lane_off, sP, sdS, true, tid, qi, k0, /*need_mask=*/ib == jb, row_ok, lse_l2, dl, c1,
-                  scale);
+    bwd_make_p_ds(tS, tdP, lane_off, sP, sdS, true, rowi, half, qi, k0, /*need_mask=*/ib == jb, row_ok, lse_l2, dl,
+                  c1, scale);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -422,16 +425,16 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     }
     (void)NT;
   }
-  // ---- write dK, dV rows (thread = key row)
-  const int ki = k0 + tid;
+  // ---- write dK, dV rows (thread pair = key row; each thread writes DH/2 columns)
+  const int ki = k0 + rowi;
 #pragma unroll 1
   for (int which = 0; which < 2; ++which) {
     const uint32_t tsrc = which == 0 ? tdK : tdV;
-    bf16* dst = dqkv + ((((long long)b * S + ki) * 3 + (which == 0 ? 1 : 2)) * H + h) * DH;
+    bf16* dst = dqkv + ((((long long)b * S + ki) * 3 + (which == 0 ? 1 : 2)) * H + h) * DH + half * (DH / 2);
 #pragma unroll 1
-    for (int c = 0; c < DH / 32; ++c) {
+    for (int c = 0; c < DH / 64; ++c) {
       uint32_t r[32];
-      tmem_ld_x32(tsrc + lane_off + c * 32, r);
+      tmem_ld_x32(tsrc + lane_off + half * (DH / 2) + c * 32, r);
       tmem_ld_wait();
       if (ki < S) {
 #pragma unroll
@@ -458,7 +461,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 // backward dQ
 // ------------------------------------------------------------------------------------------------------------------
 template <int DH>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(256, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                    const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S,
                    int H, float scale) {
@@ -473,6 +476,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int tid = threadIdx.x, warp = tid >> 5;
+  const int rowi = tid & 127, half = tid >> 7;
   const int ib = gridDim.x - 1 - blockIdx.x;  // heavy query blocks first
   const int h = blockIdx.y, b = blockIdx.z;
   const int q0 = ib * 128;
@@ -489,7 +493,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
-  const uint32_t lane_off = uint32_t(warp * 32) << 16;
+  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
 
   if (tid == 0) {
     mbar_expect_tx(bar_q, 2 * C::TILE);
@@ -503,7 +507,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
   constexpr uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);  // dQ = dS K : A K-major (K = keys), B MN-major
   const float c1 = scale * LOG2E;
-  const int qi = q0 + tid;
+  const int qi = q0 + rowi;
   const bool row_ok = qi < S;
   float lse_l2 = 0.f, dl = 0.f;
   if (row_ok) {
@@ -537,8 +541,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       mbar_expect_tx(bar_v, C::TILE);
       tma_load_tile<DH>(sV, T128, &tmQKV, bar_v, 2 * H + h, (jb + 1) * 128, b);
     }
-    bwd_make_p_ds(tS, tdP, lane_off, 0, sdS, false, tid, qi, jb * 128, /*need_mask=*/jb == ib, row_ok, lse_l2, dl, c1,
-                  scale);
+    bwd_make_p_ds(tS, tdP, lane_off, 0, sdS, false, rowi, half, qi, jb * 128, /*need_mask=*/jb == ib, row_ok, lse_l2,
+                  dl, c1, scale);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -558,11 +562,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       tma_load_tile<DH>(sK, T128, &tmQKV, bar_k, 1 * H + h, (jb + 1) * 128, b);
     }
   }
-  bf16* dst = dqkv + ((((long long)b * S + qi) * 3 + 0) * H + h) * DH;
+  bf16* dst = dqkv + ((((long long)b * S + qi) * 3 + 0) * H + h) * DH + half * (DH / 2);
 #pragma unroll 1
-  for (int c = 0; c < DH / 32; ++c) {
+  for (int c = 0; c < DH / 64; ++c) {
     uint32_t r[32];
-    tmem_ld_x32(tdQ + lane_off + c * 32, r);
+    tmem_ld_x32(tdQ + lane_off + half * (DH / 2) + c * 32, r);
     tmem_ld_wait();
     if (row_ok) {
 #pragma unroll
@@ -614,7 +618,7 @@ static int fwd_launch(cudaStream_t stream, const void* qkv, void* out, float* ls
     attr = true;
   }
   dim3 grid((S + 127) / 128, H, B);
-  attn_fwd_kernel<DH><<<grid, 128, C::SMEM, stream>>>(tmQ, tmKV, (bf16*)out, lse, S, H, scale);
+  attn_fwd_kernel<DH><<<grid, 256, C::SMEM, stream>>>(tmQ, tmKV, (bf16*)out, lse, S, H, scale);
   return check_launch("attn_fwd_kernel");
 }
 
@@ -636,10 +640,10 @@ static int bwd_launch(cudaStream_t stream, const void* qkv, const void* dout, co
     attr = true;
   }
   dim3 grid((S + 127) / 128, H, B);
-  attn_bwd_dkdv_kernel<DH><<<grid, 128, C::SMEM_DKDV, stream>>>(tmQKV, tmDO, lse, delta, (bf16*)dqkv, S, H, scale);
+  attn_bwd_dkdv_kernel<DH><<<grid, 256, C::SMEM_DKDV, stream>>>(tmQKV, tmDO, lse, delta, (bf16*)dqkv, S, H, scale);
   rc = check_launch("attn_bwd_dkdv_kernel");
   if (rc != DB200_OK) return rc;
-  attn_bwd_dq_kernel<DH><<<grid, 128, C::SMEM_DQ, stream>>>(tmQKV, tmDO, lse, delta, (bf16*)dqkv, S, H, scale);
+  attn_bwd_dq_kernel<DH><<<grid, 256, C::SMEM_DQ, stream>>>(tmQKV, tmDO, lse, delta, (bf16*)dqkv, S, H, scale);
   return check_launch("attn_bwd_dq_kernel");
 }
 
