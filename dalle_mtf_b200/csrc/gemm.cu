@@ -56,6 +56,7 @@ struct GemmParams {
   const float* lse;
   int n_valid;
   int n_parts;  // CE_STATS: partials per row = 2 * n_tiles (one per half tile)
+  float* colsum;  // CE_GRAD / RELU_BWD: colsum[n] += sum_m D[m,n] (bias gradient), or NULL
 };
 
 struct TileCoord {
@@ -184,6 +185,24 @@ __device__ __forceinline__ void stage_fetch_bf16(uint32_t stg, const bf16* src, 
   __syncwarp();
 }
 
+// column sums of the staged [32 rows][64 bf16] block (the values exactly as they are written to D), accumulated into
+// colsum[col0 .. col0+64): lane l owns columns 2l, 2l+1.  Rows >= M hold zeros (their `o` was zeroed).
+__device__ __forceinline__ void stage_colsum_bf16(uint32_t stg, float* colsum, int col0, int N, int lane) {
+  __syncwarp();
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < 32; ++r) {
+    uint32_t w;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(stg_addr(stg, r, lane >> 2) + (lane & 3) * 4) : "memory");
+    const float2 f = unpack_bf16x2(w);
+    s0 += f.x;
+    s1 += f.y;
+  }
+  const int col = col0 + 2 * lane;
+  if (col < N) atomicAdd(colsum + col, s0);
+  if (col + 1 < N) atomicAdd(colsum + col + 1, s1);
+}
+
 template <int CH>
 __device__ __forceinline__ void epi_store(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase,
                                           uint32_t stg, int row0, int lane) {
@@ -293,6 +312,7 @@ __device__ __forceinline__ void epi_relu_bwd(const GemmParams& p, uint32_t t_add
       for (int j = 0; j < 32; ++j) o[j] = am[j] > 0.f ? __uint_as_float(r[j]) * p.alpha : 0.f;
       stage_put_bf16(stg, lane, h, o);  // in place: this lane overwrites the slots it just read
     }
+    if (p.colsum) stage_colsum_bf16(stg, p.colsum, colp, p.N, lane);
     stage_flush<2>(stg, p.D, p.ldd, row0, colp, p.M, p.N, lane);
   }
   (void)row; (void)row_ok;
@@ -399,6 +419,7 @@ __device__ __forceinline__ void epi_ce_grad(const GemmParams& p, uint32_t t_addr
       }
       stage_put_bf16(stg, lane, h, o);
     }
+    if (p.colsum) stage_colsum_bf16(stg, p.colsum, colp, p.N, lane);
     stage_flush<2>(stg, p.D, p.ldd, row0, colp, p.M, p.N, lane);
   }
 }
@@ -655,6 +676,7 @@ extern "C" int db200_gemm_bf16(db200_stream_t stream_, const void* A, int a_mn_m
   p.label_logit = epi->label_logit;
   p.lse = epi->lse;
   p.n_valid = epi->n_valid;
+  p.colsum = (mode == DB200_EPI_CE_GRAD || mode == DB200_EPI_RELU_BWD) ? epi->colsum : nullptr;
 
   // tile width: 256 unless that leaves most SMs idle (CE epilogues are defined on 256-wide tiles)
   int bn = 256;

@@ -153,13 +153,13 @@ __global__ void __launch_bounds__(128)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ g,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dg,
-                     float* __restrict__ db, int rows) {
+                     float* __restrict__ db, float* __restrict__ dxsum, int rows) {
   constexpr int d = NCH * 256;
   __shared__ float red[4][d];  // NCH <= 8 -> <= 32 KiB
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float gg[NCH][8];
-  float adg[NCH][8], adb[NCH][8];
+  float adg[NCH][8], adb[NCH][8], adx[NCH][8];
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     const int col = (c * 32 + lane) * 8;
@@ -167,7 +167,7 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     gg[c][0] = g0.x; gg[c][1] = g0.y; gg[c][2] = g0.z; gg[c][3] = g0.w;
     gg[c][4] = g1.x; gg[c][5] = g1.y; gg[c][6] = g1.z; gg[c][7] = g1.w;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) adg[c][j] = adb[c][j] = 0.f;
+    for (int j = 0; j < 8; ++j) adg[c][j] = adb[c][j] = adx[c][j] = 0.f;
   }
   for (int row = blockIdx.x * 4 + warp; row < rows; row += gridDim.x * 4) {
     const float mean = mean_in[row], rstd = rstd_in[row];
@@ -207,18 +207,27 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] += r[j];
       }
-      *reinterpret_cast<uint4*>(dxr + col) = pack8(o);
+      const uint4 packed = pack8(o);
+      *reinterpret_cast<uint4*>(dxr + col) = packed;
+      if (dxsum) {  // sum the values exactly as stored (bf16-rounded), like a separate column-sum pass would
+        float ro[8];
+        unpack8(packed, ro);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) adx[c][j] += ro[j];
+      }
     }
   }
-  // block reduction of dg, then db
-#pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  // block reduction of dg, then db (then dxsum)
+  const int npass = dxsum ? 3 : 2;
+#pragma unroll 1
+  for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll
     for (int c = 0; c < NCH; ++c)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) red[warp][(c * 32 + lane) * 8 + j] = pass == 0 ? adg[c][j] : adb[c][j];
+      for (int j = 0; j < 8; ++j)
+        red[warp][(c * 32 + lane) * 8 + j] = pass == 0 ? adg[c][j] : (pass == 1 ? adb[c][j] : adx[c][j]);
     __syncthreads();
-    float* dst = pass == 0 ? dg : db;
+    float* dst = pass == 0 ? dg : (pass == 1 ? db : dxsum);
     for (int col = threadIdx.x; col < d; col += 128)
       atomicAdd(dst + col, red[0][col] + red[1][col] + red[2][col] + red[3][col]);
     __syncthreads();
@@ -382,9 +391,9 @@ extern "C" int db200_layernorm_fwd(db200_stream_t stream_, const void* x, const 
   return check_launch("layernorm_fwd_kernel");
 }
 
-extern "C" int db200_layernorm_bwd(db200_stream_t stream_, const void* dy, const void* x, const float* g,
-                                   const float* mean, const float* rstd, const void* dres, void* dx, float* dg,
-                                   float* db, int rows, int d) {
+extern "C" int db200_layernorm_bwd_ex(db200_stream_t stream_, const void* dy, const void* x, const float* g,
+                                      const float* mean, const float* rstd, const void* dres, void* dx, float* dg,
+                                      float* db, float* dxsum, int rows, int d) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   DB200_REQUIRE(rows > 0, DB200_E_INVALID, "layernorm_bwd: rows must be positive");
   DB200_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx) && aligned16(g) && mean && rstd && dg && db &&
@@ -395,15 +404,21 @@ extern "C" int db200_layernorm_bwd(db200_stream_t stream_, const void* dy, const
   const bf16 *dyp = (const bf16*)dy, *xp = (const bf16*)x, *drp = (const bf16*)dres;
   bf16* dxp = (bf16*)dx;
   switch (d) {
-    case 256:  layernorm_bwd_kernel<1><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, rows); break;
-    case 512:  layernorm_bwd_kernel<2><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, rows); break;
-    case 768:  layernorm_bwd_kernel<3><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, rows); break;
-    case 1024: layernorm_bwd_kernel<4><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, rows); break;
-    case 2048: layernorm_bwd_kernel<8><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, rows); break;
+    case 256:  layernorm_bwd_kernel<1><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, dxsum, rows); break;
+    case 512:  layernorm_bwd_kernel<2><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, dxsum, rows); break;
+    case 768:  layernorm_bwd_kernel<3><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, dxsum, rows); break;
+    case 1024: layernorm_bwd_kernel<4><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, dxsum, rows); break;
+    case 2048: layernorm_bwd_kernel<8><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, dxsum, rows); break;
     default:
       return set_error(DB200_E_UNSUPPORTED, "layernorm: d=%d not in {256,512,768,1024,2048}", d);
   }
   return check_launch("layernorm_bwd_kernel");
+}
+
+extern "C" int db200_layernorm_bwd(db200_stream_t stream_, const void* dy, const void* x, const float* g,
+                                   const float* mean, const float* rstd, const void* dres, void* dx, float* dg,
+                                   float* db, int rows, int d) {
+  return db200_layernorm_bwd_ex(stream_, dy, x, g, mean, rstd, dres, dx, dg, db, nullptr, rows, d);
 }
 
 extern "C" int db200_colsum_bf16(db200_stream_t stream_, const void* x, int64_t ld, int rows, int cols,

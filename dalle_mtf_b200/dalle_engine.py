@@ -295,30 +295,29 @@ class DalleEngine:
         return out.view(B, S, self.Vpad)[:, :, :self.V]
 
     # ------------------------------------------------------------------------------------------ backward
-    def _block_bwd(self, i, x_in, sv, dx_out, dx_in, bufs, B):
+    def _block_bwd(self, i, x_in, sv, dx_out, dx_in, bufs, B, dxsum_below):
+        """Backward of one block.  Bias gradients are column sums of activation gradients; they are produced by the
+        kernel that WRITES that gradient (LayerNorm-backward / ReLU-mask epilogue) instead of separate passes:
+        db2 (= colsum of this block's output gradient) was already accumulated by whoever produced dx_out."""
         p = f"l{i}."
-        T = B * self.S
-        d = self.d
         # ---- MLP
-        ops.linear_dgrad(dx_out, self.W(p + "w2"), bufs["dh1"], relu_mask_of=sv["h1"])       # dH = (dx W2^T) * [h1>0]
+        ops.linear_dgrad(dx_out, self.W(p + "w2"), bufs["dh1"], relu_mask_of=sv["h1"],
+                         colsum=self.G(p + "b1"))                                       # dH = (dx W2^T)*[h1>0]; db1
         ops.linear_wgrad(sv["h1"], dx_out, self.G(p + "w2"))
-        ops.colsum(dx_out, self.G(p + "b2"))
         ops.linear_dgrad(bufs["dh1"], self.W(p + "w1"), bufs["dtmp"])                         # dLN2 out
         ops.linear_wgrad(sv["ln2"], bufs["dh1"], self.G(p + "w1"))
-        ops.colsum(bufs["dh1"], self.G(p + "b1"))
         dx_mid = bufs["dx_b"] if dx_out is bufs["dx_a"] else bufs["dx_a"]
         ops.layernorm_bwd(bufs["dtmp"], sv["xmid"], self.P(p + "ln2_g"), sv["mean2"], sv["rstd2"], dx_out, dx_mid,
-                          self.G(p + "ln2_g"), self.G(p + "ln2_b"))
+                          self.G(p + "ln2_g"), self.G(p + "ln2_b"), dxsum=self.G(p + "o_b"))  # do_b = colsum(dx_mid)
         # ---- attention
         ops.linear_dgrad(dx_mid, self.W(p + "wo"), bufs["dtmp"])                              # d(attn out)
         ops.linear_wgrad(sv["attn"], dx_mid, self.G(p + "wo"))
-        ops.colsum(dx_mid, self.G(p + "o_b"))
         ops.attn_bwd(sv["qkv"], sv["attn"], bufs["dtmp"], sv["lse"], bufs["dq_acc"], bufs["delta"], bufs["dqkv"], B,
                      self.S, self.H, self.dh, self.attn_scale)
         ops.linear_dgrad(bufs["dqkv"], self.W(p + "wqkv"), bufs["dtmp"])                      # dLN1 out
         ops.linear_wgrad(sv["ln1"], bufs["dqkv"], self.G(p + "wqkv"))
         ops.layernorm_bwd(bufs["dtmp"], x_in, self.P(p + "ln1_g"), sv["mean1"], sv["rstd1"], dx_mid, dx_in,
-                          self.G(p + "ln1_g"), self.G(p + "ln1_b"))
+                          self.G(p + "ln1_g"), self.G(p + "ln1_b"), dxsum=dxsum_below)        # db2 of the layer below
 
     def backward(self, grad_scale, on_bucket_ready=None):
         """Back-propagates d(sum(loss_rows) * grad_scale).  Gradients ACCUMULATE into self.grads.
@@ -330,13 +329,12 @@ class DalleEngine:
         labels = bufs["labels"].view(T)
         ops.gemm(bufs["hf"], self.W("wout"), bufs["dlogits"], T, self.Vpad, d, a_mn=False, b_mn=True,
                  mode=L.EPI_CE_GRAD, alpha=grad_scale, bias=self.P("bout"), labels=labels, lse=bufs["lse_v"],
-                 n_valid=self.V)
-        ops.colsum(bufs["dlogits"], self.G("bout"))
+                 n_valid=self.V, colsum=self.G("bout"))                 # dlogits + fused d(bout) = colsum(dlogits)
         ops.linear_wgrad(bufs["hf"], bufs["dlogits"], self.G("wout"))
         ops.linear_dgrad(bufs["dlogits"], self.W("wout"), bufs["dtmp"])
         dx = bufs["dx_a"]
         ops.layernorm_bwd(bufs["dtmp"], bufs["xs"][self.L], self.P("lnf_g"), bufs["meanf"], bufs["rstdf"], None, dx,
-                          self.G("lnf_g"), self.G("lnf_b"))
+                          self.G("lnf_g"), self.G("lnf_b"), dxsum=self.G(f"l{self.L - 1}.b2"))   # db2 of the last block
         if on_bucket_ready:
             s, e = self.layout.span("lnf_g", "bout")
             on_bucket_ready(s, e + 64)  # + the aux scalars (loss) that sit behind the last parameter
@@ -348,7 +346,7 @@ class DalleEngine:
                 sv = bufs["layers"][i]
             # dx (grad w.r.t. the block output) is dead once dx_mid has been formed in the other buffer, so the
             # block's input gradient is written back into the same storage.
-            self._block_bwd(i, bufs["xs"][i], sv, dx, dx, bufs, B)
+            self._block_bwd(i, bufs["xs"][i], sv, dx, dx, bufs, B, self.G(f"l{i - 1}.b2") if i > 0 else None)
             if on_bucket_ready:
                 s, e = self.layout.span(f"l{i}.ln1_g", f"l{i}.b2")
                 on_bucket_ready(s, e)

@@ -28,7 +28,7 @@ class GemmEpilogue(ctypes.Structure):
         ("alpha", c_f32),
         ("bias", c_vp), ("residual", c_vp), ("ldr", c_i64), ("aux", c_vp), ("ldaux", c_i64),
         ("labels", c_vp), ("part_max", c_vp), ("part_sum", c_vp), ("label_logit", c_vp), ("lse", c_vp),
-        ("n_valid", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("n_valid", ctypes.c_int32), ("reserved", ctypes.c_int32), ("colsum", c_vp),
     ]
 
 
@@ -49,6 +49,7 @@ _SIGNATURES = {
     "db200_shift_labels": [c_vp, c_vp, c_vp, c_int, c_int, c_int],
     "db200_layernorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32],
     "db200_layernorm_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int],
+    "db200_layernorm_bwd_ex": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int],
     "db200_gemm_bf16": [c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_i64, c_vp, c_i64, c_int, c_int, c_int,
                         ctypes.POINTER(GemmEpilogue)],
     "db200_gemm_ce_tiles": [c_int],

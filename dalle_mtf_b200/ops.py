@@ -34,7 +34,7 @@ GEMM_PROFILE = None
 
 def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, ldd=None, mode=L.EPI_STORE,
          alpha=1.0, bias=None, relu=False, residual=None, aux=None, split_k=1, labels=None, part_max=None,
-         part_sum=None, label_logit=None, lse=None, n_valid=0):
+         part_sum=None, label_logit=None, lse=None, n_valid=0, colsum=None):
     """D[M,N] = A[M,K] @ B[K,N] on tcgen05.  a_mn / b_mn: operand is stored with M (resp. N) contiguous.
 
     a: [M,K] (k-major) or [K,M] (mn-major);  b: [N,K] (k-major) or [K,N] (mn-major).
@@ -62,6 +62,8 @@ def gemm(a, b, out, M, N, K, *, a_mn=False, b_mn=False, lda=None, ldb=None, ldd=
     e.labels = ptr(labels)
     e.part_max, e.part_sum, e.label_logit, e.lse = ptr(part_max), ptr(part_sum), ptr(label_logit), ptr(lse)
     e.n_valid = n_valid
+    _chk(colsum, F32, "gemm colsum")
+    e.colsum = ptr(colsum)
     if out is not None:
         if mode == L.EPI_ATOMIC:
             _chk(out, F32, "gemm D (atomic)")
@@ -87,12 +89,12 @@ def linear_fwd(x, w, out, bias=None, relu=False, residual=None):
     return gemm(x, w, out, T, N, K, a_mn=False, b_mn=True, bias=bias, relu=relu, residual=residual)
 
 
-def linear_dgrad(dy, w, out, relu_mask_of=None):
-    """out[T,K] = dy[T,N] @ w[K,N]^T  (optionally masked by relu_mask_of > 0)."""
+def linear_dgrad(dy, w, out, relu_mask_of=None, colsum=None):
+    """out[T,K] = dy[T,N] @ w[K,N]^T  (optionally masked by relu_mask_of > 0; colsum[k] += sum_t out[t,k])."""
     T, N = dy.shape
     K = w.shape[0]
     if relu_mask_of is not None:
-        return gemm(dy, w, out, T, K, N, a_mn=False, b_mn=False, mode=L.EPI_RELU_BWD, aux=relu_mask_of)
+        return gemm(dy, w, out, T, K, N, a_mn=False, b_mn=False, mode=L.EPI_RELU_BWD, aux=relu_mask_of, colsum=colsum)
     return gemm(dy, w, out, T, K, N, a_mn=False, b_mn=False)
 
 
@@ -160,13 +162,14 @@ def layernorm_fwd(x, g, b, y, mean, rstd, eps=1e-5):
     return y
 
 
-def layernorm_bwd(dy, x, g, mean, rstd, dres, dx, dg, db):
+def layernorm_bwd(dy, x, g, mean, rstd, dres, dx, dg, db, dxsum=None):
+    """dxsum (optional, f32 [d]): += column sums of the produced dx (fused bias gradient of the layer below)."""
     L.require_device()
     _chk(dy, BF16, "dy"); _chk(x, BF16, "x"); _chk(dres, BF16, "dres"); _chk(dx, BF16, "dx")
-    _chk(g, F32, "g"); _chk(dg, F32, "dg"); _chk(db, F32, "db")
+    _chk(g, F32, "g"); _chk(dg, F32, "dg"); _chk(db, F32, "db"); _chk(dxsum, F32, "dxsum")
     rows, d = x.shape
-    check(L.load().db200_layernorm_bwd(stream_ptr(), ptr(dy), ptr(x), ptr(g), ptr(mean), ptr(rstd), ptr(dres),
-                                       ptr(dx), ptr(dg), ptr(db), rows, d), "layernorm_bwd")
+    check(L.load().db200_layernorm_bwd_ex(stream_ptr(), ptr(dy), ptr(x), ptr(g), ptr(mean), ptr(rstd), ptr(dres),
+                                          ptr(dx), ptr(dg), ptr(db), ptr(dxsum), rows, d), "layernorm_bwd")
     return dx
 
 

@@ -68,6 +68,11 @@ int db200_layernorm_fwd(db200_stream_t stream, const void* x_bf16, const float* 
 int db200_layernorm_bwd(db200_stream_t stream, const void* dy_bf16, const void* x_bf16, const float* g,
                         const float* mean, const float* rstd, const void* dres_bf16_or_null, void* dx_bf16, float* dg,
                         float* db, int rows, int d);
+/* same, and additionally dxsum[c] += sum_rows dx[row][c]: the bias gradient of the linear layer whose output
+ * gradient dx is (fuses the column-sum pass; dxsum may be NULL) */
+int db200_layernorm_bwd_ex(db200_stream_t stream, const void* dy_bf16, const void* x_bf16, const float* g,
+                           const float* mean, const float* rstd, const void* dres_bf16_or_null, void* dx_bf16,
+                           float* dg, float* db, float* dxsum_or_null, int rows, int d);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * K3/K5/K6/K8  bf16 GEMM on tcgen05 (TMA-fed, TMEM accumulators, fp32 accumulate):   D[M,N] = A[M,K] * B[K,N]
@@ -103,6 +108,7 @@ typedef struct db200_gemm_epilogue {
   const float* lse;      /* [M] (CE_GRAD)                                                         */
   int32_t n_valid;       /* CE_*: number of real vocabulary columns (<= N)                        */
   int32_t reserved;
+  float* colsum;         /* CE_GRAD / RELU_BWD: colsum[n] += sum_m D[m][n] (fused bias gradient) or NULL */
 } db200_gemm_epilogue;
 
 int db200_gemm_bf16(db200_stream_t stream, const void* A, int a_mn_major, int64_t lda, const void* B, int b_mn_major,

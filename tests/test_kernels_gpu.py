@@ -64,6 +64,10 @@ def test_gemm_epilogues(ops):
     dx = torch.empty(M, K, dtype=torch.bfloat16, device=DEV)
     ops.linear_dgrad(DY.to(DEV), w, dx, relu_mask_of=H.to(DEV))
     assert relmax(dx, (DY.float() @ W.float().t()) * (H.float() > 0)) < 1e-2
+    cs = torch.zeros(K, device=DEV)
+    dx2 = torch.empty_like(dx)
+    ops.linear_dgrad(DY.to(DEV), w, dx2, relu_mask_of=H.to(DEV), colsum=cs)     # fused bias gradient
+    assert torch.equal(dx2, dx) and relmax(cs, dx.float().sum(0)) < 1e-5
     T = 4096
     X, DY2 = bf(torch.randn(T, K, generator=g)), bf(torch.randn(T, N, generator=g))
     dw = torch.ones(K, N, dtype=torch.float32, device=DEV)
@@ -116,6 +120,12 @@ def test_cross_entropy_epilogues(ops):
     ref = torch.zeros(T, Vpad); ref[:, :V] = p / T
     assert relmax(dl, ref) < 1e-2
     assert (dl[:, V:] == 0).all()                                              # padded vocabulary columns stay exactly zero
+    # fused bias gradient: column sums of the bf16 values actually written
+    cs = torch.zeros(Vpad, device=DEV)
+    dl2 = torch.empty_like(dl)
+    ops.gemm(x, w, dl2, T, Vpad, d, b_mn=True, mode=L.EPI_CE_GRAD, alpha=1.0 / T, bias=bpad, labels=lab, lse=lse, n_valid=V,
+             colsum=cs)
+    assert torch.equal(dl2, dl) and relmax(cs, dl.float().sum(0)) < 1e-5
 
 
 def test_c_abi_reports_errors_instead_of_crashing(ops):
@@ -178,6 +188,10 @@ def test_layernorm_fwd_bwd(ops, d):
     ops.layernorm_bwd(dy.to(DEV), x.to(DEV), gg.to(DEV), mean, rstd, dres.to(DEV), dx, dg, db)
     assert relmax(dx, xf.grad + dres.float()) < 1e-2
     assert relmax(dg, gp.grad) < 1e-4 and relmax(db, bp.grad) < 1e-4
+    dx2, dxs = torch.empty_like(dx), torch.zeros(d, device=DEV)
+    ops.layernorm_bwd(dy.to(DEV), x.to(DEV), gg.to(DEV), mean, rstd, dres.to(DEV), dx2, torch.zeros(d, device=DEV),
+                      torch.zeros(d, device=DEV), dxsum=dxs)                    # fused column sums of dx
+    assert torch.equal(dx2, dx) and relmax(dxs, dx.float().sum(0)) < 1e-5
 
 
 def test_colsum_and_casts(ops):
