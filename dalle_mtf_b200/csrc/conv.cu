@@ -255,6 +255,76 @@ __global__ void __launch_bounds__(256) colsum_act_kernel(const T* __restrict__ x
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// First encoder layer: 4x4 stride-2 SAME convolution of the fp32 image (Cin = 3) -> bf16 activations.
+// K = 48 is far too small for the tensor pipe and the generic kernel wastes 5/6 of its 16-wide K chunks on padding,
+// so this layer gets its own kernel: one output pixel per thread, a (2*8+2) x (2*16+2) x 3 input patch and the whole
+// 4x4x3xCout kernel staged in shared memory, weights read as broadcast float4, 64 fp32 accumulators per thread,
+// each thread stores its pixel's 64 channels as one contiguous 128-byte line.  Also absorbs the fp32 -> bf16 cast of
+// the image.   Reference: the first conv_downsample of src/vae_tf/models.py:95.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int CF_TH = 8, CF_TW = 16;  // output tile per CTA (128 threads)
+__global__ void __launch_bounds__(128)
+conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  bf16* __restrict__ y, int NB, int H, int W, int Cout) {
+  extern __shared__ float cf_smem[];
+  float* sw = cf_smem;                          // [48][Cout]
+  float* sx = cf_smem + 48 * Cout;              // [(2*TH+2)][(2*TW+2)][3]
+  constexpr int PH = 2 * CF_TH + 2, PW = 2 * CF_TW + 2;
+  const int Ho = H / 2, Wo = W / 2;
+  const int tiles_w = (Wo + CF_TW - 1) / CF_TW, tiles_h = (Ho + CF_TH - 1) / CF_TH;
+  int t = blockIdx.x;
+  const int tw = t % tiles_w; t /= tiles_w;
+  const int th = t % tiles_h; t /= tiles_h;
+  const int n = t;
+  const int oy0 = th * CF_TH, ox0 = tw * CF_TW;
+  for (int i = threadIdx.x; i < 48 * Cout; i += 128) sw[i] = w[i];
+  const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;  // SAME padding for k=4, s=2: one pixel before
+  for (int i = threadIdx.x; i < PH * PW * 3; i += 128) {
+    const int c = i % 3, px = (i / 3) % PW, py = i / (3 * PW);
+    const int iy = iy0 + py, ix = ix0 + px;
+    sx[i] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? x[(((long long)n * H + iy) * W + ix) * 3 + c] : 0.f;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x / CF_TW, lx = threadIdx.x % CF_TW;
+  const int oy = oy0 + ly, ox = ox0 + lx;
+  float in[48];
+#pragma unroll
+  for (int kh = 0; kh < 4; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 4; ++kw)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) in[(kh * 4 + kw) * 3 + c] = sx[((2 * ly + kh) * PW + (2 * lx + kw)) * 3 + c];
+  for (int c0 = 0; c0 < Cout; c0 += 64) {
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = bias ? bias[c0 + j] : 0.f;
+#pragma unroll
+    for (int k = 0; k < 48; ++k) {
+      const float xv = in[k];
+      const float4* wr = reinterpret_cast<const float4*>(sw + k * Cout + c0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 wv = wr[j];  // same address for every thread: smem broadcast
+        acc[j * 4 + 0] = fmaf(xv, wv.x, acc[j * 4 + 0]);
+        acc[j * 4 + 1] = fmaf(xv, wv.y, acc[j * 4 + 1]);
+        acc[j * 4 + 2] = fmaf(xv, wv.z, acc[j * 4 + 2]);
+        acc[j * 4 + 3] = fmaf(xv, wv.w, acc[j * 4 + 3]);
+      }
+    }
+    if (oy < Ho && ox < Wo) {
+      bf16* dst = y + (((long long)n * Ho + oy) * Wo + ox) * Cout + c0;
+#pragma unroll
+      for (int j = 0; j < 64; j += 8) {
+        uint4 q;
+        q.x = pack_bf16x2(acc[j], acc[j + 1]); q.y = pack_bf16x2(acc[j + 2], acc[j + 3]);
+        q.z = pack_bf16x2(acc[j + 4], acc[j + 5]); q.w = pack_bf16x2(acc[j + 6], acc[j + 7]);
+        *reinterpret_cast<uint4*>(dst + j) = q;
+      }
+    }
+  }
+}
+
 static int launch_gemm(cudaStream_t stream, const ConvGemmParams& p, bool act_f32) {
   const long long M = (long long)p.NB * p.OH * p.OW;
   dim3 grid((unsigned)((M + 63) / 64), (unsigned)((p.Nn + 63) / 64));
@@ -503,4 +573,26 @@ extern "C" int db200_rowmatmul_tn_f32(db200_stream_t stream_, const float* a, co
   p.a_stride = N; p.b_stride = 1;
   p.P = a; p.Q = b; p.dw = out_accum;
   return launch_wgrad(stream, p, true);
+}
+
+// y (bf16 NHWC) = conv4x4/s2/SAME(x fp32 NHWC [N][H][W][3], w f32 [4][4][3][Cout]) + bias.   Cout % 64 == 0.
+extern "C" int db200_conv2d_first_fwd(db200_stream_t stream_, const float* x, const float* w, const float* bias,
+                                      void* y_bf16, int N, int H, int W, int Cout) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(x && w && y_bf16 && N > 0 && H > 0 && W > 0, DB200_E_INVALID, "conv2d_first_fwd: bad arguments");
+  DB200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cout % 64 == 0 && Cout <= 256, DB200_E_UNSUPPORTED,
+                "conv2d_first_fwd: needs even H, W and Cout in {64,128,192,256}");
+  DB200_REQUIRE(aligned16(w) && aligned16(y_bf16), DB200_E_ALIGN, "conv2d_first_fwd: unaligned pointer");
+  const int Ho = H / 2, Wo = W / 2;
+  const int tiles = ((Wo + CF_TW - 1) / CF_TW) * ((Ho + CF_TH - 1) / CF_TH) * N;
+  const size_t smem = (size_t)(48 * Cout + (2 * CF_TH + 2) * (2 * CF_TW + 2) * 3) * sizeof(float);
+  if (smem > 48 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      DB200_CUDA(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr = true;
+    }
+  }
+  conv_first_kernel<<<tiles, 128, smem, stream>>>(x, w, bias, reinterpret_cast<bf16*>(y_bf16), N, H, W, Cout);
+  return check_launch("conv_first_kernel");
 }

@@ -53,9 +53,12 @@ __global__ void embed_bwd_wte_kernel(const int* __restrict__ ids, const bf16* __
     if (id < 0 || id >= V) continue;
     float g[8];
     unpack8(*reinterpret_cast<const uint4*>(dx + (long long)t * d + c), g);
-    float* dst = dwte + (long long)id * d + c;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(dst + j, g[j]);
+    float* dst = dwte + (long long)id * d + c;  // 32-byte aligned: two REDG.E.ADD.F32x4
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g[0]), "f"(g[1]), "f"(g[2]), "f"(g[3])
+                 : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(g[4]), "f"(g[5]), "f"(g[6]),
+                 "f"(g[7])
+                 : "memory");
   }
 }
 

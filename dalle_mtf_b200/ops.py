@@ -262,6 +262,16 @@ def conv2d_fwd_tc(c, x, w_bf16, bias, residual, y):
     return y
 
 
+def conv2d_first_fwd(x_f32, w, bias, y_bf16):
+    """First encoder layer: fp32 image [N,H,W,3] -> bf16 [N,H/2,W/2,Cout] (4x4, stride 2, SAME)."""
+    L.require_device()
+    _chk(x_f32, F32, "x"); _chk(w, F32, "w"); _chk(bias, F32, "bias"); _chk(y_bf16, BF16, "y")
+    N, H, W_, _ = x_f32.shape
+    check(L.load().db200_conv2d_first_fwd(stream_ptr(), ptr(x_f32), ptr(w), ptr(bias), ptr(y_bf16), N, H, W_,
+                                          w.shape[-1]), "conv2d_first_fwd")
+    return y_bf16
+
+
 def conv_tc_supported(c):
     return (not c.transposed and not c.act_f32 and c.Cin % 64 == 0 and c.Cout % 8 == 0 and c.KH * c.KW <= 16 and
             (c.stride == 1 or (c.stride == 2 and c.H % 2 == 0 and c.W % 2 == 0)))

@@ -201,15 +201,21 @@ class VaeEngine:
         self._conv_fwd(self._desc(B, res, ch, ch, 3, 1), sv["t"], pre + "conv_out", x, sv["out"])
         return sv["out"]
 
-    def encode_logits(self, img):
+    def encode_logits(self, img, for_training=False):
         """DiscreteVAE.encoder (src/vae_tf/models.py:81-120): img fp32 NHWC [B,H,W,C] -> fp32 logits [B*h*w, K]."""
         B = img.shape[0]
         self._alloc(B)
         b = self._b
-        x = self._to_act(img, b["x_in"])
+        # bf16 inference path: the first layer reads the fp32 image directly (dedicated kernel, cast fused)
+        first_direct = (self.use_bf16 and not for_training and self.C == 3 and self.enc[0][0] == "down" and
+                        self.enc[0][3] % 64 == 0 and self.H % 2 == 0)
+        x = img if first_direct else self._to_act(img, b["x_in"])
         self._x0 = x
-        for (kind, name, cin, ch, res), sv in zip(self.enc, b["enc"]):
-            if kind == "down":
+        for li, ((kind, name, cin, ch, res), sv) in enumerate(zip(self.enc, b["enc"])):
+            if li == 0 and first_direct:
+                ops.conv2d_first_fwd(img, self.P(name + "/kernel"), self.P(name + "/bias"), sv["out"])
+                x = sv["out"]
+            elif kind == "down":
                 self._conv_fwd(self._desc(B, res, cin, ch, 4, 2), x, name, None, sv["out"])
                 x = sv["out"]
             else:
@@ -231,7 +237,7 @@ class VaeEngine:
         """DiscreteVAE.forward(return_recon_loss=True) (src/vae_tf/models.py:165-184).  u: fp32 uniform noise
         [B*h*w, K] in [1e-9, 1) or None (no noise).  Adds sum((img-out)^2)/numel into loss_accum; returns recon."""
         B = img.shape[0]
-        logits = self.encode_logits(img)
+        logits = self.encode_logits(img, for_training=True)
         b = self._b
         rows = B * self.hw * self.hw
         self._tau = float(temperature)

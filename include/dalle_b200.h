@@ -186,6 +186,10 @@ int db200_conv2d_fwd(db200_stream_t stream, const db200_conv_desc* c, const void
  * Returns DB200_E_UNSUPPORTED otherwise (callers choose the direct kernel explicitly; there is no silent fallback). */
 int db200_conv2d_fwd_tc(db200_stream_t stream, const db200_conv_desc* c, const void* x_bf16, const void* w_bf16,
                         const float* bias_or_null, const void* residual_bf16_or_null, void* y_bf16);
+/* First encoder layer (Cin = 3, 4x4, stride 2, SAME) straight from the fp32 image to bf16 activations:
+ * dedicated CUDA-core kernel (K = 48 is too small for the tensor pipe).  x: f32 [N][H][W][3], w: f32 [4][4][3][Cout]. */
+int db200_conv2d_first_fwd(db200_stream_t stream, const float* x, const float* w, const float* bias_or_null,
+                           void* y_bf16, int N, int H, int W, int Cout);
 int db200_conv2d_dgrad(db200_stream_t stream, const db200_conv_desc* c, const void* dy, const float* w,
                        const void* x_for_relu_mask_or_null, const void* dres_or_null, void* dx);
 int db200_conv2d_wgrad(db200_stream_t stream, const db200_conv_desc* c, const void* x, const void* dy, float* dw,

@@ -206,6 +206,20 @@ def test_vae_engine_fp32_matches_oracle_exactly_enough(convblocks, K, size, B, h
         assert relfro(after[k] - p[k], ref - p[k]) < 1e-3
 
 
+@pytest.mark.parametrize("N,H,Cout", [(2, 16, 64), (3, 24, 128), (1, 256, 64)])
+def test_first_layer_conv_kernel(N, H, Cout):
+    from dalle_mtf_b200 import ops
+    from oracle import vae as OV
+    g = torch.Generator().manual_seed(H)
+    x = torch.rand(N, H, H, 3, generator=g) * 2 - 1
+    w = torch.randn(4, 4, 3, Cout, generator=g) * 0.2
+    bias = torch.randn(Cout, generator=g) * 0.1
+    y = OV.conv2d_same(x, w, bias, 2)
+    yd = torch.zeros(N, H // 2, H // 2, Cout, dtype=torch.bfloat16, device=DEV)
+    ops.conv2d_first_fwd(x.to(DEV), w.to(DEV), bias.to(DEV), yd)
+    assert relfro(yd, y) < 5e-3      # fp32 math, bf16 output rounding only
+
+
 def test_bf16_tensor_core_tokenizer_agrees_with_fp32_oracle_up_to_near_ties():
     from dalle_mtf_b200.vae_engine import VaeEngine
     from oracle import vae as OV
