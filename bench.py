@@ -81,9 +81,14 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
 
-    def stop(self):
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken inside [t0, t1] (the timed region); if the region was shorter than the sampling
+        period, fall back to every sample taken under load (warm-up included)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -91,8 +96,10 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             pass
+        inside = [s for ts, s in self.samples if t0 is not None and t0 <= ts <= t1]
+        window = "timed region" if inside else "warm-up + timed region"
         sm, mx, reasons = [], None, set()
-        for s in self.samples:
+        for s in (inside or [s for _, s in self.samples]):
             f = [x.strip() for x in s.split(",")]
             if len(f) < 8:
                 continue
@@ -105,7 +112,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def usable_cores():
@@ -161,11 +168,39 @@ def cpu_reference_step_rate(steps, warmup, seqs, label):
         f"fwd+bwd+clip+Adam, reference-faithful graph (one-hot embedding/CE, materialised [S,S] attention)"
 
 
+def vae_example_rate(dp, device, steps=20, warmup=5):
+    """Second half of BASELINE.json's metric: discrete-VAE training images/s on configs/vae_example.json
+    (CIFAR-10-shaped 32x32 inputs, 3-stage VAE, batch 32, fp32, hard Gumbel) through vae_model_fn's train_op."""
+    from dalle_mtf_b200.input_fns import vae_input_fn
+    from dalle_mtf_b200.model_fns import TRAIN, vae_model_fn
+    from dalle_mtf_b200.utils import fetch_model_params
+    p = fetch_model_params(os.path.join(ROOT, "configs", "vae_example.json"))
+    p["_dp"] = dp
+    p["model_path"] = None
+    it = iter(vae_input_fn(p))
+    batches = [next(it)[0].to(device) for _ in range(4)]
+    spec = vae_model_fn(batches[0], batches[0], TRAIN, p)
+    for i in range(warmup):
+        spec.train_op(batches[i % 4])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        spec.train_op(batches[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"metric": "vae_imgs_per_sec", "value": p["train_batch_size"] * 1000.0 / ms, "unit": "imgs/s",
+            "ms_per_step": ms, "config": "vae_example: 32x32x3, convblocks [[3,64],[3,128],[3,256]], K=512, batch 32, "
+            "fp32 activations, hard Gumbel; fwd+bwd+Adam", "loss": float(spec.loss_sum.item()) * spec.loss_scale}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     seqs = 2
+    args.steps = min(args.steps, 3)      # bounded: the whole run must end within a few minutes
     value, ms, cores, sample = cpu_reference_step_rate(args.steps, min(args.warmup, 1), seqs, "bounded sample")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -228,14 +263,15 @@ def main():
         return dp.max_over_ranks(e0.elapsed_time(e1))
 
     # ---- device-resident inputs: `value`
+    sampler.start()                      # nvidia-smi needs a moment to start: launch it before the warm-up
     timed(dev_batches, args.warmup, False)
-    sampler.start()
     ops.GEMM_PROFILE = []
     n0 = L.launch_count()
+    t_begin = sampler.mark()
     ms_total = timed(dev_batches, args.steps, False)
+    t_end = sampler.mark()
     launches = L.launch_count() - n0
     prof, ops.GEMM_PROFILE = ops.GEMM_PROFILE, None
-    clocks = sampler.stop()
     ms_per_step = ms_total / args.steps
     value = tokens_per_step * 1000.0 / ms_per_step
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in prof)
@@ -255,6 +291,8 @@ def main():
     # ---- host inputs through the public API: `e2e`
     timed(host_batches, 2, True)
     ms_e2e = timed(host_batches, args.steps, True) / args.steps
+    clocks = sampler.stop(t_begin, t_end)
+    vae_line = vae_example_rate(dp, device) if args.gpus == 1 else None
     f0, l0 = host_batches[0]
     h2d = f0.numel() * f0.element_size() + l0.numel() * l0.element_size()
 
@@ -283,6 +321,8 @@ def main():
                          "peak_kind": f"bf16_tflops_sustained ({peak_kind})", "traffic": None,
                          "launches_per_step": len(prof) / args.steps, "share_of_step": gemm_ms / ms_total},
         }
+        if vae_line is not None:
+            line["vae"] = vae_line
         if args.gpus == 1 and not args.no_cpu_baseline:
             v, ms, cores, sample = cpu_reference_step_rate(2, 1, 2, "bounded sample")
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
