@@ -64,6 +64,8 @@ _SIGNATURES = {
                         c_f32, c_int, c_int],
     "db200_conv2d_fwd": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp],
     "db200_conv2d_fwd_tc": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp],
+    "db200_conv2d_dgrad_tc": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp],
+    "db200_conv2d_wgrad_tc": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp],
     "db200_conv2d_first_fwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int],
     "db200_conv2d_dgrad": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp],
     "db200_conv2d_wgrad": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp],

@@ -272,9 +272,39 @@ def conv2d_first_fwd(x_f32, w, bias, y_bf16):
     return y_bf16
 
 
+def _tc_geometry_ok(c):
+    if c.act_f32 or c.KH * c.KW > 16:
+        return False
+    if c.transposed:
+        return c.KH == 4 and c.KW == 4 and c.stride == 2
+    return c.stride == 1 or (c.stride == 2 and c.H % 2 == 0 and c.W % 2 == 0)
+
+
 def conv_tc_supported(c):
-    return (not c.transposed and not c.act_f32 and c.Cin % 64 == 0 and c.Cout % 8 == 0 and c.KH * c.KW <= 16 and
-            (c.stride == 1 or (c.stride == 2 and c.H % 2 == 0 and c.W % 2 == 0)))
+    """forward (conv or conv-transpose) on tcgen05"""
+    return _tc_geometry_ok(c) and c.Cin % 64 == 0 and c.Cout % 8 == 0
+
+
+def conv_dgrad_tc_supported(c):
+    return _tc_geometry_ok(c) and c.Cout % 64 == 0 and c.Cin % 8 == 0
+
+
+def conv_wgrad_tc_supported(c):
+    return _tc_geometry_ok(c) and c.Cin % 64 == 0 and c.Cout % 64 == 0
+
+
+def conv2d_dgrad_tc(c, dy, w_bf16, x_mask, dres, dx):
+    L.require_device()
+    _chk(dy, BF16, "dy"); _chk(w_bf16, BF16, "w"); _chk(x_mask, BF16, "x_mask"); _chk(dres, BF16, "dres"); _chk(dx, BF16, "dx")
+    check(L.load().db200_conv2d_dgrad_tc(stream_ptr(), ctypes.byref(c), ptr(dy), ptr(w_bf16), ptr(x_mask), ptr(dres),
+                                         ptr(dx)), "conv2d_dgrad_tc")
+    return dx
+
+
+def conv2d_wgrad_tc(c, x, dy, dw):
+    L.require_device()
+    _chk(x, BF16, "x"); _chk(dy, BF16, "dy"); _chk(dw, F32, "dw")
+    check(L.load().db200_conv2d_wgrad_tc(stream_ptr(), ctypes.byref(c), ptr(x), ptr(dy), ptr(dw)), "conv2d_wgrad_tc")
 
 
 def conv2d_dgrad(c, dy, w, x_mask, dres, dx):

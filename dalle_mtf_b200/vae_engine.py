@@ -104,9 +104,20 @@ class VaeEngine:
         """One forward convolution: tcgen05 implicit GEMM when the layer qualifies (bf16, Cin % 64 == 0), else the
         shared-memory-staged direct kernel (first layer with 3 input channels, transposed convs, fp32 mode)."""
         if self.use_bf16 and ops.conv_tc_supported(dsc):
-            return ops.conv2d_fwd_tc(dsc, x, self.W16(name + "/kernel").view(-1, dsc.Cout), self.P(name + "/bias"),
-                                     residual, y)
+            return ops.conv2d_fwd_tc(dsc, x, self.W16(name + "/kernel"), self.P(name + "/bias"), residual, y)
         return ops.conv2d_fwd(dsc, x, self.P(name + "/kernel"), self.P(name + "/bias"), residual, y)
+
+    def _conv_dgrad(self, dsc, dy, name, mask, dres, dx):
+        if self.use_bf16 and ops.conv_dgrad_tc_supported(dsc):
+            return ops.conv2d_dgrad_tc(dsc, dy, self.W16(name + "/kernel"), mask, dres, dx)
+        return ops.conv2d_dgrad(dsc, dy, self.P(name + "/kernel"), mask, dres, dx)
+
+    def _conv_wgrad(self, dsc, x, dy, name):
+        if self.use_bf16 and ops.conv_wgrad_tc_supported(dsc):
+            ops.conv2d_wgrad_tc(dsc, x, dy, self.G(name + "/kernel"))
+            ops.colsum(dy.view(-1, dsc.Cout), self.G(name + "/bias"))       # bias gradient
+        else:
+            ops.conv2d_wgrad(dsc, x, dy, self.G(name + "/kernel"), self.G(name + "/bias"))
 
     def load_params(self, named):
         self.master.zero_()
@@ -248,8 +259,7 @@ class VaeEngine:
         self._z = x
         for (kind, name, cin, ch, res), sv in zip(self.dec, b["dec"]):
             if kind == "up":
-                ops.conv2d_fwd(self._desc(B, res, cin, ch, 4, 2, transposed=True), x, self.P(name + "/kernel"),
-                               self.P(name + "/bias"), None, sv["out"])
+                self._conv_fwd(self._desc(B, res, cin, ch, 4, 2, transposed=True), x, name, None, sv["out"])
                 x = sv["out"]
             else:
                 x = self._res_fwd(B, name, ch, res, x, sv)
@@ -269,12 +279,12 @@ class VaeEngine:
     def _res_bwd(self, B, pre, ch, res, x_in, sv, dx, scratch):
         """Backward of x_out = x_in + conv_out(t), t = relu(conv_in(x_in)); dx is overwritten with d(x_in)."""
         d_out = self._desc(B, res, ch, ch, 3, 1)
-        ops.conv2d_wgrad(d_out, sv["t"], dx, self.G(pre + "conv_out/kernel"), self.G(pre + "conv_out/bias"))
+        self._conv_wgrad(d_out, sv["t"], dx, pre + "conv_out")
         dt = scratch
-        ops.conv2d_dgrad(d_out, dx, self.P(pre + "conv_out/kernel"), sv["t"], None, dt)      # masked by t > 0
-        ops.conv2d_wgrad(d_out, x_in, dt, self.G(pre + "conv_in/kernel"), self.G(pre + "conv_in/bias"))
-        # d(x_in) = dgrad(conv_in)(dt) + dx: read dx as the residual and write the result over dt's partner
-        ops.conv2d_dgrad(d_out, dt, self.P(pre + "conv_in/kernel"), None, dx, dx)
+        self._conv_dgrad(d_out, dx, pre + "conv_out", sv["t"], None, dt)                     # masked by t > 0
+        self._conv_wgrad(d_out, x_in, dt, pre + "conv_in")
+        # d(x_in) = dgrad(conv_in)(dt) + dx: read dx as the residual and write the result in place
+        self._conv_dgrad(d_out, dt, pre + "conv_in", None, dx, dx)
         return dx
 
     def backward(self, grad_scale=1.0):
@@ -295,9 +305,9 @@ class VaeEngine:
         for (kind, name, cin, ch, res), sv, x_in in reversed(list(zip(self.dec, b["dec"], inputs))):
             if kind == "up":
                 dsc = self._desc(B, res, cin, ch, 4, 2, transposed=True)
-                ops.conv2d_wgrad(dsc, x_in, dx, self.G(name + "/kernel"), self.G(name + "/bias"))
+                self._conv_wgrad(dsc, x_in, dx, name)
                 nxt = b["gscratch"][tuple(x_in.shape)][0]
-                ops.conv2d_dgrad(dsc, dx, self.P(name + "/kernel"), None, None, nxt)
+                self._conv_dgrad(dsc, dx, name, None, None, nxt)
                 dx = nxt
             else:
                 pair = b["gscratch"][tuple(x_in.shape)]
@@ -320,10 +330,10 @@ class VaeEngine:
         for li, ((kind, name, cin, ch, res), sv, x_in) in reversed(list(enumerate(zip(self.enc, b["enc"], inputs)))):
             if kind == "down":
                 dsc = self._desc(B, res, cin, ch, 4, 2)
-                ops.conv2d_wgrad(dsc, x_in, dx, self.G(name + "/kernel"), self.G(name + "/bias"))
+                self._conv_wgrad(dsc, x_in, dx, name)
                 if li > 0:  # the gradient w.r.t. the image itself is never needed
                     nxt = b["gscratch"][tuple(x_in.shape)][0]
-                    ops.conv2d_dgrad(dsc, dx, self.P(name + "/kernel"), None, None, nxt)
+                    self._conv_dgrad(dsc, dx, name, None, None, nxt)
                     dx = nxt
             else:
                 pair = b["gscratch"][tuple(x_in.shape)]

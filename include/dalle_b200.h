@@ -181,11 +181,19 @@ typedef struct db200_conv_desc {
 
 int db200_conv2d_fwd(db200_stream_t stream, const db200_conv_desc* c, const void* x, const float* w,
                      const float* bias_or_null, const void* residual_or_null, void* y);
-/* Tensor-core forward (tcgen05 implicit GEMM, 4-D TMA boxes per filter tap, no im2col): bf16 NHWC activations,
- * bf16 HWIO kernel, f32 bias, optional bf16 residual; needs Cin % 64 == 0, Cout % 8 == 0, stride 1 or 2 (even H, W).
- * Returns DB200_E_UNSUPPORTED otherwise (callers choose the direct kernel explicitly; there is no silent fallback). */
+/* Tensor-core paths (tcgen05 implicit GEMM; 4-D TMA boxes per filter tap, no im2col), bf16 NHWC activations, bf16
+ * kernels (same memory layout as the f32 kernels: HWIO, or [kh][kw][out][in] for conv2d_transpose), f32 bias / dw.
+ *   fwd_tc   : conv or conv2d_transpose forward; needs Cin % 64 == 0, Cout % 8 == 0
+ *   dgrad_tc : needs Cout % 64 == 0, Cin % 8 == 0; optional ReLU mask (dx *= x_mask > 0) and residual-gradient add
+ *   wgrad_tc : dw (f32) += ...; needs Cin % 64 == 0 and Cout % 64 == 0; bias gradient = db200_colsum_bf16 of dy
+ * Stride 1 or 2 (even H, W).  Unsupported shapes return DB200_E_UNSUPPORTED: callers pick the direct kernels
+ * explicitly, there is no silent fallback. */
 int db200_conv2d_fwd_tc(db200_stream_t stream, const db200_conv_desc* c, const void* x_bf16, const void* w_bf16,
                         const float* bias_or_null, const void* residual_bf16_or_null, void* y_bf16);
+int db200_conv2d_dgrad_tc(db200_stream_t stream, const db200_conv_desc* c, const void* dy_bf16, const void* w_bf16,
+                          const void* x_mask_bf16_or_null, const void* dres_bf16_or_null, void* dx_bf16);
+int db200_conv2d_wgrad_tc(db200_stream_t stream, const db200_conv_desc* c, const void* x_bf16, const void* dy_bf16,
+                          float* dw);
 /* First encoder layer (Cin = 3, 4x4, stride 2, SAME) straight from the fp32 image to bf16 activations:
  * dedicated CUDA-core kernel (K = 48 is too small for the tensor pipe).  x: f32 [N][H][W][3], w: f32 [4][4][3][Cout]. */
 int db200_conv2d_first_fwd(db200_stream_t stream, const float* x, const float* w, const float* bias_or_null,

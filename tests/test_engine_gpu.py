@@ -167,6 +167,65 @@ def test_tensor_core_conv_forward_bf16(N, H, Cin, Cout, k, stride, relu, res):
     assert relfro(yd, y) < 1e-2
 
 
+@pytest.mark.parametrize("N,H,Cin,Cout,k,stride,transposed", [
+    (2, 16, 64, 64, 3, 1, False), (2, 16, 128, 64, 3, 1, False), (3, 12, 64, 128, 3, 1, False),
+    (2, 16, 64, 128, 4, 2, False), (2, 8, 128, 64, 4, 2, True), (5, 4, 256, 128, 4, 2, True),
+    (1, 32, 256, 256, 3, 1, False)])
+def test_tensor_core_conv_training_kernels_bf16(N, H, Cin, Cout, k, stride, transposed):
+    """conv-transpose forward, dgrad (with ReLU mask + residual-gradient add) and wgrad on tcgen05 vs autograd."""
+    from dalle_mtf_b200 import ops
+    from oracle import vae as OV
+    g = torch.Generator().manual_seed(Cin * 7 + Cout + H)
+    bf = lambda t: t.to(torch.bfloat16)
+    x = bf(torch.randn(N, H, H, Cin, generator=g))
+    wshape = (k, k, Cout, Cin) if transposed else (k, k, Cin, Cout)
+    w = bf(torch.randn(*wshape, generator=g) * (k * k * Cin) ** -0.5)
+    bias = torch.randn(Cout, generator=g) * 0.1
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    y = OV.conv2d_transpose_same(xr, wr, bias) if transposed else OV.conv2d_same(xr, wr, bias, stride)
+    dy = bf(torch.randn(y.shape, generator=g))
+    y.backward(dy.float())
+    c = ops.conv_desc(N, H, H, Cin, Cout, k, k, stride, transposed=transposed, act_f32=False)
+    xd, wd, dyd = x.to(DEV), w.to(DEV), dy.to(DEV)
+    yd = torch.zeros(y.shape, dtype=torch.bfloat16, device=DEV)
+    ops.conv2d_fwd_tc(c, xd, wd, bias.to(DEV), None, yd)
+    assert relfro(yd, y) < 1e-2
+    mask = bf(torch.randn(x.shape, generator=g))
+    dres = bf(torch.randn(x.shape, generator=g))
+    dxd = torch.zeros(x.shape, dtype=torch.bfloat16, device=DEV)
+    ops.conv2d_dgrad_tc(c, dyd, wd, mask.to(DEV), dres.to(DEV), dxd)
+    assert relfro(dxd, xr.grad * (mask.float() > 0) + dres.float()) < 1e-2
+    dwd = torch.ones(wshape, device=DEV)
+    ops.conv2d_wgrad_tc(c, xd, dyd, dwd)
+    assert relfro(dwd, 1.0 + wr.grad) < 1e-4        # bf16 inputs are exact in the reference too; fp32 accumulate
+
+
+def test_vae_engine_bf16_training_step_on_tensor_cores():
+    """Whole VAE step with bf16 activations (tcgen05 conv fwd/dgrad/wgrad): loss and gradients vs the fp32 oracle."""
+    from dalle_mtf_b200.vae_engine import VaeEngine
+    from oracle import vae as OV
+    cb, K, size, B = [[2, 64], [2, 128]], 128, 32, 4
+    g = torch.Generator().manual_seed(77)
+    p = OV.init_params(cb, K, seed=5)
+    img = torch.rand(B, size, size, 3, generator=g) * 2 - 1
+    hw = size // 4
+    u = torch.rand(B * hw * hw, K, generator=g).clamp_(1e-9, 1.0)
+    loss, out, logits, grads = OV.loss_and_grads(p, img, u.view(B, hw, hw, K), cb, 1.0, False)
+    _, _, _, g16 = OV.loss_and_grads(p, img, u.view(B, hw, hw, K), cb, 1.0, False, bf16=True)
+    eng = VaeEngine(K, size, cb, use_bf16=True)
+    eng.load_params(p)
+    eng.zero_grads()
+    acc = torch.zeros(1, device=DEV)
+    eng.forward(img.to(DEV), u.to(DEV), 1.0, False, loss_accum=acc)
+    eng.backward()
+    torch.cuda.synchronize()
+    assert relfro(acc, loss.reshape(1)) < 2e-2
+    eg = eng.export_params(eng.grads)
+    for k in grads:   # no worse than the reference's own bf16 policy (+ slack)
+        e_engine, e_ref = relfro(eg[k], grads[k]), relfro(g16[k], grads[k])
+        assert e_engine <= 1.5 * e_ref + 2e-2, (k, e_engine, e_ref)
+
+
 @pytest.mark.parametrize("convblocks,K,size,B,hard,tau", [
     ([[2, 32], [2, 64]], 64, 16, 4, True, 1.0), ([[2, 32], [2, 64]], 64, 16, 4, False, 0.5),
     ([[3, 64], [3, 128], [3, 256]], 512, 32, 8, True, 1.0)])          # last = vae_example geometry
