@@ -168,15 +168,17 @@ def cpu_reference_step_rate(steps, warmup, seqs, label):
         f"fwd+bwd+clip+Adam, reference-faithful graph (one-hot embedding/CE, materialised [S,S] attention)"
 
 
-def vae_example_rate(dp, device, steps=20, warmup=5):
-    """Second half of BASELINE.json's metric: discrete-VAE training images/s on configs/vae_example.json
-    (CIFAR-10-shaped 32x32 inputs, 3-stage VAE, batch 32, fp32, hard Gumbel) through vae_model_fn's train_op."""
+def vae_example_rate(dp, device, steps=20, warmup=5, config="vae_example", per_gpu_batch=None):
+    """Second half of BASELINE.json's metric: discrete-VAE training images/s through vae_model_fn's train_op.
+    Default: configs/vae_example.json (CIFAR-10-shaped 32x32 inputs, 3-stage VAE, batch 32, fp32, hard Gumbel)."""
     from dalle_mtf_b200.input_fns import vae_input_fn
     from dalle_mtf_b200.model_fns import TRAIN, vae_model_fn
     from dalle_mtf_b200.utils import fetch_model_params
-    p = fetch_model_params(os.path.join(ROOT, "configs", "vae_example.json"))
+    p = fetch_model_params(os.path.join(ROOT, "configs", config + ".json"))
     p["_dp"] = dp
     p["model_path"] = None
+    if per_gpu_batch:
+        p["train_batch_size"] = per_gpu_batch * dp.world
     it = iter(vae_input_fn(p))
     batches = [next(it)[0].to(device) for _ in range(4)]
     spec = vae_model_fn(batches[0], batches[0], TRAIN, p)
@@ -191,8 +193,11 @@ def vae_example_rate(dp, device, steps=20, warmup=5):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     return {"metric": "vae_imgs_per_sec", "value": p["train_batch_size"] * 1000.0 / ms, "unit": "imgs/s",
-            "ms_per_step": ms, "config": "vae_example: 32x32x3, convblocks [[3,64],[3,128],[3,256]], K=512, batch 32, "
-            "fp32 activations, hard Gumbel; fwd+bwd+Adam", "loss": float(spec.loss_sum.item()) * spec.loss_scale}
+            "ms_per_step": ms,
+            "config": f"{config}: {p['dataset']['image_size']}^2x3, convblocks {p['convblocks']}, K={p['num_tokens']}, "
+                      f"global batch {p['train_batch_size']}, {'bf16' if p.get('use_bf16') else 'fp32'} activations, "
+                      f"{'hard' if p.get('train_gumbel_hard') else 'soft'} Gumbel; fwd+bwd+Adam",
+            "loss": float(spec.loss_sum.item()) * spec.loss_scale}
 
 
 def run_reference(args):
@@ -223,6 +228,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vae-coco", action="store_true",
+                    help="measure configs/vae_coco_b200.json (256x256, K=8192, bf16, 16 images per GPU) instead")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -239,6 +246,14 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={dp.world}: launch with torch.distributed.run")
     L.require_device()
     device = torch.device("cuda", torch.cuda.current_device())
+    if args.vae_coco:
+        line = vae_example_rate(dp, device, steps=args.steps, warmup=args.warmup, config="vae_coco_b200",
+                                per_gpu_batch=16)
+        line.update({"n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup})
+        if dp.rank == 0:
+            print(json.dumps(line), flush=True)
+        dp.shutdown()
+        return 0
     params = load_params(args.gpus)
     params["_dp"] = dp
     it = iter(dalle_input_fn(params))

@@ -333,7 +333,93 @@ static int launch_gemm(cudaStream_t stream, const ConvGemmParams& p, bool act_f3
   return check_launch("conv_gemm_kernel");
 }
 
+// wgrad when one side has <= 4 channels (the RGB image on the first layer, the RGB output of the last 1x1 conv):
+// the generic 64x64 outer-product tile would waste 94 % of its FMAs.  Here a CTA owns (tap, 64 channels of the wide
+// side, pixel split); thread (c = tid & 63, lane-group = tid >> 6) streams pixels (coalesced over c) and keeps
+// <= 4 accumulators; one smem reduction + <= 256 atomics per CTA.  HBM-bound.
+struct SkinnyWgradParams {
+  int NB, OH, OW;
+  int wH, wW, wC, w_stride;   // wide tensor (64-channel slices)
+  int nH, nW, nC, n_stride;   // narrow tensor (nC <= 4)
+  int ntaps, splits;
+  WgradTap taps[MAX_TAPS];    // pd* -> wide tensor offsets, qd* -> narrow tensor offsets
+  long long wide_stride, narrow_stride;  // element strides of dw along the wide / narrow channel index
+  const void* Wd;
+  const void* Nr;
+  float* dw;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_wgrad_skinny_kernel(const SkinnyWgradParams p) {
+  __shared__ float red[4][64][4];
+  const int c = threadIdx.x & 63, pl = threadIdx.x >> 6;
+  const int c0 = blockIdx.x * 64;
+  const int t = blockIdx.y % p.ntaps, split = blockIdx.y / p.ntaps;
+  const WgradTap tap = p.taps[t];
+  const long long M = (long long)p.NB * p.OH * p.OW;
+  const long long per = (M + p.splits - 1) / p.splits;
+  const long long mbeg = split * per, mend = (mbeg + per < M) ? mbeg + per : M;
+  const T* Wd = reinterpret_cast<const T*>(p.Wd);
+  const T* Nr = reinterpret_cast<const T*>(p.Nr);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool c_ok = c0 + c < p.wC;
+  for (long long m = mbeg + pl; m < mend; m += 4) {
+    const int ox = (int)(m % p.OW);
+    const int oy = (int)((m / p.OW) % p.OH);
+    const int n = (int)(m / ((long long)p.OW * p.OH));
+    const int wy = oy * p.w_stride + tap.pdy, wx = ox * p.w_stride + tap.pdx;
+    const int ny = oy * p.n_stride + tap.qdy, nx = ox * p.n_stride + tap.qdx;
+    if (wy < 0 || wy >= p.wH || wx < 0 || wx >= p.wW || ny < 0 || ny >= p.nH || nx < 0 || nx >= p.nW) continue;
+    const float wv = c_ok ? ldf<T>(Wd + (((long long)n * p.wH + wy) * p.wW + wx) * p.wC + c0 + c) : 0.f;
+    const T* nr = Nr + (((long long)n * p.nH + ny) * p.nW + nx) * p.nC;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < p.nC) acc[j] = fmaf(wv, ldf<T>(nr + j), acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[pl][c][j] = acc[j];
+  __syncthreads();
+  if (pl == 0 && c_ok) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < p.nC)
+        atomicAdd(p.dw + tap.w_off + (long long)(c0 + c) * p.wide_stride + (long long)j * p.narrow_stride,
+                  red[0][c][j] + red[1][c][j] + red[2][c][j] + red[3][c][j]);
+  }
+}
+
 static int launch_wgrad(cudaStream_t stream, ConvWgradParams& p, bool act_f32) {
+  if (p.pC <= 4 || p.qC <= 4) {
+    SkinnyWgradParams q{};
+    const bool p_narrow = p.pC <= 4 && !(p.qC <= 4 && p.qC < p.pC);
+    q.NB = p.NB; q.OH = p.OH; q.OW = p.OW; q.ntaps = p.ntaps; q.dw = p.dw;
+    for (int i = 0; i < p.ntaps; ++i) {
+      q.taps[i] = p.taps[i];
+      if (p_narrow) {  // wide = Q, narrow = P: swap the per-tap offsets so pd* always addresses the wide tensor
+        q.taps[i].pdy = p.taps[i].qdy; q.taps[i].pdx = p.taps[i].qdx;
+        q.taps[i].qdy = p.taps[i].pdy; q.taps[i].qdx = p.taps[i].pdx;
+      }
+    }
+    if (p_narrow) {
+      q.Wd = p.Q; q.wH = p.qH; q.wW = p.qW; q.wC = p.qC; q.w_stride = p.q_stride; q.wide_stride = p.b_stride;
+      q.Nr = p.P; q.nH = p.pH; q.nW = p.pW; q.nC = p.pC; q.n_stride = p.p_stride; q.narrow_stride = p.a_stride;
+    } else {
+      q.Wd = p.P; q.wH = p.pH; q.wW = p.pW; q.wC = p.pC; q.w_stride = p.p_stride; q.wide_stride = p.a_stride;
+      q.Nr = p.Q; q.nH = p.qH; q.nW = p.qW; q.nC = p.qC; q.n_stride = p.q_stride; q.narrow_stride = p.b_stride;
+    }
+    const long long M = (long long)p.NB * p.OH * p.OW;
+    const int cblocks = (q.wC + 63) / 64;
+    int splits = (sm_count() * 8 + cblocks * p.ntaps - 1) / (cblocks * p.ntaps);
+    const long long max_splits = (M + 1023) / 1024;
+    if (splits > max_splits) splits = (int)max_splits;
+    if (splits < 1) splits = 1;
+    q.splits = splits;
+    dim3 grid(cblocks, p.ntaps * splits);
+    if (act_f32) conv_wgrad_skinny_kernel<float><<<grid, 256, 0, stream>>>(q);
+    else         conv_wgrad_skinny_kernel<bf16><<<grid, 256, 0, stream>>>(q);
+    return check_launch("conv_wgrad_skinny_kernel");
+  }
   const long long M = (long long)p.NB * p.OH * p.OW;
   const int tiles = ((p.pC + 63) / 64) * ((p.qC + 63) / 64) * p.ntaps;
   int splits = (sm_count() * 4 + tiles - 1) / tiles;

@@ -286,6 +286,31 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __rest
   if (blockIdx.x == 0 && threadIdx.x < (n & 7)) dst[(nv << 3) + threadIdx.x] = __bfloat162float(src[(nv << 3) + threadIdx.x]);
 }
 
+// x (f32) -> hi = bf16(x), lo = bf16(x - hi): x = hi + lo up to 2^-16 relative.  Lets an fp32 operand go through the
+// bf16 tensor pipe as two products with fp32 accumulation (used for the VAE codebook matmuls, which the reference
+// keeps in fp32: src/vae_tf/models.py:115-118).
+__global__ void split_f32_kernel(const float* __restrict__ src, bf16* __restrict__ hi, bf16* __restrict__ lo, size_t n) {
+  const size_t nv = n >> 3;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i], b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    float h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      h[j] = __bfloat162float(__float2bfloat16(f[j]));
+      l[j] = f[j] - h[j];
+    }
+    reinterpret_cast<uint4*>(hi)[i] = pack8(h);
+    if (lo) reinterpret_cast<uint4*>(lo)[i] = pack8(l);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const size_t i = (nv << 3) + threadIdx.x;
+    const bf16 hh = __float2bfloat16(src[i]);
+    hi[i] = hh;
+    if (lo) lo[i] = __float2bfloat16(src[i] - __bfloat162float(hh));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ CE finish
 // one warp per row: combine the per-vocab-tile (max, sum-exp) partials into lse, loss_row; block-sum the loss.
 __global__ void __launch_bounds__(128)
@@ -458,6 +483,18 @@ extern "C" int db200_cast_bf16_to_f32(db200_stream_t stream_, const void* src, f
   if (blocks < 1) blocks = 1;
   cast_bf16_f32_kernel<<<(int)blocks, 256, 0, stream>>>((const bf16*)src, dst, n);
   return check_launch("cast_bf16_f32_kernel");
+}
+
+extern "C" int db200_split_f32_to_bf16x2(db200_stream_t stream_, const float* src, void* hi, void* lo_or_null, size_t n) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (n == 0) return DB200_OK;
+  DB200_REQUIRE(src && hi && aligned16(src) && aligned16(hi) && aligned16(lo_or_null), DB200_E_ALIGN,
+                "split_f32: NULL or unaligned pointer");
+  size_t blocks = (n / 8 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  split_f32_kernel<<<(int)blocks, 256, 0, stream>>>(src, (bf16*)hi, (bf16*)lo_or_null, n);
+  return check_launch("split_f32_kernel");
 }
 
 extern "C" int db200_ce_finish(db200_stream_t stream_, const float* part_max, const float* part_sum,

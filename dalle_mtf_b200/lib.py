@@ -59,6 +59,7 @@ _SIGNATURES = {
     "db200_colsum_bf16": [c_vp, c_vp, c_i64, c_int, c_int, c_vp],
     "db200_cast_f32_to_bf16": [c_vp, c_vp, c_vp, c_sz],
     "db200_cast_bf16_to_f32": [c_vp, c_vp, c_vp, c_sz],
+    "db200_split_f32_to_bf16x2": [c_vp, c_vp, c_vp, c_vp, c_sz],
     "db200_sqnorm_f32": [c_vp, c_vp, c_sz, c_vp],
     "db200_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp, c_f32,
                         c_f32, c_int, c_int],

@@ -195,6 +195,13 @@ def cast_bf16_to_f32(src, dst):
     return dst
 
 
+def split_f32(src, hi, lo=None):
+    """hi = bf16(src), lo = bf16(src - hi)."""
+    L.require_device()
+    _chk(src, F32, "src"); _chk(hi, BF16, "hi"); _chk(lo, BF16, "lo")
+    check(L.load().db200_split_f32_to_bf16x2(stream_ptr(), ptr(src), ptr(hi), ptr(lo), src.numel()), "split_f32")
+
+
 # ----------------------------------------------------------------------------------------------- attention
 def attn_fwd(qkv, out, lse, B, S, H, dh, scale=1.0):
     L.require_device()

@@ -81,6 +81,12 @@ class VaeEngine:
         self.adam_v = torch.zeros(n, dtype=F32, device=dev)
         # bf16 copy of the kernels for the tensor-core convolutions (use_bf16 only)
         self.shadow = torch.zeros(n, dtype=BF16, device=dev) if self.use_bf16 else None
+        # codebook matmuls: the reference keeps them in fp32 (models.py:115-118).  In bf16 mode they run on the
+        # tcgen05 GEMM with every fp32 operand split into bf16 hi + lo parts (fp32 accumulation): ~2^-16 relative.
+        self._cb_tc = self.use_bf16 and self.n_hid % 8 == 0 and self.K % 8 == 0
+        if self._cb_tc:
+            self.cb_hi = torch.zeros(self.n_hid, self.K, dtype=BF16, device=dev)
+            self.cb_lo = torch.zeros(self.n_hid, self.K, dtype=BF16, device=dev)
         self._B = None
 
     # ------------------------------------------------------------------------------------------ parameters
@@ -99,6 +105,19 @@ class VaeEngine:
     def refresh_shadow(self):
         if self.shadow is not None:
             ops.cast_f32_to_bf16(self.master[:self.n_params_padded], self.shadow[:self.n_params_padded])
+        if self._cb_tc:
+            ops.split_f32(self.P("codebook/codebook"), self.cb_hi, self.cb_lo)
+
+    def _mm_split(self, a_parts, b_parts, out_f32, M, N, K, b_mn):
+        """out = sum over the listed (a, b) pairs of a @ b on tcgen05 (first product stores, the rest red.add)."""
+        first = True
+        for a, bb in zip(a_parts, b_parts):
+            if first:
+                ops.gemm(a, bb, out_f32, M, N, K, a_mn=False, b_mn=b_mn)
+                first = False
+            else:
+                ops.gemm(a, bb, out_f32, M, N, K, a_mn=False, b_mn=b_mn, mode=L.EPI_ATOMIC, split_k=1)
+        return out_f32
 
     def _conv_fwd(self, dsc, x, name, residual, y):
         """One forward convolution: tcgen05 implicit GEMM when the layer qualifies (bf16, Cin % 64 == 0), else the
@@ -174,6 +193,9 @@ class VaeEngine:
                 b["dec"].append({"out": e(B, res * 2, res * 2, ch)})
             else:
                 b["dec"].append({"t": e(B, res, res, ch), "out": e(B, res, res, ch)})
+        if self._cb_tc:
+            b.update({"y_hi": e(rows, self.K, dtype=BF16), "y_lo": e(rows, self.K, dtype=BF16),
+                      "dl_hi": e(rows, self.K, dtype=BF16), "dl_lo": e(rows, self.K, dtype=BF16)})
         b.update({
             "recon_act": e(B, self.H, self.W, self.C), "recon": e(B, self.H, self.W, self.C, dtype=F32),
             "drecon": e(B, self.H, self.W, self.C, dtype=F32), "drecon_act": e(B, self.H, self.W, self.C),
@@ -232,6 +254,11 @@ class VaeEngine:
             else:
                 x = self._res_fwd(B, name, ch, res, x, sv)
         rows = B * self.hw * self.hw
+        if self._cb_tc:   # x is exactly bf16: logits = x @ (C_hi + C_lo)
+            xb = x.view(rows, self.n_hid)
+            self._enc_bf16 = xb
+            self._mm_split([xb, xb], [self.cb_hi, self.cb_lo], b["logits"], rows, self.K, self.n_hid, b_mn=True)
+            return b["logits"]
         xf = self._to_f32(x.view(rows, self.n_hid), b["enc_f32"])
         self._enc_f32 = xf
         ops.rowmatmul(xf, self.P("codebook/codebook"), b["logits"], rows, self.n_hid, self.K)
@@ -253,8 +280,13 @@ class VaeEngine:
         rows = B * self.hw * self.hw
         self._tau = float(temperature)
         ops.gumbel_softmax_fwd(logits, u, b["y_soft"], b["y_out"], b["idx"], rows, self.K, self._tau, hard)
-        ops.rowmatmul(b["y_out"], self.P("codebook/codebook"), b["z_f32"], rows, self.K, self.n_hid,
-                      b_transposed=True)                                                     # models.py:127
+        if self._cb_tc:   # z = y @ C^T with y, C split into bf16 hi + lo (the lo*lo term is below fp32 resolution)
+            ops.split_f32(b["y_out"], b["y_hi"], b["y_lo"])
+            self._mm_split([b["y_hi"], b["y_hi"], b["y_lo"]], [self.cb_hi, self.cb_lo, self.cb_hi], b["z_f32"], rows,
+                           self.n_hid, self.K, b_mn=False)
+        else:
+            ops.rowmatmul(b["y_out"], self.P("codebook/codebook"), b["z_f32"], rows, self.K, self.n_hid,
+                          b_transposed=True)                                                 # models.py:127
         x = self._to_act(b["z_f32"], b["z"].view(rows, self.n_hid)).view(B, self.hw, self.hw, self.n_hid)
         self._z = x
         for (kind, name, cin, ch, res), sv in zip(self.dec, b["dec"]):
@@ -314,14 +346,25 @@ class VaeEngine:
                 scratch = pair[1] if dx is pair[0] else pair[0]
                 dx = self._res_bwd(B, name, ch, res, x_in, sv, dx, scratch)
         # quantiser
-        dz = self._to_f32(dx.view(rows, self.n_hid), b["dz_f32"])
         cb = self.P("codebook/codebook")
-        ops.rowmatmul_tn(dz, b["y_out"], self.G("codebook/codebook"), rows, self.n_hid, self.K)   # d codebook (decode)
-        ops.rowmatmul(dz, cb, b["dy"], rows, self.n_hid, self.K)                                  # dy = dz @ C
-        ops.gumbel_softmax_bwd(b["y_soft"], b["dy"], b["dlogits"], rows, self.K, self._tau)       # straight-through
-        ops.rowmatmul_tn(self._enc_f32, b["dlogits"], self.G("codebook/codebook"), rows, self.n_hid, self.K)
-        ops.rowmatmul(b["dlogits"], cb, b["denc_f32"], rows, self.K, self.n_hid, b_transposed=True)
+        gcb = self.G("codebook/codebook")
         pair = b["gscratch"][(B, self.hw, self.hw, self.n_hid)]
+        if self._cb_tc:
+            dzb = dx.view(rows, self.n_hid)                                                       # exactly bf16
+            ops.linear_wgrad(dzb, b["y_hi"], gcb); ops.linear_wgrad(dzb, b["y_lo"], gcb)          # d codebook (decode)
+            self._mm_split([dzb, dzb], [self.cb_hi, self.cb_lo], b["dy"], rows, self.K, self.n_hid, b_mn=True)
+            ops.gumbel_softmax_bwd(b["y_soft"], b["dy"], b["dlogits"], rows, self.K, self._tau)   # straight-through
+            ops.split_f32(b["dlogits"], b["dl_hi"], b["dl_lo"])
+            ops.linear_wgrad(self._enc_bf16, b["dl_hi"], gcb); ops.linear_wgrad(self._enc_bf16, b["dl_lo"], gcb)
+            self._mm_split([b["dl_hi"], b["dl_hi"], b["dl_lo"]], [self.cb_hi, self.cb_lo, self.cb_hi],
+                           b["denc_f32"], rows, self.n_hid, self.K, b_mn=False)
+        else:
+            dz = self._to_f32(dx.view(rows, self.n_hid), b["dz_f32"])
+            ops.rowmatmul_tn(dz, b["y_out"], gcb, rows, self.n_hid, self.K)                       # d codebook (decode)
+            ops.rowmatmul(dz, cb, b["dy"], rows, self.n_hid, self.K)                              # dy = dz @ C
+            ops.gumbel_softmax_bwd(b["y_soft"], b["dy"], b["dlogits"], rows, self.K, self._tau)   # straight-through
+            ops.rowmatmul_tn(self._enc_f32, b["dlogits"], gcb, rows, self.n_hid, self.K)
+            ops.rowmatmul(b["dlogits"], cb, b["denc_f32"], rows, self.K, self.n_hid, b_transposed=True)
         dx = self._to_act(b["denc_f32"], pair[0].view(rows, self.n_hid)).view(B, self.hw, self.hw, self.n_hid)
         if not self.use_bf16:
             dx = b["denc_f32"].view(B, self.hw, self.hw, self.n_hid)
@@ -354,3 +397,5 @@ class VaeEngine:
         ops.adam_step(self.master[:n], self.adam_m[:n], self.adam_v[:n], self.grads[:n],
                       None if self.shadow is None else self.shadow[:n], lr, beta1, beta2, eps, 0.0, None, 0.0,
                       grad_scale, True, step)
+        if self._cb_tc:
+            ops.split_f32(self.P("codebook/codebook"), self.cb_hi, self.cb_lo)

@@ -143,6 +143,8 @@ int db200_attn_causal_bwd(db200_stream_t stream, const void* qkv_bf16, const voi
 int db200_colsum_bf16(db200_stream_t stream, const void* x_bf16, int64_t ld, int rows, int cols, float* out_accum);
 int db200_cast_f32_to_bf16(db200_stream_t stream, const float* src, void* dst_bf16, size_t n);
 int db200_cast_bf16_to_f32(db200_stream_t stream, const void* src_bf16, float* dst, size_t n);
+/* hi = bf16(x), lo = bf16(x - hi) (lo may be NULL): an fp32 operand as two bf16 tensor-core operands */
+int db200_split_f32_to_bf16x2(db200_stream_t stream, const float* src, void* hi_bf16, void* lo_bf16_or_null, size_t n);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * K9/K10  optimiser.  Replaces clip_by_global_norm src/optimizers.py:11-16 and
