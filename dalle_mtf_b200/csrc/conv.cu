@@ -352,41 +352,60 @@ struct SkinnyWgradParams {
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_wgrad_skinny_kernel(const SkinnyWgradParams p) {
-  __shared__ float red[4][64][4];
+  // one pass over the pixels for ALL taps: the wide value is loaded once per pixel, the (<= 4-channel) narrow values
+  // of each tap are warp-broadcast loads; MAX_TAPS x 4 accumulators per thread; 32-bit index arithmetic.
+  __shared__ float red[4][64];
   const int c = threadIdx.x & 63, pl = threadIdx.x >> 6;
   const int c0 = blockIdx.x * 64;
-  const int t = blockIdx.y % p.ntaps, split = blockIdx.y / p.ntaps;
-  const WgradTap tap = p.taps[t];
-  const long long M = (long long)p.NB * p.OH * p.OW;
-  const long long per = (M + p.splits - 1) / p.splits;
-  const long long mbeg = split * per, mend = (mbeg + per < M) ? mbeg + per : M;
+  const int M = p.NB * p.OH * p.OW;
+  const int per = (M + p.splits - 1) / p.splits;
+  const int mbeg = blockIdx.y * per, mend = min(M, mbeg + per);
   const T* Wd = reinterpret_cast<const T*>(p.Wd);
   const T* Nr = reinterpret_cast<const T*>(p.Nr);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[MAX_TAPS][4];
+#pragma unroll
+  for (int t = 0; t < MAX_TAPS; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
   const bool c_ok = c0 + c < p.wC;
-  for (long long m = mbeg + pl; m < mend; m += 4) {
-    const int ox = (int)(m % p.OW);
-    const int oy = (int)((m / p.OW) % p.OH);
-    const int n = (int)(m / ((long long)p.OW * p.OH));
-    const int wy = oy * p.w_stride + tap.pdy, wx = ox * p.w_stride + tap.pdx;
-    const int ny = oy * p.n_stride + tap.qdy, nx = ox * p.n_stride + tap.qdx;
-    if (wy < 0 || wy >= p.wH || wx < 0 || wx >= p.wW || ny < 0 || ny >= p.nH || nx < 0 || nx >= p.nW) continue;
-    const float wv = c_ok ? ldf<T>(Wd + (((long long)n * p.wH + wy) * p.wW + wx) * p.wC + c0 + c) : 0.f;
-    const T* nr = Nr + (((long long)n * p.nH + ny) * p.nW + nx) * p.nC;
+  for (int m = mbeg + pl; m < mend; m += 4) {
+    const int ox = m % p.OW;
+    const int oy = (m / p.OW) % p.OH;
+    const int n = m / (p.OW * p.OH);
+    int last_wy = -0x7fffffff, last_wx = 0;
+    float wv = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < p.nC) acc[j] = fmaf(wv, ldf<T>(nr + j), acc[j]);
+    for (int t = 0; t < MAX_TAPS; ++t) {
+      if (t >= p.ntaps) break;
+      const int wy = oy * p.w_stride + p.taps[t].pdy, wx = ox * p.w_stride + p.taps[t].pdx;
+      if (wy != last_wy || wx != last_wx) {
+        const bool ok = c_ok && wy >= 0 && wy < p.wH && wx >= 0 && wx < p.wW;
+        wv = ok ? ldf<T>(Wd + ((long long)(n * p.wH + wy) * p.wW + wx) * p.wC + c0 + c) : 0.f;
+        last_wy = wy; last_wx = wx;
+      }
+      const int ny = oy * p.n_stride + p.taps[t].qdy, nx = ox * p.n_stride + p.taps[t].qdx;
+      if (ny < 0 || ny >= p.nH || nx < 0 || nx >= p.nW) continue;
+      const T* nr = Nr + ((long long)(n * p.nH + ny) * p.nW + nx) * p.nC;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (j < p.nC) acc[t][j] = fmaf(wv, ldf<T>(nr + j), acc[t][j]);
+    }
   }
+  for (int t = 0; t < p.ntaps; ++t)
+    for (int j = 0; j < p.nC; ++j) {
+      float v = 0.f;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) red[pl][c][j] = acc[j];
-  __syncthreads();
-  if (pl == 0 && c_ok) {
+      for (int tt = 0; tt < MAX_TAPS; ++tt)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < p.nC)
-        atomicAdd(p.dw + tap.w_off + (long long)(c0 + c) * p.wide_stride + (long long)j * p.narrow_stride,
-                  red[0][c][j] + red[1][c][j] + red[2][c][j] + red[3][c][j]);
-  }
+        for (int jj = 0; jj < 4; ++jj)
+          if (tt == t && jj == j) v = acc[tt][jj];  // compile-time indexed registers
+      red[pl][c] = v;
+      __syncthreads();
+      if (pl == 0 && c_ok)
+        atomicAdd(p.dw + p.taps[t].w_off + (long long)(c0 + c) * p.wide_stride + (long long)j * p.narrow_stride,
+                  red[0][c] + red[1][c] + red[2][c] + red[3][c]);
+      __syncthreads();
+    }
 }
 
 static int launch_wgrad(cudaStream_t stream, ConvWgradParams& p, bool act_f32) {
@@ -409,13 +428,14 @@ static int launch_wgrad(cudaStream_t stream, ConvWgradParams& p, bool act_f32) {
       q.Nr = p.Q; q.nH = p.qH; q.nW = p.qW; q.nC = p.qC; q.n_stride = p.q_stride; q.narrow_stride = p.b_stride;
     }
     const long long M = (long long)p.NB * p.OH * p.OW;
+    DB200_REQUIRE(M < (1ll << 31), DB200_E_UNSUPPORTED, "conv2d_wgrad: more than 2^31 pixels");
     const int cblocks = (q.wC + 63) / 64;
-    int splits = (sm_count() * 8 + cblocks * p.ntaps - 1) / (cblocks * p.ntaps);
+    int splits = (sm_count() * 8 + cblocks - 1) / cblocks;
     const long long max_splits = (M + 1023) / 1024;
     if (splits > max_splits) splits = (int)max_splits;
     if (splits < 1) splits = 1;
     q.splits = splits;
-    dim3 grid(cblocks, p.ntaps * splits);
+    dim3 grid(cblocks, splits);
     if (act_f32) conv_wgrad_skinny_kernel<float><<<grid, 256, 0, stream>>>(q);
     else         conv_wgrad_skinny_kernel<bf16><<<grid, 256, 0, stream>>>(q);
     return check_launch("conv_wgrad_skinny_kernel");
