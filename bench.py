@@ -38,11 +38,19 @@ METRIC = "tokens_per_sec"
 UNIT = "tokens/s"
 
 
-def load_params(n_gpus):
+WORKLOADS = {
+    # name: (config file, sequences per GPU, d, layers, vocab)
+    "dalle_example": ("dalle_example_b200.json", 32, 512, 6, 50771),
+    "dalle_coco": ("dalle_coco_b200.json", 16, 1024, 24, 50258 + 8192 + 1),
+}
+
+
+def load_params(n_gpus, workload="dalle_example"):
     from dalle_mtf_b200.utils import fetch_model_params
-    p = fetch_model_params(os.path.join(ROOT, "configs", "dalle_example_b200.json"))
+    cfg, per_gpu, _, _, _ = WORKLOADS[workload]
+    p = fetch_model_params(os.path.join(ROOT, "configs", cfg))
     p["vae_params"] = fetch_model_params(os.path.join(ROOT, "configs", p["vae_model"] + ".json"))
-    p["train_batch_size"] = PER_GPU_BATCH * n_gpus
+    p["train_batch_size"] = per_gpu * n_gpus
     p["mesh_shape"] = f"data:{n_gpus}"
     p["vae_random_init"] = True        # no pretrained VAE checkpoint in a throughput run (random-init weights)
     p["padding_id"] = 50257
@@ -228,6 +236,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", type=str, default="dalle_example", choices=sorted(WORKLOADS),
+                    help="dalle_example = BASELINE.json configs[1] (the default, what the driver measures); "
+                         "dalle_coco = configs[3] shape (n_embd 1024, 24 layers, 16 heads, 16 sequences per GPU)")
     ap.add_argument("--vae-coco", action="store_true",
                     help="measure configs/vae_coco_b200.json (256x256, K=8192, bf16, 16 images per GPU) instead")
     args = ap.parse_args()
@@ -254,8 +265,9 @@ def main():
             print(json.dumps(line), flush=True)
         dp.shutdown()
         return 0
-    params = load_params(args.gpus)
+    params = load_params(args.gpus, args.workload)
     params["_dp"] = dp
+    cfg_file, per_gpu_batch, d_model, n_layers, vocab = WORKLOADS[args.workload]
     it = iter(dalle_input_fn(params))
     host_batches = [next(it) for _ in range(4)]                 # pinned host memory
     dev_batches = [(f.to(device), l.to(device)) for f, l in host_batches]   # 4 x 25 MB of images: rotated every step
@@ -307,21 +319,22 @@ def main():
     timed(host_batches, 2, True)
     ms_e2e = timed(host_batches, args.steps, True) / args.steps
     clocks = sampler.stop(t_begin, t_end)
-    vae_line = vae_example_rate(dp, device) if args.gpus == 1 else None
+    vae_line = vae_example_rate(dp, device) if (args.gpus == 1 and args.workload == "dalle_example") else None
     f0, l0 = host_batches[0]
     h2d = f0.numel() * f0.element_size() + l0.numel() * l0.element_size()
 
     line = None
     if dp.rank == 0:
-        d, Lyr, S, V = 512, 6, 1280, 50771
+        d, Lyr, S, V = d_model, n_layers, 1280, vocab
         f_tok = 3 * (Lyr * (24 * d * d + 2 * S * d) + 2 * d * V)     # BASELINE.md §4 training FLOPs per token
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "dalle_example_b200: n_embd=512 n_layers=6 n_heads=4 seq=256+1024 (image_size 256 "
-                                   "-> 3-stage vae_example tokenizer -> 1024 image tokens), V=50771",
-                       "global_batch": PER_GPU_BATCH * args.gpus, "per_gpu_batch": PER_GPU_BATCH, "seq_len": S,
+            "config": {"workload": (f"{cfg_file[:-5]}: n_embd={d} n_layers={Lyr} n_heads={params['n_heads']} "
+                                    f"seq=256+1024 (image_size 256 -> {params['vae_model']} tokenizer -> 1024 image "
+                                    f"tokens), V={V}" + (", recompute_grad" if params.get("recompute_grad") else "")),
+                       "global_batch": per_gpu_batch * args.gpus, "per_gpu_batch": per_gpu_batch, "seq_len": S,
                        "parallelism": f"dp{args.gpus}", "step": "vae-encode + fwd + bwd + allreduce + clip + adam",
                        "l2": "inputs rotate over 4 batches; each step streams several GB of activations (>> 126 MB L2)"},
             "tokens_per_sec_per_gpu": value / args.gpus,
@@ -338,7 +351,7 @@ def main():
         }
         if vae_line is not None:
             line["vae"] = vae_line
-        if args.gpus == 1 and not args.no_cpu_baseline:
+        if args.gpus == 1 and not args.no_cpu_baseline and args.workload == "dalle_example":
             v, ms, cores, sample = cpu_reference_step_rate(2, 1, 2, "bounded sample")
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                                     "ms_per_step": ms}

@@ -24,6 +24,14 @@ namespace db200 {
 
 constexpr float LOG2E = 1.4426950408889634f;
 
+// MUFU.EX2 directly (exp2f() adds range handling the softmax does not need: arguments are <= 0 or the result is
+// masked / multiplied by 0).  ex2.approx(-inf) = +0.
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -150,7 +158,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_before();
     __syncthreads();  // (1) both halves' maxima visible; every thread has finished reading S from TMEM
     const float m_new = fmaxf(m_run, fmaxf(mx, xch[(half ^ 1) * 128 + rowi]));  // finite: key 0 is always visible
-    const float alpha = exp2f((m_run - m_new) * c1);
+    const float alpha = ex2((m_run - m_new) * c1);
     const float mc = m_new * c1;
     float lsum = 0.f;
 #pragma unroll
@@ -158,7 +166,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t pk[16];
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        const float p0 = exp2f(sv[c * 32 + i] * c1 - mc), p1 = exp2f(sv[c * 32 + i + 1] * c1 - mc);  // exp2(-inf) = 0
+        const float p0 = ex2(fmaf(sv[c * 32 + i], c1, -mc)), p1 = ex2(fmaf(sv[c * 32 + i + 1], c1, -mc));  // ex2(-inf) = 0
         lsum += p0 + p1;
         pk[i >> 1] = pack_bf16x2(p0, p1);
       }
@@ -277,16 +285,29 @@ __device__ __forceinline__ void bwd_make_p_ds(uint32_t tS, uint32_t tdP, uint32_
     tmem_ld_x32(tdP + lane_off + col0, rd);
     tmem_ld_wait();
     uint32_t pk[16], dk[16];
+    if (!row_ok) {  // out-of-range query row: contributes nothing
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      float p0 = exp2f(__uint_as_float(rs[i]) * c1 - lse_l2);
-      float p1 = exp2f(__uint_as_float(rs[i + 1]) * c1 - lse_l2);
-      if (!row_ok || (need_mask && (k0 + col0 + i) > qi)) p0 = 0.f;
-      if (!row_ok || (need_mask && (k0 + col0 + i + 1) > qi)) p1 = 0.f;
-      const float d0 = p0 * (__uint_as_float(rd[i]) - delta) * scale;
-      const float d1 = p1 * (__uint_as_float(rd[i + 1]) - delta) * scale;
-      pk[i >> 1] = pack_bf16x2(p0, p1);
-      dk[i >> 1] = pack_bf16x2(d0, d1);
+      for (int i = 0; i < 16; ++i) pk[i] = dk[i] = 0u;
+    } else if (need_mask && (k0 + col0 + 31) > qi) {  // chunk crosses the diagonal: per-element causal mask
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = ex2(fmaf(__uint_as_float(rs[i]), c1, -lse_l2));
+        float p1 = ex2(fmaf(__uint_as_float(rs[i + 1]), c1, -lse_l2));
+        if ((k0 + col0 + i) > qi) p0 = 0.f;
+        if ((k0 + col0 + i + 1) > qi) p1 = 0.f;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+        dk[i >> 1] = pack_bf16x2((p0 * scale) * (__uint_as_float(rd[i]) - delta),
+                                 (p1 * scale) * (__uint_as_float(rd[i + 1]) - delta));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ex2(fmaf(__uint_as_float(rs[i]), c1, -lse_l2));
+        const float p1 = ex2(fmaf(__uint_as_float(rs[i + 1]), c1, -lse_l2));
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+        dk[i >> 1] = pack_bf16x2((p0 * scale) * (__uint_as_float(rd[i]) - delta),
+                                 (p1 * scale) * (__uint_as_float(rd[i + 1]) - delta));
+      }
     }
     const uint32_t sub_off = half * (128 * 128);
     const int cc = c * 32;
