@@ -38,6 +38,12 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 
 // Load a [ROWS][DH] tile (DH/64 swizzled sub-tiles of ROWS*128 bytes) from a rank-4 map {dh, chan, seq, batch}.
 template <int DH>
+__device__ __forceinline__ void tma_prefetch_tile(const CUtensorMap* tm, int chan, int row0, int b) {
+#pragma unroll
+  for (int t = 0; t < DH / 64; ++t) tma_prefetch_4d(tm, 64 * t, chan, row0, b);
+}
+
+template <int DH>
 __device__ __forceinline__ void tma_load_tile(uint32_t dst, uint32_t rows_bytes, const CUtensorMap* tm, uint32_t bar,
                                               int chan, int row0, int b) {
 #pragma unroll
@@ -146,12 +152,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t r[32];
       tmem_ld_x32(tS + lane_off + half * HC + c * 32, r);
       tmem_ld_wait();
+      if (need_mask && (k0 + c * 32 + 31) > qi) {  // chunk crosses the diagonal
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float s = __uint_as_float(r[i]);
-        if (need_mask && (k0 + c * 32 + i) > qi) s = -INFINITY;
-        sv[c * 32 + i] = s;
-        mx = fmaxf(mx, s);
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(r[i]);
+          if ((k0 + c * 32 + i) > qi) s = -INFINITY;
+          sv[c * 32 + i] = s;
+          mx = fmaxf(mx, s);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float s = __uint_as_float(r[i]);
+          sv[c * 32 + i] = s;
+          mx = fmaxf(mx, s);
+        }
       }
     }
     xch[half * 128 + rowi] = mx;
@@ -413,6 +428,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
                      kk > 0);
       }
       umma_commit(bar_a);
+      if (ib + 1 < n_q) {  // the smem buffers are single: at least pull the next Q / dO tiles into L2 now
+        tma_prefetch_tile<DH>(&tmQKV, 0 * H + h, (ib + 1) * 128, b);
+        tma_prefetch_tile<DH>(&tmDO, h, (ib + 1) * 128, b);
+      }
     }
     mbar_wait(bar_a, ph);
     tc_fence_after();
