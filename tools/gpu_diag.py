@@ -249,6 +249,10 @@ def main():
         gemm_case(200, 264, 200, False, False, seed=6)
         gemm_case(1000, 128, 328, False, True, seed=7)     # BN=128 path
         gemm_case(2048, 1536, 512, False, True, seed=8)    # multi-wave persistent
+        for a_mn in (False, True):           # large M: takes the 2-CTA (cta_group::2) path
+            for b_mn in (False, True):
+                gemm_case(19976, 520, 264, a_mn, b_mn, seed=9)
+        gemm_case(40960, 512, 512, False, True, seed=10)
         gemm_epilogues()
         gemm_ce()
     if "rowops" in which or "all" in which:
