@@ -47,6 +47,7 @@ struct ConvTcParams {
   int tiles_w, tiles_h, tiles_n, tiles_c;
   int ntaps, kchunks;
   int b_kmajor;            // 1: weight matrix rows = produced channel, K contiguous;  0: rows = k, N contiguous
+  int b_3d;                // MN-major weight slabs fetched by ONE rank-3 TMA op {64, rows, Nn/64}
   ConvTcTap taps[16];
   int relu;
   const float* bias;
@@ -125,6 +126,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             const uint32_t b_dst = sB + stage * Cfg::B_BYTES;
             if (p.b_kmajor) {
               tma_load_2d(b_dst, &tmB, fb, kc * 64, tp.wrow + t.c_blk * BN);
+            } else if (p.b_3d) {
+              tma_load_3d(b_dst, &tmB, fb, 0, tp.wrow + kc * 64, (t.c_blk * BN) >> 6);
             } else {
 #pragma unroll
               for (int s = 0; s < BN / 64; ++s)
@@ -261,8 +264,23 @@ static int pow2_floor(int x) {
 
 // 4-D maps of an NHWC bf16 tensor [N][H][W][C]: the plain view (stride 1) or the four parity views
 // view(ph,pw)[n][h2][w2][c] = t[n][2*h2+ph][2*w2+pw][c]   (H, W even).
-static int make_act_maps(CUtensorMap* tm, const bf16* t, int N, int H, int W, int C, int stride, const uint32_t* box) {
+// slabs > 0: rank-5 variant {64, W, H, N, C/64} with a box of `slabs` 64-channel slabs (C % 64 == 0).
+static int make_act_maps(CUtensorMap* tm, const bf16* t, int N, int H, int W, int C, int stride, const uint32_t* box,
+                         int slabs = 0) {
   int rc;
+  if (slabs > 0) {
+    for (int ph = 0; ph < (stride == 1 ? 1 : 2); ++ph)
+      for (int pw = 0; pw < (stride == 1 ? 1 : 2); ++pw) {
+        const uint64_t s = (uint64_t)stride;
+        uint64_t dims[5] = {64, (uint64_t)W / s, (uint64_t)H / s, (uint64_t)N, (uint64_t)C / 64};
+        uint64_t str[4] = {s * C * 2, s * W * C * 2, (uint64_t)H * W * C * 2, 128};
+        uint32_t bx[5] = {64, box[1], box[2], box[3], (uint32_t)slabs};
+        rc = make_tmap_bf16(&tm[ph * 2 + pw], t + ((long long)ph * W + pw) * C, 5, dims, str, bx);
+        if (rc != DB200_OK) return rc;
+      }
+    if (stride == 1) tm[1] = tm[2] = tm[3] = tm[0];
+    return DB200_OK;
+  }
   if (stride == 1) {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     uint64_t str[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
@@ -304,8 +322,14 @@ static int run_gather(cudaStream_t stream, ConvTcParams& p, const CUtensorMap* t
   p.tiles_c = (p.Nn + bn - 1) / bn;
   CUtensorMap tmB;
   int rc;
+  p.b_3d = (!p.b_kmajor && p.Nn % 64 == 0) ? 1 : 0;
   if (p.b_kmajor) rc = make_tmap_2d(&tmB, w_bf16, (uint64_t)p.K, (uint64_t)wrows, (uint64_t)p.K, 64, (uint32_t)bn);
-  else            rc = make_tmap_2d(&tmB, w_bf16, (uint64_t)p.Nn, (uint64_t)wrows, (uint64_t)p.Nn, 64, 64);
+  else if (p.b_3d) {
+    uint64_t dims[3] = {64, (uint64_t)wrows, (uint64_t)p.Nn / 64};
+    uint64_t str[2] = {(uint64_t)p.Nn * 2, 128};
+    uint32_t box[3] = {64, 64, (uint32_t)bn / 64};
+    rc = make_tmap_bf16(&tmB, w_bf16, 3, dims, str, box);
+  } else rc = make_tmap_2d(&tmB, w_bf16, (uint64_t)p.Nn, (uint64_t)wrows, (uint64_t)p.Nn, 64, 64);
   if (rc != DB200_OK) return rc;
   if (bn == 256) return conv_tc_launch<256>(stream, tmA, tmB, p);
   if (bn == 128) return conv_tc_launch<128>(stream, tmA, tmB, p);
@@ -398,12 +422,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_cons
           const uint32_t fb = full_bar + 8 * stage;
           mbar_expect_tx(fb, Cfg::STAGE_BYTES);
           const uint32_t a_dst = sA + stage * Cfg::A_BYTES, b_dst = sB + stage * Cfg::B_BYTES;
-#pragma unroll
-          for (int s = 0; s < 2; ++s)
-            tma_load_4d(a_dst + s * (128 * 128), pm[tp.pmap], fb, a_blk * 128 + 64 * s, ox0 + tp.pdx, oy0 + tp.pdy, n0);
-#pragma unroll
-          for (int s = 0; s < BN / 64; ++s)
-            tma_load_4d(b_dst + s * (128 * 128), qm[tp.qmap], fb, b_blk * BN + 64 * s, ox0 + tp.qdx, oy0 + tp.qdy, n0);
+          // rank-5 maps {64 ch, W, H, N, C/64}: all 64-channel slabs of the operand in one TMA op
+          tma_load_5d(a_dst, pm[tp.pmap], fb, 0, ox0 + tp.pdx, oy0 + tp.pdy, n0, a_blk * 2);
+          tma_load_5d(b_dst, qm[tp.qmap], fb, 0, ox0 + tp.qdx, oy0 + tp.qdy, n0, b_blk * (BN / 64));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -662,6 +683,7 @@ extern "C" int db200_conv2d_wgrad_tc(db200_stream_t stream_, const db200_conv_de
   WgradTcParams p{};
   p.dw = dw;
   p.pC = c->Cin; p.qC = c->Cout;
+  const int wg_bn = p.qC >= 256 ? 256 : (p.qC >= 128 ? 128 : 64);
   p.ntaps = c->KH * c->KW;
   const bf16* xb = reinterpret_cast<const bf16*>(x_bf16);
   const bf16* dyb = reinterpret_cast<const bf16*>(dy_bf16);
@@ -671,9 +693,9 @@ extern "C" int db200_conv2d_wgrad_tc(db200_stream_t stream_, const db200_conv_de
     p.NB = c->N; p.OH = c->Ho; p.OW = c->Wo;  // contract over output pixels
     choose_tile(p.OW, p.OH, p.TW, p.TH, p.TN);
     const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
-    rc = make_act_maps(tmP, xb, c->N, c->H, c->W, c->Cin, c->stride, box);
+    rc = make_act_maps(tmP, xb, c->N, c->H, c->W, c->Cin, c->stride, box, 2);
     if (rc != DB200_OK) return rc;
-    rc = make_act_maps(tmQ, dyb, c->N, c->Ho, c->Wo, c->Cout, 1, box);
+    rc = make_act_maps(tmQ, dyb, c->N, c->Ho, c->Wo, c->Cout, 1, box, wg_bn / 64);
     if (rc != DB200_OK) return rc;
     for (int kh = 0; kh < c->KH; ++kh)
       for (int kw = 0; kw < c->KW; ++kw) {
@@ -690,9 +712,9 @@ extern "C" int db200_conv2d_wgrad_tc(db200_stream_t stream_, const db200_conv_de
     p.NB = c->N; p.OH = c->H; p.OW = c->W;  // contract over input (low-res) pixels
     choose_tile(p.OW, p.OH, p.TW, p.TH, p.TN);
     const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
-    rc = make_act_maps(tmP, xb, c->N, c->H, c->W, c->Cin, 1, box);
+    rc = make_act_maps(tmP, xb, c->N, c->H, c->W, c->Cin, 1, box, 2);
     if (rc != DB200_OK) return rc;
-    rc = make_act_maps(tmQ, dyb, c->N, c->Ho, c->Wo, c->Cout, 2, box);
+    rc = make_act_maps(tmQ, dyb, c->N, c->Ho, c->Wo, c->Cout, 2, box, wg_bn / 64);
     if (rc != DB200_OK) return rc;
     for (int kh = 0; kh < 4; ++kh)
       for (int kw = 0; kw < 4; ++kw) {
@@ -709,7 +731,7 @@ extern "C" int db200_conv2d_wgrad_tc(db200_stream_t stream_, const db200_conv_de
   p.tiles_w = (p.OW + p.TW - 1) / p.TW;
   p.tiles_h = (p.OH + p.TH - 1) / p.TH;
   p.tiles_n = (p.NB + p.TN - 1) / p.TN;
-  const int bn = p.qC >= 256 ? 256 : (p.qC >= 128 ? 128 : 64);
+  const int bn = wg_bn;
   p.a_tiles = (p.pC + 127) / 128;
   p.b_tiles = (p.qC + bn - 1) / bn;
   const int items = p.a_tiles * p.b_tiles * p.ntaps;
