@@ -15,8 +15,7 @@
 //
 // Same warp-specialised pipeline as gemm.cu (TMA producer / MMA issuer / TMEM accumulators / 8 epilogue warps).
 // Reference: tf.layers.conv2d / conv2d_transpose call sites src/vae_tf/models.py:95-109, 139-155 and their gradients.
-#include "common.cuh"
-#include "ptx.cuh"
+#include "gemm_common.cuh"  // staging helpers for coalesced epilogue I/O
 
 namespace db200 {
 
@@ -30,7 +29,7 @@ struct ConvTcCfg {
   static constexpr uint32_t B_BYTES = BN * 64 * 2;
   static constexpr uint32_t STAGE_BYTES = CT_A_BYTES + B_BYTES;
   static constexpr uint32_t TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;
-  static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + 256;
+  static constexpr size_t SMEM_BYTES = 1024 + size_t(STAGES) * STAGE_BYTES + 256 + 8 * 4096 /*epilogue staging*/;
 };
 
 struct ConvTcTap {
@@ -166,66 +165,93 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
+    // Epilogue.  A thread owns one output PIXEL (accumulator row) and its channels are contiguous in NHWC, so the
+    // same coalescing scheme as the GEMM applies: 32 pixels x 64 channels are transposed through a swizzled 4 KiB smem
+    // block and every global access covers 4 pixels x 128 contiguous bytes (outputs, residual and ReLU-mask operands).
     const int ew = warp - 4, wq = ew & 3, half = ew >> 2;
     constexpr int HALF = BN / 2;
+    const uint32_t stg = bars + 256 + ew * STG_BYTES;
+    const int slot = lane & 7, rsub = lane >> 3;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const ConvTile t = conv_decode(p, tile);
-      const int r = wq * 32 + lane;  // pixel index inside the tile: ((tn*TH + th)*TW + tw)
-      const int tw = r % p.TW, th = (r / p.TW) % p.TH, tn = r / (p.TW * p.TH);
-      const int n = t.n0 + tn, oy = t.oy0 + th, ox = t.ox0 + tw;
-      const bool ok = n < p.NB && oy < p.OH && ox < p.OW;
-      const long long o =
-          (((long long)n * p.out_H + (oy * p.out_stride + p.oa)) * p.out_W + (ox * p.out_stride + p.ob)) * p.Nn;
+      // element offsets (or -1) of the 8 pixels this lane moves during block loads / stores
+      long long poff[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = wq * 32 + i * 4 + rsub;
+        const int tw = r % p.TW, th = (r / p.TW) % p.TH, tn = r / (p.TW * p.TH);
+        const int n = t.n0 + tn, oy = t.oy0 + th, ox = t.ox0 + tw;
+        poff[i] = (n < p.NB && oy < p.OH && ox < p.OW)
+                      ? (((long long)n * p.out_H + (oy * p.out_stride + p.oa)) * p.out_W + (ox * p.out_stride + p.ob)) * p.Nn
+                      : -1;
+      }
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + half * HALF + (uint32_t(wq * 32) << 16);
       const int cbase = t.c_blk * BN + half * HALF;
+      constexpr int CW = (HALF >= 64) ? 64 : 32;  // channels per staged block
 #pragma unroll 1
-      for (int c = 0; c < HALF / 32; ++c) {
-        const int col0 = cbase + c * 32;
-        if (col0 >= p.Nn) break;
-        uint32_t rr[32];
-        tmem_ld_x32(t_addr + c * 32, rr);
-        tmem_ld_wait();
-        if (!ok) continue;
+      for (int cb = 0; cb < HALF / CW; ++cb) {
+        const int colp = cbase + cb * CW;
+        if (colp >= p.Nn) break;
+        float v[CW];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int col = col0 + g * 8;
-          if (col + 8 > p.Nn) break;
-          float v[8];
+        for (int h = 0; h < CW / 32; ++h) {
+          uint32_t rr[32];
+          tmem_ld_x32(t_addr + cb * CW + h * 32, rr);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(rr[g * 8 + j]);
-          if (p.bias) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col)),
-                         b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col) + 1);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-          }
-          if (p.relu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (p.mask) {
-            const uint4 q = *reinterpret_cast<const uint4*>(p.mask + o + col);
-            const float2 m0 = unpack_bf16x2(q.x), m1 = unpack_bf16x2(q.y), m2 = unpack_bf16x2(q.z),
-                         m3 = unpack_bf16x2(q.w);
-            const float mm[8] = {m0.x, m0.y, m1.x, m1.y, m2.x, m2.y, m3.x, m3.y};
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = mm[j] > 0.f ? v[j] : 0.f;
-          }
-          if (p.residual) {
-            const uint4 q = *reinterpret_cast<const uint4*>(p.residual + o + col);
-            const float2 r0 = unpack_bf16x2(q.x), r1 = unpack_bf16x2(q.y), r2 = unpack_bf16x2(q.z),
-                         r3 = unpack_bf16x2(q.w);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r1.x; v[3] += r1.y;
-            v[4] += r2.x; v[5] += r2.y; v[6] += r3.x; v[7] += r3.y;
-          }
-          uint4 q;
-          q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
-          q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(p.y + o + col) = q;
+          for (int j = 0; j < 32; ++j) v[h * 32 + j] = __uint_as_float(rr[j]);
         }
+        if (p.bias) {
+#pragma unroll
+          for (int g = 0; g < CW / 8; ++g) {
+            if (colp + g * 8 + 8 > p.Nn) break;
+            float bb[8];
+            load8(p.bias + colp + g * 8, bb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[g * 8 + j] += bb[j];
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        // optional operands with the output's layout: block-load -> per-row read
+        for (int which = 0; which < 2; ++which) {
+          const bf16* src = which == 0 ? p.mask : p.residual;
+          if (!src) continue;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int col = colp + slot * 8;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (poff[i] >= 0 && slot * 8 < CW && col + 8 <= p.Nn) q = __ldg(reinterpret_cast<const uint4*>(src + poff[i] + col));
+            st_shared_v4u(stg_addr(stg, i * 4 + rsub, slot), q.x, q.y, q.z, q.w);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < CW / 32; ++h) {
+            float o[32];
+            stage_get_bf16(stg, lane, h, o);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (which == 0) v[h * 32 + j] = o[j] > 0.f ? v[h * 32 + j] : 0.f;
+              else            v[h * 32 + j] += o[j];
+            }
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int h = 0; h < CW / 32; ++h) stage_put_bf16(stg, lane, h, v + h * 32);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int col = colp + slot * 8;
+          const uint4 q = ld_shared_v4u(stg_addr(stg, i * 4 + rsub, slot));
+          if (poff[i] >= 0 && slot * 8 < CW && col + 8 <= p.Nn) *reinterpret_cast<uint4*>(p.y + poff[i] + col) = q;
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
