@@ -159,6 +159,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const int cbase = t.n_blk * BN + half * (BN / 2);
+      // pull this half-tile's bias into L1 while the accumulator is still being produced: the epilogue's first use of
+      // it sat on an L2 round trip per 32-column chunk (ncu source page: top stall of the CE epilogues)
+      if (p.bias && lane < BN / 64 && cbase + lane * 32 < p.N)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + cbase + lane * 32));
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + half * (BN / 2) + (uint32_t(wq * 32) << 16);
@@ -256,8 +260,8 @@ extern "C" int db200_gemm_bf16(db200_stream_t stream_, const void* A, int a_mn_m
                       epi->n_valid <= N,
                   DB200_E_INVALID, "gemm: CE_STATS needs labels/part_max/part_sum/label_logit and 0 < n_valid <= N");
   if (mode == DB200_EPI_CE_GRAD)
-    DB200_REQUIRE(epi->labels && epi->lse && epi->n_valid > 0 && epi->n_valid <= N, DB200_E_INVALID,
-                  "gemm: CE_GRAD needs labels/lse and 0 < n_valid <= N");
+    DB200_REQUIRE(epi->labels && epi->lse && epi->n_valid > 0 && epi->n_valid <= N && epi->alpha > 0.f,
+                  DB200_E_INVALID, "gemm: CE_GRAD needs labels/lse, 0 < n_valid <= N and alpha > 0");
   int splits = 1;
   const int kb_total = (K + BK - 1) / BK;
   if (mode == DB200_EPI_ATOMIC) {

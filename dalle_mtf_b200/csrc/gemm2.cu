@@ -226,6 +226,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const int cbase = t.n_blk * BN + half * (BN / 2);
+      // pull this half-tile's bias into L1 while the accumulator is still being produced: the epilogue's first use of
+      // it sat on an L2 round trip per 32-column chunk (ncu source page: top stall of the CE epilogues)
+      if (p.bias && lane < BN / 64 && cbase + lane * 32 < p.N)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + cbase + lane * 32));
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + half * (BN / 2) + (uint32_t(wq * 32) << 16);

@@ -138,13 +138,26 @@ __device__ __forceinline__ void stage_flush(uint32_t stg, void* D, long long ldd
   constexpr int EPS = 16 / ESZ;  // elements per 16-byte slot
   __syncwarp();
   const int slot = lane & 7, rsub = lane >> 3;
+  char* dst = reinterpret_cast<char*>(D) + ((long long)(row0 + rsub) * ldd + col0 + slot * EPS) * ESZ;
+  const long long step = ldd * (4 * ESZ);
+  // (slot ^ r) & 7 with r = 4 i + rsub: the low two bits of r are rsub's, bit 2 alternates with i
+  const uint32_t a0 = stg + rsub * 128 + (((slot ^ rsub) & 7) << 4);
+  const uint32_t a1 = stg + (rsub + 4) * 128 + (((slot ^ (rsub + 4)) & 7) << 4);
+  if (row0 + 32 <= M && col0 + 8 * EPS <= N) {  // interior block (warp-uniform): no per-row guards
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = i * 4 + rsub;
-    const uint4 v = ld_shared_v4u(stg_addr(stg, r, slot));
-    const int row = row0 + r, col = col0 + slot * EPS;
-    if (row < M && col + EPS <= N)
-      *reinterpret_cast<uint4*>(reinterpret_cast<char*>(D) + ((long long)row * ldd + col) * ESZ) = v;
+    for (int i = 0; i < 8; ++i) {
+      const uint4 v = ld_shared_v4u(((i & 1) ? a1 : a0) + (i >> 1) * 1024);
+      *reinterpret_cast<uint4*>(dst) = v;
+      dst += step;
+    }
+  } else {
+    const bool col_ok = col0 + slot * EPS + EPS <= N;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint4 v = ld_shared_v4u(((i & 1) ? a1 : a0) + (i >> 1) * 1024);
+      if (col_ok && row0 + i * 4 + rsub < M) *reinterpret_cast<uint4*>(dst) = v;
+      dst += step;
+    }
   }
   __syncwarp();
 }
@@ -167,18 +180,27 @@ __device__ __forceinline__ void stage_fetch_bf16(uint32_t stg, const bf16* src, 
 // colsum[col0 .. col0+64): lane l owns columns 2l, 2l+1.  Rows >= M hold zeros (their `o` was zeroed).
 __device__ __forceinline__ void stage_colsum_bf16(uint32_t stg, float* colsum, int col0, int N, int lane) {
   __syncwarp();
-  float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
-  for (int r = 0; r < 32; ++r) {
-    uint32_t w;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(stg_addr(stg, r, lane >> 2) + (lane & 3) * 4) : "memory");
-    const float2 f = unpack_bf16x2(w);
-    s0 += f.x;
-    s1 += f.y;
+  // word `lane` of row r sits at r*128 + (((lane>>2) ^ r) & 7)*16 + (lane&3)*4: the swizzle depends on r & 7 only, so 8
+  // bases cover all 32 rows with immediate offsets (no address arithmetic inside the loop)
+  const uint32_t w0 = stg + (lane & 3) * 4;
+  const int slot = lane >> 2;
+  uint32_t base[8];
+#pragma unroll
+  for (int t = 0; t < 8; ++t) base[t] = w0 + t * 128 + (((slot ^ t) & 7) << 4);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // two accumulator pairs: shorter dependency chains
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      uint32_t w;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(base[t] + q * 1024) : "memory");
+      const float2 f = unpack_bf16x2(w);
+      if (t & 1) { s2 += f.x; s3 += f.y; } else { s0 += f.x; s1 += f.y; }
+    }
   }
   const int col = col0 + 2 * lane;
-  if (col < N) atomicAdd(colsum + col, s0);
-  if (col + 1 < N) atomicAdd(colsum + col + 1, s1);
+  if (col < N) atomicAdd(colsum + col, s0 + s2);
+  if (col + 1 < N) atomicAdd(colsum + col + 1, s1 + s3);
 }
 
 template <int CH>
@@ -353,12 +375,13 @@ __device__ __forceinline__ void epi_ce_stats(const GemmParams& p, uint32_t t_add
   }
 }
 
-// dlogits = alpha * (softmax - onehot), zero in the padded vocabulary columns
+// dlogits = alpha * (softmax - onehot), zero in the padded vocabulary columns.  alpha > 0 (checked by the host): it is
+// folded into the exponent, alpha * 2^(x - l) = 2^(x - (l - log2 alpha)), which removes one multiply per element.
 template <int CH>
 __device__ __forceinline__ void epi_ce_grad(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase,
                                             uint32_t stg, int row0, int lane) {
   const int label = row_ok ? p.labels[row] : -1;
-  const float l2 = row_ok ? p.lse[row] * kLog2e : 0.f;
+  const float l2 = row_ok ? fmaf(p.lse[row], kLog2e, -log2f(p.alpha)) : 0.f;
 #pragma unroll 1
   for (int pc = 0; pc < CH / 2; ++pc) {
     const int colp = cbase + pc * 64;
@@ -372,32 +395,32 @@ __device__ __forceinline__ void epi_ce_grad(const GemmParams& p, uint32_t t_addr
       const int col0 = colp + h * 32;
       const uint32_t* r = rr2[h];
       float o[32];
+      if (col0 + 32 <= p.n_valid) {  // interior chunk (warp-uniform)
 #pragma unroll
-      for (int j = 0; j < 32; ++j) o[j] = 0.f;
-      if (row_ok && col0 < p.n_valid) {
-        if (col0 + 32 <= p.n_valid) {
+        for (int g = 0; g < 4; ++g) {
+          float b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          if (p.bias) load8(p.bias + col0 + g * 8, b);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            if (p.bias) load8(p.bias + col0 + g * 8, b);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o[g * 8 + j] = fast_exp2(fmaf(__uint_as_float(r[g * 8 + j]) + b[j], kLog2e, -l2)) * p.alpha;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int cc = col0 + j;
-            if (cc < p.n_valid)
-              o[j] = fast_exp2(fmaf(__uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + cc) : 0.f), kLog2e, -l2)) *
-                     p.alpha;
-          }
+          for (int j = 0; j < 8; ++j)
+            o[g * 8 + j] = fast_exp2(fmaf(__uint_as_float(r[g * 8 + j]) + b[j], kLog2e, -l2));
         }
-        if (label >= col0 && label < col0 + 32) {
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j == label) o[j] -= p.alpha;
+        for (int j = 0; j < 32; ++j) {
+          const int cc = col0 + j;
+          o[j] = cc < p.n_valid
+                     ? fast_exp2(fmaf(__uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + cc) : 0.f), kLog2e, -l2))
+                     : 0.f;
         }
+      }
+      if (label >= col0 && label < col0 + 32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j == label) o[j] -= p.alpha;
+      }
+      if (!row_ok) {  // rows past M: zeros (they are not stored, but the fused column sums read the staged block)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = 0.f;
       }
       stage_put_bf16(stg, lane, h, o);
     }
@@ -405,6 +428,5 @@ __device__ __forceinline__ void epi_ce_grad(const GemmParams& p, uint32_t t_addr
     stage_flush<2>(stg, p.D, p.ldd, row0, colp, p.M, p.N, lane);
   }
 }
-
 
 }  // namespace db200

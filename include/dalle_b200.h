@@ -87,7 +87,7 @@ enum {
   DB200_EPI_ATOMIC = 1,   /* D(f32) += alpha*acc  (red.global.add; used for split-K / gradient accumulation)       */
   DB200_EPI_RELU_BWD = 2, /* D(bf16) = alpha*acc * (aux[m,n] > 0)          (backward of the MLP's ReLU)            */
   DB200_EPI_CE_STATS = 3, /* no D: per (row, n-tile) max & sum-exp of acc+bias over valid columns + label logit    */
-  DB200_EPI_CE_GRAD = 4   /* D(bf16) = alpha * (exp(acc+bias - lse[m]) - [n == label[m]]), 0 for n >= n_valid      */
+  DB200_EPI_CE_GRAD = 4   /* D(bf16) = alpha * (exp(acc+bias - lse[m]) - [n == label[m]]), 0 for n >= n_valid; alpha > 0 */
 };
 
 typedef struct db200_gemm_epilogue {
