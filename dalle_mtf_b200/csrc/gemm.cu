@@ -163,6 +163,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // it sat on an L2 round trip per 32-column chunk (ncu source page: top stall of the CE epilogues)
       if (p.bias && lane < BN / 64 && cbase + lane * 32 < p.N)
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + cbase + lane * 32));
+      // same for the per-element operands the epilogue will read (ReLU mask / residual rows): DRAM -> L2 now
+      if (row_ok && cbase < p.N) {
+        if (p.aux) {
+          const bf16* a = p.aux + (long long)row * p.ldaux + cbase;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          if (BN == 256 && cbase + 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 64));
+        }
+        if (p.residual) {
+          const bf16* a = p.residual + (long long)row * p.ldr + cbase;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          if (BN == 256 && cbase + 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 64));
+        }
+      }
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + half * (BN / 2) + (uint32_t(wq * 32) << 16);
@@ -171,7 +184,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         case DB200_EPI_ATOMIC:   epi_atomic<CH>(p, t_addr, row, row_ok, cbase); break;
         case DB200_EPI_RELU_BWD: epi_relu_bwd<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
         case DB200_EPI_CE_STATS: epi_ce_stats<CH>(p, t_addr, row, row_ok, cbase, t.n_blk * 2 + half); break;
-        default:                 epi_ce_grad<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
+        case DB200_EPI_CE_GRAD:  epi_ce_grad<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
+        default: break;  // mode -1 (DB200_GEMM_NOEPI=1, timing experiments only): drain nothing
       }
       // release the accumulator stage back to the MMA warp
       tc_fence_before();
@@ -288,6 +302,10 @@ extern "C" int db200_gemm_bf16(db200_stream_t stream_, const void* A, int a_mn_m
   p.splits = splits;
   p.kb_total = kb_total;
   p.mode = mode;
+  {  // timing experiments only: skip the epilogue work (results are garbage) to expose the TMA + MMA ceiling
+    static const bool noepi = [] { const char* e = getenv("DB200_GEMM_NOEPI"); return e && e[0] == '1'; }();
+    if (noepi) p.mode = -1;
+  }
   p.out_f32 = epi->out_f32;
   p.relu = epi->relu;
   p.alpha = epi->alpha;

@@ -230,6 +230,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // it sat on an L2 round trip per 32-column chunk (ncu source page: top stall of the CE epilogues)
       if (p.bias && lane < BN / 64 && cbase + lane * 32 < p.N)
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p.bias + cbase + lane * 32));
+      // same for the per-element operands the epilogue will read (ReLU mask / residual rows): DRAM -> L2 now
+      if (row_ok && cbase < p.N) {
+        if (p.aux) {
+          const bf16* a = p.aux + (long long)row * p.ldaux + cbase;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          if (BN == 256 && cbase + 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 64));
+        }
+        if (p.residual) {
+          const bf16* a = p.residual + (long long)row * p.ldr + cbase;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+          if (BN == 256 && cbase + 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 64));
+        }
+      }
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + half * (BN / 2) + (uint32_t(wq * 32) << 16);
@@ -238,7 +251,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         case DB200_EPI_ATOMIC:   epi_atomic<CH>(p, t_addr, row, row_ok, cbase); break;
         case DB200_EPI_RELU_BWD: epi_relu_bwd<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
         case DB200_EPI_CE_STATS: epi_ce_stats<CH>(p, t_addr, row, row_ok, cbase, t.n_blk * 2 + half); break;
-        default:                 epi_ce_grad<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
+        case DB200_EPI_CE_GRAD:  epi_ce_grad<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
+        default: break;  // mode -1 (DB200_GEMM_NOEPI=1, timing experiments only): drain nothing
       }
       tc_fence_before();
       __syncwarp();
