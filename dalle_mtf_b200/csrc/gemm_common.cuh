@@ -370,8 +370,8 @@ __device__ __forceinline__ void epi_ce_stats(const GemmParams& p, uint32_t t_add
     run_max = new_max;
   }
   if (row_ok) {
-    p.part_max[(long long)row * p.n_parts + part_idx] = run_max;
-    p.part_sum[(long long)row * p.n_parts + part_idx] = run_sum;
+    p.part_max[(long long)part_idx * p.M + row] = run_max;  // [n_parts][M]: a warp stores 32 consecutive floats
+    p.part_sum[(long long)part_idx * p.M + row] = run_sum;
   }
 }
 

@@ -312,34 +312,37 @@ __global__ void split_f32_kernel(const float* __restrict__ src, bf16* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ CE finish
-// one warp per row: combine the per-vocab-tile (max, sum-exp) partials into lse, loss_row; block-sum the loss.
+// one thread per row: combine the per-vocab-tile (max, sum-exp) partials into lse, loss_row; block-sum the loss.
+// Partials are stored [n_tiles][M] (tile-major): the GEMM epilogue's 32 lanes = 32 consecutive rows write one 128-byte
+// line per store, and consecutive threads here read consecutive rows.
 __global__ void __launch_bounds__(128)
 ce_finish_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
                  const float* __restrict__ label_logit, float* __restrict__ lse, float* __restrict__ loss_rows,
                  float* __restrict__ loss_sum, int M, int n_tiles) {
   __shared__ float blk[4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x * 4 + warp;
+  const int row = blockIdx.x * 128 + threadIdx.x;
   float loss = 0.f;
   if (row < M) {
-    const float* pm = part_max + (long long)row * n_tiles;
-    const float* ps = part_sum + (long long)row * n_tiles;
-    float m = -INFINITY;
-    for (int t = lane; t < n_tiles; t += 32) m = fmaxf(m, pm[t]);
-    m = warp_max(m);
-    float s = 0.f;
-    for (int t = lane; t < n_tiles; t += 32) {
-      const float pmt = pm[t];
-      if (pmt > -INFINITY) s += ps[t] * expf(pmt - m);
+    float m = -INFINITY, s = 0.f;
+    for (int t = 0; t < n_tiles; ++t) {
+      const float pmt = part_max[(long long)t * M + row];
+      if (pmt > -INFINITY) {
+        const float pst = part_sum[(long long)t * M + row];
+        if (pmt > m) {
+          s = s * expf(m - pmt) + pst;  // expf(-inf) = 0 on the first valid tile
+          m = pmt;
+        } else {
+          s += pst * expf(pmt - m);
+        }
+      }
     }
-    s = warp_sum(s);
     const float l = m + logf(s);
     loss = l - label_logit[row];
-    if (lane == 0) {
-      lse[row] = l;
-      loss_rows[row] = loss;
-    }
+    lse[row] = l;
+    loss_rows[row] = loss;
   }
+  loss = warp_sum(loss);
   if (lane == 0) blk[warp] = loss;
   __syncthreads();
   if (threadIdx.x == 0) atomicAdd(loss_sum, blk[0] + blk[1] + blk[2] + blk[3]);
@@ -504,7 +507,7 @@ extern "C" int db200_ce_finish(db200_stream_t stream_, const float* part_max, co
   DB200_REQUIRE(M > 0 && n_tiles > 0, DB200_E_INVALID, "ce_finish: M and n_tiles must be positive");
   DB200_REQUIRE(part_max && part_sum && label_logit && lse && loss_rows && loss_sum, DB200_E_INVALID,
                 "ce_finish: NULL pointer");
-  ce_finish_kernel<<<(M + 3) / 4, 128, 0, stream>>>(part_max, part_sum, label_logit, lse, loss_rows, loss_sum, M,
+  ce_finish_kernel<<<(M + 127) / 128, 128, 0, stream>>>(part_max, part_sum, label_logit, lse, loss_rows, loss_sum, M,
                                                     n_tiles);
   return check_launch("ce_finish_kernel");
 }

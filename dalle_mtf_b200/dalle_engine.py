@@ -233,7 +233,7 @@ class DalleEngine:
             } for _ in range(n_saved)],
             "hf": e(T, d), "meanf": e(T, dtype=F32), "rstdf": e(T, dtype=F32),
             "labels": e(B, S, dtype=I32),
-            "part_max": e(T, nt, dtype=F32), "part_sum": e(T, nt, dtype=F32),
+            "part_max": e(nt, T, dtype=F32), "part_sum": e(nt, T, dtype=F32),
             "label_logit": e(T, dtype=F32), "lse_v": e(T, dtype=F32), "loss_rows": e(T, dtype=F32),
             "dlogits": e(T, self.Vpad),
             # backward scratch

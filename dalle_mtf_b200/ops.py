@@ -111,7 +111,7 @@ def ce_tiles(N):
 
 def ce_finish(part_max, part_sum, label_logit, lse, loss_rows, loss_sum):
     L.require_device()
-    M, n_tiles = part_max.shape
+    n_tiles, M = part_max.shape          # tile-major partials [n_tiles][M]
     check(L.load().db200_ce_finish(stream_ptr(), ptr(part_max), ptr(part_sum), ptr(label_logit), ptr(lse),
                                    ptr(loss_rows), ptr(loss_sum), M, n_tiles), "db200_ce_finish")
 

@@ -102,8 +102,8 @@ typedef struct db200_gemm_epilogue {
   const void* aux;      /* bf16 [M][ldaux] (RELU_BWD)                                             */
   int64_t ldaux;
   const int32_t* labels; /* [M]  (CE_*)                                                           */
-  float* part_max;       /* [M][n_tiles] (CE_STATS)   n_tiles = ceil(N / 256)                     */
-  float* part_sum;       /* [M][n_tiles] (CE_STATS)                                               */
+  float* part_max;       /* [n_tiles][M] (CE_STATS)   n_tiles = db200_gemm_ce_tiles(N)              */
+  float* part_sum;       /* [n_tiles][M] (CE_STATS)                                               */
   float* label_logit;    /* [M] (CE_STATS)                                                        */
   const float* lse;      /* [M] (CE_GRAD)                                                         */
   int32_t n_valid;       /* CE_*: number of real vocabulary columns (<= N)                        */

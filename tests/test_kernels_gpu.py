@@ -105,7 +105,7 @@ def test_cross_entropy_epilogues(ops):
     lse_ref = torch.logsumexp(logits, -1)
     loss_ref = lse_ref - logits[torch.arange(T), labels.long()]
     nt = ops.ce_tiles(Vpad)
-    pm, ps = torch.empty(T, nt, device=DEV), torch.empty(T, nt, device=DEV)
+    pm, ps = torch.empty(nt, T, device=DEV), torch.empty(nt, T, device=DEV)
     ll, lse, lr, lsum = torch.zeros(T, device=DEV), torch.empty(T, device=DEV), torch.empty(T, device=DEV), torch.zeros(1, device=DEV)
     x, w, lab = X.to(DEV), W.to(DEV), labels.to(DEV)
     bpad = torch.zeros(Vpad, device=DEV); bpad[:V] = bias.to(DEV)

@@ -115,7 +115,7 @@ def gemm_ce():
     lse_ref = torch.logsumexp(logits, -1)
     loss_ref = lse_ref - logits[torch.arange(T), labels.long()]
     nt = ops.ce_tiles(Vpad)
-    pm = torch.empty(T, nt, device=DEV); ps = torch.empty(T, nt, device=DEV)
+    pm = torch.empty(nt, T, device=DEV); ps = torch.empty(nt, T, device=DEV)
     ll = torch.zeros(T, device=DEV); lse = torch.empty(T, device=DEV); lr = torch.empty(T, device=DEV)
     lsum = torch.zeros(1, device=DEV)
     x, w, b, lab = X.to(DEV), W.to(DEV), bias.to(DEV), labels.to(DEV)
