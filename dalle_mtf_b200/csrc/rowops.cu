@@ -312,40 +312,61 @@ __global__ void split_f32_kernel(const float* __restrict__ src, bf16* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------ CE finish
-// one thread per row: combine the per-vocab-tile (max, sum-exp) partials into lse, loss_row; block-sum the loss.
+// Combine the per-vocab-tile (max, sum-exp) partials into lse, loss_row; block-sum the loss.
 // Partials are stored [n_tiles][M] (tile-major): the GEMM epilogue's 32 lanes = 32 consecutive rows write one 128-byte
-// line per store, and consecutive threads here read consecutive rows.
-__global__ void __launch_bounds__(128)
+// line per store.  Here a block owns 32 consecutive rows; warp g of 8 folds tiles g, g+8, ... (every load is one
+// 128-byte line), then the 8 partial (max, sum) pairs of a row are merged through shared memory.
+constexpr int CEF_ROWS = 32, CEF_GROUPS = 8;
+__global__ void __launch_bounds__(CEF_ROWS * CEF_GROUPS)
 ce_finish_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum,
                  const float* __restrict__ label_logit, float* __restrict__ lse, float* __restrict__ loss_rows,
                  float* __restrict__ loss_sum, int M, int n_tiles) {
-  __shared__ float blk[4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row = blockIdx.x * 128 + threadIdx.x;
-  float loss = 0.f;
+  __shared__ float sm_m[CEF_GROUPS][CEF_ROWS], sm_s[CEF_GROUPS][CEF_ROWS];
+  const int r = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int row = blockIdx.x * CEF_ROWS + r;
+  float m = -INFINITY, s = 0.f;
   if (row < M) {
-    float m = -INFINITY, s = 0.f;
-    for (int t = 0; t < n_tiles; ++t) {
-      const float pmt = part_max[(long long)t * M + row];
-      if (pmt > -INFINITY) {
-        const float pst = part_sum[(long long)t * M + row];
-        if (pmt > m) {
-          s = s * expf(m - pmt) + pst;  // expf(-inf) = 0 on the first valid tile
-          m = pmt;
-        } else {
-          s += pst * expf(pmt - m);
-        }
+    constexpr int U = 4;  // tiles in flight per thread: the loop is load-latency bound otherwise
+    for (int t0 = g; t0 < n_tiles; t0 += CEF_GROUPS * U) {
+      float pm[U], ps[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int t = t0 + u * CEF_GROUPS;
+        pm[u] = t < n_tiles ? __ldg(part_max + (long long)t * M + row) : -INFINITY;
+        ps[u] = t < n_tiles ? __ldg(part_sum + (long long)t * M + row) : 0.f;
+      }
+      float mn = m;
+#pragma unroll
+      for (int u = 0; u < U; ++u) mn = fmaxf(mn, pm[u]);
+      if (mn > -INFINITY) {
+        s *= expf(m - mn);  // expf(-inf) = 0 on the first valid tile
+#pragma unroll
+        for (int u = 0; u < U; ++u) s += ps[u] * expf(pm[u] - mn);  // tiles with no valid column: 0 * exp(-inf) = 0
+        m = mn;
       }
     }
-    const float l = m + logf(s);
-    loss = l - label_logit[row];
-    lse[row] = l;
-    loss_rows[row] = loss;
   }
-  loss = warp_sum(loss);
-  if (lane == 0) blk[warp] = loss;
+  sm_m[g][r] = m;
+  sm_s[g][r] = s;
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(loss_sum, blk[0] + blk[1] + blk[2] + blk[3]);
+  if (g == 0) {
+    float loss = 0.f;
+    if (row < M) {
+      float mm = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < CEF_GROUPS; ++i) mm = fmaxf(mm, sm_m[i][r]);
+      float ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < CEF_GROUPS; ++i)
+        if (sm_m[i][r] > -INFINITY) ss += sm_s[i][r] * expf(sm_m[i][r] - mm);
+      const float l = mm + logf(ss);
+      loss = l - label_logit[row];
+      lse[row] = l;
+      loss_rows[row] = loss;
+    }
+    loss = warp_sum(loss);
+    if (r == 0) atomicAdd(loss_sum, loss);
+  }
 }
 
 }  // namespace db200
@@ -507,7 +528,7 @@ extern "C" int db200_ce_finish(db200_stream_t stream_, const float* part_max, co
   DB200_REQUIRE(M > 0 && n_tiles > 0, DB200_E_INVALID, "ce_finish: M and n_tiles must be positive");
   DB200_REQUIRE(part_max && part_sum && label_logit && lse && loss_rows && loss_sum, DB200_E_INVALID,
                 "ce_finish: NULL pointer");
-  ce_finish_kernel<<<(M + 127) / 128, 128, 0, stream>>>(part_max, part_sum, label_logit, lse, loss_rows, loss_sum, M,
+  ce_finish_kernel<<<(M + CEF_ROWS - 1) / CEF_ROWS, CEF_ROWS * CEF_GROUPS, 0, stream>>>(part_max, part_sum, label_logit, lse, loss_rows, loss_sum, M,
                                                     n_tiles);
   return check_launch("ce_finish_kernel");
 }
