@@ -58,6 +58,21 @@ def load_params(n_gpus, workload="dalle_example"):
     return p
 
 
+def ncu_gemm_traffic(workload, launches_per_step):
+    """`roofline.traffic`: DRAM bytes (read + write) per GEMM launch, from the committed ncu capture of the same
+    workload's GEMM launches (profiles/ncu_gemm_step_r01.json; a profiler number, never measured inside this run).
+    None when there is no capture for this workload / launch count."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_gemm_step_r01.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f)
+    except (OSError, ValueError):
+        return None
+    if rec.get("workload") != workload or rec.get("launches") != int(round(launches_per_step)):
+        return None
+    return rec["dram_bytes_per_launch"]
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -346,8 +361,10 @@ def main():
             "clocks": clocks,
             "roofline": {"kernel": "gemm_tc_kernel (tcgen05, all launches of the step)", "bound": "tensor",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                         "peak_kind": f"bf16_tflops_sustained ({peak_kind})", "traffic": None,
-                         "launches_per_step": len(prof) / args.steps, "share_of_step": gemm_ms / ms_total},
+                         "peak_kind": f"bf16_tflops_sustained ({peak_kind})",
+                         "traffic": ncu_gemm_traffic(args.workload, len(prof) / args.steps),
+                         "launches_per_step": len(prof) / args.steps, "share_of_step": gemm_ms / ms_total,
+                         "flops_per_launch": gemm_flops / max(len(prof), 1)},
         }
         if vae_line is not None:
             line["vae"] = vae_line

@@ -132,7 +132,15 @@ __device__ __forceinline__ void stage_put_f32(uint32_t stg, int lane, const floa
                   __float_as_uint(o[g * 4 + 2]), __float_as_uint(o[g * 4 + 3]));
 }
 // smem block -> global rows [row0, row0+32) x 128 bytes starting at element column col0 (ESZ bytes per element)
-template <int ESZ>
+// STREAM: st.global.cs (evict-first) for outputs that are far larger than L2 and would only push the operands out.
+__device__ __forceinline__ void st_global_v4(void* p, const uint4& v, bool stream) {
+  if (stream)
+    asm volatile("st.global.cs.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+  else
+    *reinterpret_cast<uint4*>(p) = v;
+}
+template <int ESZ, bool STREAM = false>
 __device__ __forceinline__ void stage_flush(uint32_t stg, void* D, long long ldd, int row0, int col0, int M, int N,
                                             int lane) {
   constexpr int EPS = 16 / ESZ;  // elements per 16-byte slot
@@ -147,7 +155,7 @@ __device__ __forceinline__ void stage_flush(uint32_t stg, void* D, long long ldd
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint4 v = ld_shared_v4u(((i & 1) ? a1 : a0) + (i >> 1) * 1024);
-      *reinterpret_cast<uint4*>(dst) = v;
+      st_global_v4(dst, v, STREAM);
       dst += step;
     }
   } else {
@@ -155,7 +163,7 @@ __device__ __forceinline__ void stage_flush(uint32_t stg, void* D, long long ldd
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const uint4 v = ld_shared_v4u(((i & 1) ? a1 : a0) + (i >> 1) * 1024);
-      if (col_ok && row0 + i * 4 + rsub < M) *reinterpret_cast<uint4*>(dst) = v;
+      if (col_ok && row0 + i * 4 + rsub < M) st_global_v4(dst, v, STREAM);
       dst += step;
     }
   }
@@ -425,7 +433,7 @@ __device__ __forceinline__ void epi_ce_grad(const GemmParams& p, uint32_t t_addr
       stage_put_bf16(stg, lane, h, o);
     }
     if (p.colsum) stage_colsum_bf16(stg, p.colsum, colp, p.N, lane);
-    stage_flush<2>(stg, p.D, p.ldd, row0, colp, p.M, p.N, lane);
+    stage_flush<2, true>(stg, p.D, p.ldd, row0, colp, p.M, p.N, lane);  // 4 GB of dlogits: stream past L2
   }
 }
 
