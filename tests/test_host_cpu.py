@@ -36,11 +36,28 @@ def test_library_exports_every_symbol_declared_in_the_header():
     assert set(L.EXPORTED_SYMBOLS) == declared, set(L.EXPORTED_SYMBOLS) ^ declared
 
 
-def test_struct_mirrors_match_header_sizes():
+def test_struct_mirrors_match_header_sizes(tmp_path):
+    """The ctypes mirrors must have the size AND field offsets the C compiler gives the structs of the header."""
+    import subprocess
     from dalle_mtf_b200.lib import ConvDesc, GemmEpilogue
-    assert ctypes.sizeof(ConvDesc) == 14 * 4
-    # 4 int32 + float (+4 pad) + 10 pointers/int64 + 2 int32
-    assert ctypes.sizeof(GemmEpilogue) == 16 + 8 + 10 * 8 + 8
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    fields = {"db200_gemm_epilogue": [n for n, _ in GemmEpilogue._fields_],
+              "db200_conv_desc": [n for n, _ in ConvDesc._fields_]}
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "dalle_b200.h"', "int main(void) {"]
+    for st, names in fields.items():
+        src.append(f'  printf("{st} %zu\\n", sizeof({st}));')
+        for n in names:
+            src.append(f'  printf("{st}.{n} %zu\\n", offsetof({st}, {n}));')
+    src += ["  return 0;", "}"]
+    c = tmp_path / "sizes.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(c), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for st, cls in (("db200_gemm_epilogue", GemmEpilogue), ("db200_conv_desc", ConvDesc)):
+        assert ctypes.sizeof(cls) == int(out[st]), st
+        for n, _ in cls._fields_:
+            assert getattr(cls, n).offset == int(out[f"{st}.{n}"]), f"{st}.{n}"
 
 
 def test_no_cpu_fallback_ops_raise_without_a_gpu():
