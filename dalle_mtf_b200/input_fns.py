@@ -1,8 +1,11 @@
-"""Input contract of src/input_fns.py, served from synthetic data.
+"""Input contract of src/input_fns.py.
 
-The reference's tf.data pipelines (JPEG decode, centre-crop + resize, TFRecord parsing, shuffle/batch/prefetch) are
-host I/O outside the hot path ("next" row N2).  What the step functions rely on is the OUTPUT
-contract, reproduced here exactly:
+`dataset.train_path` / `eval_path` == "synthetic" (the *_b200 configs), or a pattern that matches no local file (the
+reference configs name gs:// buckets that cannot be reached here): synthetic data, generated below.  A pattern that
+matches files: the real pipeline of data_pipeline.py (TFRecord / JPEG files -> host decode -> CUDA crop + resize +
+normalise), which yields the image batch already on the GPU.
+
+What the step functions rely on is the OUTPUT contract, reproduced exactly in both cases:
   * images: float32 NHWC [B, size, size, n_channels], (uint8 - 127.5) / 127.5               (input_fns.py:15-21)
   * captions: int32 [B, text_seq_len], truncated / right-padded with params["padding_id"]   (input_fns.py:32-38)
   * vae_input_fn yields (image, image); dalle_input_fn yields (image, caption)              (input_fns.py:64,41-52)
@@ -45,8 +48,30 @@ def synthetic_captions(batch, text_seq_len, padding_id, generator, vocab=50257, 
     return ids
 
 
+def _real_data(params, eval):
+    """True when the configured path matches local files; warns (once per path) when a non-synthetic path matches none."""
+    path = params["dataset"].get("eval_path" if eval else "train_path")
+    if not path or path == "synthetic":
+        return False
+    from .data_pipeline import list_files
+    if list_files(path):
+        return True
+    if path not in _WARNED:
+        _WARNED.add(path)
+        import logging
+        logging.getLogger("dalle_b200").warning("no local files match %r: using SYNTHETIC data of the same shape", path)
+    return False
+
+
+_WARNED = set()
+
+
 def vae_input_fn(params, eval=False):
     """src/input_fns.py:69-104."""
+    if _real_data(params, eval):
+        from .data_pipeline import real_input_fn
+        yield from real_input_fn(params, eval, labeled=False)
+        return
     rank = int(os.environ.get("RANK", "0"))
     g = torch.Generator().manual_seed(1234 + rank + (10_000 if eval else 0))
     B = _local_batch(params, eval)
@@ -59,6 +84,10 @@ def vae_input_fn(params, eval=False):
 
 def dalle_input_fn(params, eval=False):
     """src/input_fns.py:106-120."""
+    if _real_data(params, eval):
+        from .data_pipeline import real_input_fn
+        yield from real_input_fn(params, eval, labeled=True)
+        return
     rank = int(os.environ.get("RANK", "0"))
     g = torch.Generator().manual_seed(1234 + rank + (10_000 if eval else 0))
     B = _local_batch(params, eval)

@@ -17,6 +17,7 @@ c_i64 = ctypes.c_int64
 c_f32 = ctypes.c_float
 c_vp = ctypes.c_void_p
 c_sz = ctypes.c_size_t
+c_u64 = ctypes.c_uint64
 
 EPI_STORE, EPI_ATOMIC, EPI_RELU_BWD, EPI_CE_STATS, EPI_CE_GRAD = 0, 1, 2, 3, 4
 
@@ -53,6 +54,11 @@ _SIGNATURES = {
     "db200_gemm_bf16": [c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_i64, c_vp, c_i64, c_int, c_int, c_int,
                         ctypes.POINTER(GemmEpilogue)],
     "db200_gemm_ce_tiles": [c_int],
+    "db200_crc32c": [c_vp, c_u64, c_vp],
+    "db200_tfrecord_masked_crc": [c_vp, c_u64, c_vp],
+    "db200_tfrecord_frame": [c_vp, c_u64, c_vp],
+    "db200_tfrecord_index": [c_vp, c_u64, c_int, c_vp, c_vp, c_u64, c_vp],
+    "db200_image_crop_resize_normalize": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int],
     "db200_ce_finish": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int],
     "db200_attn_causal_fwd": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32],
     "db200_attn_causal_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_f32],

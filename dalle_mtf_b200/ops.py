@@ -360,3 +360,18 @@ def mse_fwd_bwd(pred, target, dpred, loss_accum, scale):
     L.require_device()
     check(L.load().db200_mse_fwd_bwd(stream_ptr(), ptr(pred), ptr(target), ptr(dpred), ptr(loss_accum),
                                      pred.numel(), scale), "mse_fwd_bwd")
+
+
+# ----------------------------------------------------------------------------------------------- input pipeline (N2)
+def image_crop_resize_normalize(packed_u8, offsets_i64, heights_i32, widths_i32, boxes_f32, out_f32, channels, size):
+    """decode_img's crop_and_resize + (x - 127.5) / 127.5 for a packed batch of decoded uint8 images (input_fns.py:4-21)."""
+    L.require_device()
+    _chk(packed_u8, torch.uint8, "packed"); _chk(offsets_i64, torch.int64, "offsets")
+    _chk(heights_i32, torch.int32, "heights"); _chk(widths_i32, torch.int32, "widths")
+    _chk(boxes_f32, F32, "boxes"); _chk(out_f32, F32, "out")
+    B = heights_i32.numel()
+    assert out_f32.shape == (B, size, size, channels) and boxes_f32.shape == (B, 4)
+    check(L.load().db200_image_crop_resize_normalize(stream_ptr(), ptr(packed_u8), ptr(offsets_i64), ptr(heights_i32),
+                                                     ptr(widths_i32), ptr(boxes_f32), ptr(out_f32), B, channels, size),
+          "db200_image_crop_resize_normalize")
+    return out_f32

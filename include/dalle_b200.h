@@ -226,6 +226,28 @@ int db200_argmax_rows_f32(db200_stream_t stream, const float* x, int32_t* idx, i
 int db200_mse_fwd_bwd(db200_stream_t stream, const float* pred, const float* target, float* dpred_or_null,
                       float* loss_accum, size_t n, float scale);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * N2/N3  data formats either side of the step ("next" rows of SURVEY.md section 8f).
+ *   Host-memory functions (no CUDA): CRC-32C, TFRecord framing / indexing.  Replace tf.io.TFRecordWriter
+ *   (src/data/create_tfrecords.py:153-178) and tf.data.TFRecordDataset (src/input_fns.py:80,116).
+ *     record = u64le length | u32le masked_crc(length bytes) | data | u32le masked_crc(data)
+ *     masked_crc(x) = rotr15(crc32c(x)) + 0xa282ead8
+ *   db200_tfrecord_index: payload offsets / lengths of every record in a file image; *n_records = records found (may
+ *   exceed max_records: call again with larger arrays); truncated / corrupt input is DB200_E_INVALID.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int db200_crc32c(const void* data, uint64_t n, uint32_t* crc_out);
+int db200_tfrecord_masked_crc(const void* data, uint64_t n, uint32_t* crc_out);
+int db200_tfrecord_frame(const void* data, uint64_t n, void* out_n_plus_16_bytes);
+int db200_tfrecord_index(const void* buf, uint64_t n, int verify_crc, uint64_t* offsets, uint64_t* lengths,
+                         uint64_t max_records, uint64_t* n_records);
+/* Batch of decoded uint8 HWC images (concatenated in `packed`, image b at byte offsets[b], heights[b] x widths[b] x
+ * channels) -> out f32 NHWC [batch][out_size][out_size][channels] = (crop_and_resize(img, boxes[b]) - 127.5) / 127.5
+ * with TensorFlow's bilinear CropAndResize semantics (extrapolation value 0).  boxes[b] = {y1, x1, y2, x2} normalised.
+ * Replaces decode_img's tf.image.crop_and_resize + scaling, src/input_fns.py:4-21.  All pointers are device pointers. */
+int db200_image_crop_resize_normalize(db200_stream_t stream, const uint8_t* packed, const int64_t* offsets,
+                                      const int32_t* heights, const int32_t* widths, const float* boxes, float* out,
+                                      int batch, int channels, int out_size);
+
 #ifdef __cplusplus
 }
 #endif
