@@ -43,6 +43,8 @@ def main(n_images=512, size=256, batch=32):
     workers = min(16, len(os.sched_getaffinity(0)))
     pool = ThreadPoolExecutor(workers)
     rb = dp.record_batches(params["dataset"]["train_path"], batch, True, 0)
+    for _ in range(2):  # warm-up: thread pool, PIL plugins, the native library
+        dp.host_stage(next(rb), params, True, True, pool)
     t0 = time.perf_counter()
     hbs = [dp.host_stage(next(rb), params, True, True, pool) for _ in range(12)]
     host_s = (time.perf_counter() - t0) / 12
