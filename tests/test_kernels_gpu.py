@@ -31,7 +31,8 @@ def bf(x):
 
 # ------------------------------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 512), (200, 264, 200), (1000, 128, 328), (2048, 1536, 512),
-                                   (1, 8, 8), (129, 8, 72)])
+                                   (1, 8, 8), (129, 8, 72),
+                                   (2504, 2056, 200)])  # 10 x 9 ragged 256x256 pair tiles >= 74: the 2-CTA kernel
 @pytest.mark.parametrize("a_mn", [False, True])
 @pytest.mark.parametrize("b_mn", [False, True])
 def test_gemm_all_operand_layouts(ops, M, N, K, a_mn, b_mn):
@@ -74,6 +75,57 @@ def test_gemm_epilogues(ops):
     ops.linear_wgrad(X.to(DEV), DY2.to(DEV), dw)                               # split-K + vector red.add, accumulates
     assert relmax(dw, 1.0 + X.float().t() @ DY2.float()) < 1e-4
     assert L.EPI_ATOMIC == 1
+
+
+def test_gemm_epilogues_on_the_2cta_kernel(ops):
+    """Same epilogues on a ragged shape big enough (>= 74 pair tiles) to take the cta_group::2 path, including rows /
+    columns that end inside a 256x256 tile and the half of a pair that is entirely out of range."""
+    from dalle_mtf_b200 import lib as L
+    g = torch.Generator().manual_seed(11)
+    M, N, K = 2600, 2056, 136                      # 11 x 9 pair tiles; last pair: rows 2560..2599 only in CTA 0
+    A, W = bf(torch.randn(M, K, generator=g)), bf(torch.randn(K, N, generator=g) * 0.1)
+    bias, res = torch.randn(N, generator=g), bf(torch.randn(M, N, generator=g))
+    a, w = A.to(DEV), W.to(DEV)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.linear_fwd(a, w, out, bias=bias.to(DEV), relu=True, residual=res.to(DEV))
+    assert relmax(out, torch.relu(A.float() @ W.float() + bias) + res.float()) < 1e-2
+    out32 = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    ops.gemm(a, w, out32, M, N, K, a_mn=False, b_mn=True, alpha=0.5, bias=bias.to(DEV))
+    assert relmax(out32, 0.5 * (A.float() @ W.float()) + bias) < 1e-5
+    # ReLU-masked dgrad with the fused bias gradient: dx[M, N] = (dy[M, K2] @ W2^T) * (h > 0)
+    K2 = 264
+    DY, W2, H = bf(torch.randn(M, K2, generator=g)), bf(torch.randn(N, K2, generator=g) * 0.1), bf(torch.randn(M, N, generator=g))
+    dx = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    cs = torch.zeros(N, device=DEV)
+    ops.linear_dgrad(DY.to(DEV), W2.to(DEV), dx, relu_mask_of=H.to(DEV), colsum=cs)
+    assert relmax(dx, (DY.float() @ W2.float().t()) * (H.float() > 0)) < 1e-2
+    assert relmax(cs, dx.float().sum(0)) < 1e-5
+    # cross-entropy statistics and gradient over 11 x 8 pair tiles
+    T, d, V, Vpad = 2600, 128, 2000, 2048
+    X = bf(torch.randn(T, d, generator=g))
+    Wv = torch.zeros(d, Vpad); Wv[:, :V] = torch.randn(d, V, generator=g) * 0.2; Wv = bf(Wv)
+    bv = torch.randn(V, generator=g) * 0.1
+    labels = torch.randint(0, V, (T,), generator=g, dtype=torch.int32)
+    logits = X.float() @ Wv.float()[:, :V] + bv
+    lse_ref = torch.logsumexp(logits, -1)
+    nt = ops.ce_tiles(Vpad)
+    pm, ps = torch.empty(nt, T, device=DEV), torch.empty(nt, T, device=DEV)
+    ll, lse, lr, lsum = torch.zeros(T, device=DEV), torch.empty(T, device=DEV), torch.empty(T, device=DEV), torch.zeros(1, device=DEV)
+    x, wv, lab = X.to(DEV), Wv.to(DEV), labels.to(DEV)
+    bpad = torch.zeros(Vpad, device=DEV); bpad[:V] = bv.to(DEV)
+    ops.gemm(x, wv, None, T, Vpad, d, b_mn=True, mode=L.EPI_CE_STATS, bias=bpad, labels=lab, part_max=pm, part_sum=ps,
+             label_logit=ll, n_valid=V)
+    ops.ce_finish(pm, ps, ll, lse, lr, lsum)
+    assert relmax(lse, lse_ref) < 1e-4
+    assert relmax(lr, lse_ref - logits[torch.arange(T), labels.long()]) < 1e-3
+    dl = torch.full((T, Vpad), 7.0, dtype=torch.bfloat16, device=DEV)
+    cs2 = torch.zeros(Vpad, device=DEV)
+    ops.gemm(x, wv, dl, T, Vpad, d, b_mn=True, mode=L.EPI_CE_GRAD, alpha=1.0 / T, bias=bpad, labels=lab, lse=lse,
+             n_valid=V, colsum=cs2)
+    p = torch.softmax(logits, -1); p[torch.arange(T), labels.long()] -= 1
+    ref = torch.zeros(T, Vpad); ref[:, :V] = p / T
+    assert relmax(dl, ref) < 1e-2 and (dl[:, V:] == 0).all()
+    assert relmax(cs2, dl.float().sum(0)) < 1e-4
 
 
 def test_gemm_is_linear_at_full_size(ops):
