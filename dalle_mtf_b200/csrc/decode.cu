@@ -1,0 +1,176 @@
+// N4 — incremental (KV-cache) decoding kernels: the "is_incremental_inference" path the reference sketches in
+// src/dalle_mtf/models.py:246-254, 281-285 (new k/v blended into the cached states at context.position - 1, the query of
+// the current position attends to keys <= position) but never wires up (PREDICT raises NotImplementedError,
+// src/model_fns.py:135-136).  All of it is HBM / latency bound work on B rows per step.
+//
+//   embed_fwd_at   x[b,:] = wte[ids[b],:] + wpe[pos,:]                     (models.py:186-219 at one position)
+//   attn_decode    append this step's k,v to the cache at `pos`, then out[b,h,:] = softmax_j<=pos(scale q.k_j) v_j
+//                  fp32 scores / softmax, P rounded to bf16 for the PV product (same policy as attn.cu)
+//   sample_rows    idx = lo + argmax_{lo<=c<hi}(logits[c] * inv_temp + gumbel(u[c-lo]))   (first maximum; u NULL = greedy)
+//   onehot_rows    y[r, idx[r]-offset] = 1, 0 elsewhere (codebook lookup input for the VAE decoder, vae_tf/models.py:127)
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace db200 {
+
+__global__ void embed_at_kernel(const int* __restrict__ ids, const bf16* __restrict__ wte, const bf16* __restrict__ wpe,
+                                bf16* __restrict__ out, int d, int V, int pos) {
+  const int b = blockIdx.x;
+  int id = ids[b];
+  id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+  const bf16* w = wte + (long long)id * d;
+  const bf16* p = wpe + (long long)pos * d;
+  for (int i = threadIdx.x; i < d; i += blockDim.x)
+    out[(long long)b * d + i] = __float2bfloat16(__bfloat162float(w[i]) + __bfloat162float(p[i]));
+}
+
+// one CTA per (head, batch); 128 threads.  scores live in dynamic shared memory (pos + 1 floats).
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_decode_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc, bf16* __restrict__ out,
+                   int S, int H, int pos, float scale) {
+  extern __shared__ float sc[];
+  __shared__ float red[4];
+  __shared__ float qs[DH];
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bf16* q = qkv + ((long long)b * 3 + 0) * H * DH + (long long)h * DH;
+  const bf16* k = qkv + ((long long)b * 3 + 1) * H * DH + (long long)h * DH;
+  const bf16* v = qkv + ((long long)b * 3 + 2) * H * DH + (long long)h * DH;
+  bf16* kcb = kc + ((long long)b * S * H + h) * DH;  // + j * H * DH
+  bf16* vcb = vc + ((long long)b * S * H + h) * DH;
+  for (int t = tid; t < DH; t += 128) {
+    kcb[(long long)pos * H * DH + t] = k[t];
+    vcb[(long long)pos * H * DH + t] = v[t];
+    qs[t] = __bfloat162float(q[t]);
+  }
+  __syncthreads();  // this block's own global writes are visible to it after the barrier
+  const int n = pos + 1;
+  float mx = -INFINITY;
+  for (int j = warp; j < n; j += 4) {
+    const bf16* kj = kcb + (long long)j * H * DH;
+    float s = 0.f;
+#pragma unroll
+    for (int e = lane; e < DH; e += 32) s += qs[e] * __bfloat162float(kj[e]);
+    s = warp_sum(s) * scale;
+    if (lane == 0) sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int j = tid; j < n; j += 128) {
+    const float p = __expf(sc[j] - mx);
+    sum += p;
+    sc[j] = __bfloat162float(__float2bfloat16(p));  // P goes through bf16 for the PV product, the sum does not
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = red[0] + red[1] + red[2] + red[3];
+  const float inv = 1.f / sum;
+  for (int t = tid; t < DH; t += 128) {
+    float acc = 0.f;
+    for (int j = 0; j < n; ++j) acc += sc[j] * __bfloat162float(vcb[(long long)j * H * DH + t]);
+    out[((long long)b * H + h) * DH + t] = __float2bfloat16(acc * inv);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sample_rows_kernel(const float* __restrict__ logits, const float* __restrict__ u, int* __restrict__ idx, long long ld,
+                   int lo, int hi, float inv_temp) {
+  __shared__ float bv[8];
+  __shared__ int bi[8];
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* row = logits + (long long)r * ld;
+  const int n = hi - lo;
+  float best = -INFINITY;
+  int arg = 0x7fffffff;
+  for (int c = tid; c < n; c += 256) {
+    float x = row[lo + c] * inv_temp;
+    if (u) x += -logf(-logf(u[(long long)r * n + c]));
+    if (x > best || (x == best && c < arg)) { best = x; arg = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, arg, o);
+    if (ov > best || (ov == best && oi < arg)) { best = ov; arg = oi; }
+  }
+  if (lane == 0) { bv[warp] = best; bi[warp] = arg; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (bv[w] > best || (bv[w] == best && bi[w] < arg)) { best = bv[w]; arg = bi[w]; }
+    idx[r] = lo + (arg == 0x7fffffff ? 0 : arg);  // all -inf / NaN row: first allowed id
+  }
+}
+
+__global__ void onehot_rows_kernel(const int* __restrict__ idx, float* __restrict__ y, int K, int offset) {
+  const int r = blockIdx.x;
+  const int hot = idx[r] - offset;
+  for (int c = threadIdx.x; c < K; c += blockDim.x) y[(long long)r * K + c] = (c == hot) ? 1.f : 0.f;
+}
+
+}  // namespace db200
+
+using namespace db200;
+
+extern "C" int db200_embed_fwd_at(db200_stream_t stream_, const int32_t* ids, const void* wte, const void* wpe,
+                                  void* out, int B, int d, int V, int n_pos, int pos) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(ids && wte && wpe && out, DB200_E_INVALID, "embed_fwd_at: null pointer");
+  DB200_REQUIRE(B > 0 && d > 0 && V > 0 && pos >= 0 && pos < n_pos, DB200_E_INVALID,
+                "embed_fwd_at: B %d d %d V %d pos %d of %d", B, d, V, pos, n_pos);
+  embed_at_kernel<<<B, 256, 0, stream>>>(ids, static_cast<const bf16*>(wte), static_cast<const bf16*>(wpe),
+                                         static_cast<bf16*>(out), d, V, pos);
+  return check_launch("embed_at_kernel");
+}
+
+extern "C" int db200_attn_decode(db200_stream_t stream_, const void* qkv_step, void* k_cache, void* v_cache, void* out,
+                                 int B, int S, int H, int dh, int pos, float scale) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(qkv_step && k_cache && v_cache && out, DB200_E_INVALID, "attn_decode: null pointer");
+  DB200_REQUIRE(B > 0 && H > 0 && S > 0 && pos >= 0 && pos < S, DB200_E_INVALID, "attn_decode: B %d H %d pos %d of %d",
+                B, H, pos, S);
+  DB200_REQUIRE(dh == 64 || dh == 128, DB200_E_UNSUPPORTED, "attn_decode: head_dim %d not in {64,128}", dh);
+  DB200_REQUIRE((size_t)(pos + 1) * 4 <= 200 * 1024, DB200_E_UNSUPPORTED, "attn_decode: %d keys exceed shared memory",
+                pos + 1);
+  const size_t smem = (size_t)(pos + 1) * sizeof(float);
+  dim3 grid(H, B);
+  if (dh == 128) {
+    if (smem > 48 * 1024)
+      DB200_CUDA(cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_decode_kernel<128><<<grid, 128, smem, stream>>>(static_cast<const bf16*>(qkv_step),
+                                                         static_cast<bf16*>(k_cache), static_cast<bf16*>(v_cache),
+                                                         static_cast<bf16*>(out), S, H, pos, scale);
+  } else {
+    if (smem > 48 * 1024)
+      DB200_CUDA(cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attn_decode_kernel<64><<<grid, 128, smem, stream>>>(static_cast<const bf16*>(qkv_step), static_cast<bf16*>(k_cache),
+                                                        static_cast<bf16*>(v_cache), static_cast<bf16*>(out), S, H, pos,
+                                                        scale);
+  }
+  return check_launch("attn_decode_kernel");
+}
+
+extern "C" int db200_sample_rows(db200_stream_t stream_, const float* logits, const float* u_or_null, int32_t* idx,
+                                 int rows, long long ld, int lo, int hi, float inv_temp) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(logits && idx, DB200_E_INVALID, "sample_rows: null pointer");
+  DB200_REQUIRE(rows > 0 && lo >= 0 && hi > lo && hi <= ld, DB200_E_INVALID, "sample_rows: rows %d range [%d,%d) ld %lld",
+                rows, lo, hi, ld);
+  DB200_REQUIRE(inv_temp > 0.f, DB200_E_INVALID, "sample_rows: inv_temp must be positive");
+  sample_rows_kernel<<<rows, 256, 0, stream>>>(logits, u_or_null, idx, ld, lo, hi, inv_temp);
+  return check_launch("sample_rows_kernel");
+}
+
+extern "C" int db200_onehot_rows_f32(db200_stream_t stream_, const int32_t* idx, float* y, int rows, int K,
+                                     int offset) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(idx && y && rows > 0 && K > 0, DB200_E_INVALID, "onehot_rows: bad argument");
+  onehot_rows_kernel<<<rows, 256, 0, stream>>>(idx, y, K, offset);
+  return check_launch("onehot_rows_kernel");
+}

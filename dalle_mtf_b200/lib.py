@@ -54,6 +54,10 @@ _SIGNATURES = {
     "db200_gemm_bf16": [c_vp, c_vp, c_int, c_i64, c_vp, c_int, c_i64, c_vp, c_i64, c_int, c_int, c_int,
                         ctypes.POINTER(GemmEpilogue)],
     "db200_gemm_ce_tiles": [c_int],
+    "db200_embed_fwd_at": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int],
+    "db200_attn_decode": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32],
+    "db200_sample_rows": [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_f32],
+    "db200_onehot_rows_f32": [c_vp, c_vp, c_vp, c_int, c_int, c_int],
     "db200_crc32c": [c_vp, c_u64, c_vp],
     "db200_tfrecord_masked_crc": [c_vp, c_u64, c_vp],
     "db200_tfrecord_frame": [c_vp, c_u64, c_vp],

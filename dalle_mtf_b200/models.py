@@ -52,6 +52,17 @@ class DALLE:
         return loss, loss_batch
 
 
+    def sample(self, text_ids, temperature=1.0, generator=None):
+        """Autoregressive generation with a K/V cache ("next" row N4; the reference stubs inference):
+        text_ids int [B, text_seq_len] -> int32 [B, text_seq_len + image_seq_len], image positions sampled from
+        softmax(logits / temperature) restricted to the image-token ids (temperature 0 = greedy)."""
+        from .sampling import DalleSampler
+        if getattr(self, "_sampler", None) is None:
+            self._sampler = DalleSampler(self.engine)
+        text_ids = text_ids.to(device=self.engine.device, dtype=torch.int32).contiguous()
+        return self._sampler.generate(text_ids, temperature, generator)
+
+
 class DiscreteVAE:
     def __init__(self, num_tokens, dimensions, convblocks, dim=512, hidden_dim=64, input_channels=3,
                  recompute_grad=False, use_bf16=False, stack_factor=1):
@@ -79,3 +90,9 @@ class DiscreteVAE:
         if not return_recon_loss:
             return out
         return acc, out
+
+    def decode(self, image_token_ids, offset=0):
+        """Sampled image-token ids [B, image_seq_len] (minus `offset`, e.g. DALLE's text_vocab_size) -> images fp32 NHWC:
+        one-hot codes through the tied codebook and the decoder (src/vae_tf/models.py:123-163)."""
+        ids = image_token_ids.to(device=self.engine.device, dtype=torch.int32).contiguous()
+        return self.engine.decode_tokens(ids, offset)

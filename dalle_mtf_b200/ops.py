@@ -375,3 +375,45 @@ def image_crop_resize_normalize(packed_u8, offsets_i64, heights_i32, widths_i32,
                                                      ptr(widths_i32), ptr(boxes_f32), ptr(out_f32), B, channels, size),
           "db200_image_crop_resize_normalize")
     return out_f32
+
+
+# ----------------------------------------------------------------------------------------------- decoding (N4)
+def embed_fwd_at(ids, wte, wpe, out, pos):
+    """x[b,:] = wte[ids[b]] + wpe[pos]   (models.py:186-219 at one position)."""
+    L.require_device()
+    _chk(ids, I32, "ids"); _chk(wte, BF16, "wte"); _chk(wpe, BF16, "wpe"); _chk(out, BF16, "out")
+    B, d = out.shape
+    check(L.load().db200_embed_fwd_at(stream_ptr(), ptr(ids), ptr(wte), ptr(wpe), ptr(out), B, d, wte.shape[0],
+                                      wpe.shape[0], int(pos)), "db200_embed_fwd_at")
+    return out
+
+
+def attn_decode(qkv_step, k_cache, v_cache, out, pos, scale):
+    """Append this position's k, v to the caches and attend with its q over keys <= pos (models.py:246-254, 281-299)."""
+    L.require_device()
+    _chk(qkv_step, BF16, "qkv_step"); _chk(k_cache, BF16, "k_cache"); _chk(v_cache, BF16, "v_cache"); _chk(out, BF16, "out")
+    B, S, H, dh = k_cache.shape
+    assert v_cache.shape == k_cache.shape and qkv_step.numel() == B * 3 * H * dh and out.numel() == B * H * dh
+    check(L.load().db200_attn_decode(stream_ptr(), ptr(qkv_step), ptr(k_cache), ptr(v_cache), ptr(out), B, S, H, dh,
+                                     int(pos), float(scale)), "db200_attn_decode")
+    return out
+
+
+def sample_rows(logits, u, idx, lo, hi, inv_temp=1.0):
+    """idx[r] = lo + argmax over [lo, hi) of logits * inv_temp + Gumbel(u); u None = greedy (first maximum)."""
+    L.require_device()
+    _chk(logits, F32, "logits"); _chk(u, F32, "u"); _chk(idx, I32, "idx")
+    rows = logits.shape[0]
+    if u is not None:
+        assert u.shape == (rows, hi - lo)
+    check(L.load().db200_sample_rows(stream_ptr(), ptr(logits), ptr(u), ptr(idx), rows, logits.stride(0), int(lo),
+                                     int(hi), float(inv_temp)), "db200_sample_rows")
+    return idx
+
+
+def onehot_rows(idx, y, offset=0):
+    L.require_device()
+    _chk(idx, I32, "idx"); _chk(y, F32, "y")
+    rows, K = y.shape
+    check(L.load().db200_onehot_rows_f32(stream_ptr(), ptr(idx), ptr(y), rows, K, int(offset)), "db200_onehot_rows_f32")
+    return y

@@ -271,22 +271,10 @@ class VaeEngine:
         ops.argmax_rows(logits, self._b["idx"], rows, self.K)
         return self._b["idx"].view(img.shape[0], self.image_seq_len)
 
-    def forward(self, img, u, temperature=1.0, hard=True, loss_accum=None):
-        """DiscreteVAE.forward(return_recon_loss=True) (src/vae_tf/models.py:165-184).  u: fp32 uniform noise
-        [B*h*w, K] in [1e-9, 1) or None (no noise).  Adds sum((img-out)^2)/numel into loss_accum; returns recon."""
-        B = img.shape[0]
-        logits = self.encode_logits(img, for_training=True)
+    def _decode_from_z(self, B):
+        """DiscreteVAE.decoder after the tied codebook matmul (src/vae_tf/models.py:129-163): b["z_f32"] -> recon fp32."""
         b = self._b
         rows = B * self.hw * self.hw
-        self._tau = float(temperature)
-        ops.gumbel_softmax_fwd(logits, u, b["y_soft"], b["y_out"], b["idx"], rows, self.K, self._tau, hard)
-        if self._cb_tc:   # z = y @ C^T with y, C split into bf16 hi + lo (the lo*lo term is below fp32 resolution)
-            ops.split_f32(b["y_out"], b["y_hi"], b["y_lo"])
-            self._mm_split([b["y_hi"], b["y_hi"], b["y_lo"]], [self.cb_hi, self.cb_lo, self.cb_hi], b["z_f32"], rows,
-                           self.n_hid, self.K, b_mn=False)
-        else:
-            ops.rowmatmul(b["y_out"], self.P("codebook/codebook"), b["z_f32"], rows, self.K, self.n_hid,
-                          b_transposed=True)                                                 # models.py:127
         x = self._to_act(b["z_f32"], b["z"].view(rows, self.n_hid)).view(B, self.hw, self.hw, self.n_hid)
         self._z = x
         for (kind, name, cin, ch, res), sv in zip(self.dec, b["dec"]):
@@ -298,7 +286,41 @@ class VaeEngine:
         self._dec_last = x
         ops.conv2d_fwd(self._desc(B, self.H, self.dec_out_cin, self.C, 1, 1), x, self.P("decoder/conv2d/kernel"),
                        self.P("decoder/conv2d/bias"), None, b["recon_act"])                   # models.py:155
-        recon = self._to_f32(b["recon_act"], b["recon"])
+        return self._to_f32(b["recon_act"], b["recon"])
+
+    def _codebook_lookup(self, B):
+        """z = y @ codebook^T for b["y_out"] (src/vae_tf/models.py:127, tied weight)."""
+        b = self._b
+        rows = B * self.hw * self.hw
+        if self._cb_tc:   # z = y @ C^T with y, C split into bf16 hi + lo (the lo*lo term is below fp32 resolution)
+            ops.split_f32(b["y_out"], b["y_hi"], b["y_lo"])
+            self._mm_split([b["y_hi"], b["y_hi"], b["y_lo"]], [self.cb_hi, self.cb_lo, self.cb_hi], b["z_f32"], rows,
+                           self.n_hid, self.K, b_mn=False)
+        else:
+            ops.rowmatmul(b["y_out"], self.P("codebook/codebook"), b["z_f32"], rows, self.K, self.n_hid,
+                          b_transposed=True)
+
+    def decode_tokens(self, idx, offset=0):
+        """Image-token ids int32 [B, image_seq_len] (minus `offset`) -> reconstruction fp32 NHWC [B,H,W,C] in [-1,1]-ish:
+        one-hot codes through the tied codebook and the decoder — the generation-side counterpart of encode_tokens."""
+        B = idx.shape[0]
+        self._alloc(B)
+        rows = B * self.hw * self.hw
+        ops.onehot_rows(idx.reshape(rows).contiguous(), self._b["y_out"], offset)
+        self._codebook_lookup(B)
+        return self._decode_from_z(B)
+
+    def forward(self, img, u, temperature=1.0, hard=True, loss_accum=None):
+        """DiscreteVAE.forward(return_recon_loss=True) (src/vae_tf/models.py:165-184).  u: fp32 uniform noise
+        [B*h*w, K] in [1e-9, 1) or None (no noise).  Adds sum((img-out)^2)/numel into loss_accum; returns recon."""
+        B = img.shape[0]
+        logits = self.encode_logits(img, for_training=True)
+        b = self._b
+        rows = B * self.hw * self.hw
+        self._tau = float(temperature)
+        ops.gumbel_softmax_fwd(logits, u, b["y_soft"], b["y_out"], b["idx"], rows, self.K, self._tau, hard)
+        self._codebook_lookup(B)
+        recon = self._decode_from_z(B)
         self._img = img
         if loss_accum is None:
             loss_accum = self.grads[self.aux_off:self.aux_off + 1]

@@ -248,6 +248,26 @@ int db200_image_crop_resize_normalize(db200_stream_t stream, const uint8_t* pack
                                       const int32_t* heights, const int32_t* widths, const float* boxes, float* out,
                                       int batch, int channels, int out_size);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * N4  incremental decoding with a K/V cache ("next" row of SURVEY.md section 8f): the path the reference sketches with
+ *     is_incremental_inference / context (src/dalle_mtf/models.py:246-254, 281-285) but leaves unreachable
+ *     (PREDICT raises NotImplementedError, src/model_fns.py:135-136).
+ *   embed_fwd_at : out[b,:] = wte[ids[b],:] + wpe[pos,:]                                       (bf16, one position)
+ *   attn_decode  : qkv_step bf16 [B][3][H][dh] = this position's q|k|v; k,v are written into k_cache / v_cache
+ *                  (bf16 [B][S][H][dh]) at `pos`, then out[b,h,:] = softmax_{j<=pos}(scale q.k_j) v_j  (bf16 [B][H][dh])
+ *   sample_rows  : idx[r] = lo + argmax_{lo<=c<hi}(logits[r][c] * inv_temp - log(-log(u[r][c-lo]))), first maximum;
+ *                  u NULL = greedy.  logits f32 [rows][ld], u f32 [rows][hi-lo] uniform in (0,1).
+ *   onehot_rows  : y[r][c] = (c == idx[r] - offset), f32 [rows][K]   (input of the tied codebook matmul,
+ *                  src/vae_tf/models.py:127, when decoding sampled image tokens)
+ * ------------------------------------------------------------------------------------------------------------------ */
+int db200_embed_fwd_at(db200_stream_t stream, const int32_t* ids, const void* wte_bf16, const void* wpe_bf16,
+                       void* out_bf16, int B, int d, int V, int n_positions, int pos);
+int db200_attn_decode(db200_stream_t stream, const void* qkv_step_bf16, void* k_cache_bf16, void* v_cache_bf16,
+                      void* out_bf16, int B, int S, int H, int dh, int pos, float scale);
+int db200_sample_rows(db200_stream_t stream, const float* logits, const float* u_or_null, int32_t* idx, int rows,
+                      long long ld, int lo, int hi, float inv_temp);
+int db200_onehot_rows_f32(db200_stream_t stream, const int32_t* idx, float* y, int rows, int K, int offset);
+
 #ifdef __cplusplus
 }
 #endif
