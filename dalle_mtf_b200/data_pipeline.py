@@ -223,20 +223,37 @@ def real_input_fn(params, eval, labeled, seed=1234, device=None, workers=None, p
     pattern = ds["eval_path" if eval else "train_path"]
     if device is None:
         device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    pool = ThreadPoolExecutor(max_workers=workers or min(16, (os.cpu_count() or 4)))
+    pool = ThreadPoolExecutor(max_workers=workers or min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity")
+                                                          else (os.cpu_count() or 4)))
     q = queue.Queue(maxsize=prefetch)
+    stop = threading.Event()
+
+    def put(x):
+        while not stop.is_set():
+            try:
+                q.put(x, timeout=0.2)
+                return True
+            except queue.Full:
+                continue
+        return False
 
     def produce():
         try:
             for items in record_batches(pattern, gb, not eval, seed, tfrecords):
-                q.put(host_stage(items[rank * lb:(rank + 1) * lb], params, labeled, tfrecords, pool))
+                if not put(host_stage(items[rank * lb:(rank + 1) * lb], params, labeled, tfrecords, pool)):
+                    return
         except BaseException as e:  # surfaced in the consumer
-            q.put(e)
+            put(e)
 
-    threading.Thread(target=produce, daemon=True, name="db200-input").start()
-    while True:
-        hb = q.get()
-        if isinstance(hb, BaseException):
-            raise hb
-        img = device_stage(hb, params, device)
-        yield (img, hb.labels) if labeled else (img, img)
+    t = threading.Thread(target=produce, daemon=True, name="db200-input")
+    t.start()
+    try:
+        while True:
+            hb = q.get()
+            if isinstance(hb, BaseException):
+                raise hb
+            img = device_stage(hb, params, device)
+            yield (img, hb.labels) if labeled else (img, img)
+    finally:  # generator closed / garbage-collected: stop the producer and release its threads
+        stop.set()
+        pool.shutdown(wait=False, cancel_futures=True)

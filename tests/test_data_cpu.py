@@ -266,3 +266,42 @@ def test_input_fns_switch_between_synthetic_and_real(tmp_path):
     assert input_fns._real_data(params, eval=True) is False          # warns, falls back to the synthetic stand-in
     _write_shards(tmp_path, [2], prefix="none")
     assert input_fns._real_data(params, eval=True) is True
+
+
+def test_real_input_fn_streams_batches_and_stops_its_threads(tmp_path, monkeypatch):
+    """Host side of real_input_fn (record stream -> thread-pool decode -> prefetch queue) with the device stage stubbed:
+    batches keep coming across epochs, labels follow the records, and closing the generator stops the producer."""
+    import threading
+    import time
+    import torch
+    rng = np.random.default_rng(0)
+    with tfrecord.TFRecordWriter(tmp_path / "a_0.tfrecords") as w:
+        for i in range(10):
+            w.write(tfrecord.encode_example({"image": tfrecord.bytes_feature(_jpeg(rng, 16, 16)),
+                                             "caption": tfrecord.int64_feature([i, i + 1])}))
+    seen = []
+    monkeypatch.setattr(dp, "device_stage", lambda hb, params, device: (seen.append(hb), torch.zeros(hb.heights.numel(), 8, 8, 3))[1])
+    params = {"dataset": {"train_path": str(tmp_path / "a_*.tfrecords"), "eval_path": str(tmp_path / "a_*.tfrecords"),
+                          "image_size": 8}, "train_batch_size": 4, "eval_batch_size": 4, "text_seq_len": 3, "n_channels": 3}
+    before = threading.active_count()
+    it = dp.real_input_fn(params, True, True, device="cpu")
+    firsts = []
+    for _ in range(5):                                   # 10 examples, batch 4 -> 2 batches per epoch: crosses epochs
+        img, cap = next(it)
+        assert img.shape == (4, 8, 8, 3) and cap.shape == (4, 3)
+        firsts.append(cap[:, 0].tolist())
+        assert (cap[:, 1] == cap[:, 0] + 1).all() and (cap[:, 2] == 50257).all()
+    assert firsts[0] == [0, 1, 2, 3] and firsts[1] == [4, 5, 6, 7] and firsts[2] == [0, 1, 2, 3]   # eval: file order, repeat
+    assert threading.active_count() > before
+    it.close()
+    deadline = time.time() + 5
+    while threading.active_count() > before and time.time() < deadline:
+        time.sleep(0.05)
+    assert threading.active_count() == before
+    # rank 1 of 2 decodes only its half of every global batch
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    it = dp.real_input_fn(params, True, True, device="cpu")
+    _, cap = next(it)
+    assert cap[:, 0].tolist() == [2, 3]
+    it.close()
