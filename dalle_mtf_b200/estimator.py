@@ -4,8 +4,6 @@ train_vae_tf.py:51-93): build once via model_fn, restore the latest checkpoint, 
 """
 import time
 
-import torch
-
 from .model_fns import EVAL, TRAIN
 from .utils import latest_checkpoint, load_checkpoint, save_checkpoint
 

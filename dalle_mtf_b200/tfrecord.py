@@ -144,8 +144,9 @@ def _encode_feature(kind, values) -> bytes:
 
 def encode_example(features: dict) -> bytes:
     """tf.train.Example(features=tf.train.Features(feature=features)).SerializeToString().
-    `features`: name -> ("bytes"|"int64"|"float", [values]).  Map entries are written in sorted key order, which is
-    what protobuf's deterministic serialisation (and, for these small maps, the C++ runtime TF uses) produces."""
+    `features`: name -> ("bytes"|"int64"|"float", [values]).  Map entries are written in sorted key order (for the
+    reference's {"caption", "image"} records that is byte-identical to protobuf's deterministic serialisation; in
+    general the order of map entries carries no meaning and every protobuf parser accepts any order)."""
     entries = b""
     for name in sorted(features):
         kind, values = features[name]
