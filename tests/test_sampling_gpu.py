@@ -65,11 +65,11 @@ def test_sample_rows_greedy_noise_and_onehot(ops):
     n, K = 20000, 8
     lg = torch.tensor([0.0, 1.0, 2.0, -1.0, 0.5, 3.0, -2.0, 1.5])
     big = lg.repeat(n, 1).to(DEV)
-    uu = torch.empty(n, K, device=DEV).uniform_(1e-9, 1.0)
+    uu = torch.empty(n, K, device=DEV).uniform_(1e-9, 1.0, generator=torch.Generator(device=DEV).manual_seed(3))
     out = torch.empty(n, dtype=torch.int32, device=DEV)
     ops.sample_rows(big, uu, out, 0, K, inv_temp=1.0)
     freq = torch.bincount(out.cpu().long(), minlength=K).float() / n
-    assert (freq - torch.softmax(lg, 0)).abs().max() < 0.015
+    assert (freq - torch.softmax(lg, 0)).abs().max() < 0.02       # sigma <= 0.0035 at n = 20000
     y = torch.full((rows, 16), 7.0, device=DEV)
     ids = torch.randint(40, 56, (rows,), generator=g).to(torch.int32)
     ops.onehot_rows(ids.to(DEV), y, offset=40)
