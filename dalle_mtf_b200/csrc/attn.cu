@@ -17,6 +17,8 @@
 //              and the output accumulator in registers.  2 CTAs/SM overlap one CTA's softmax with the other's MMAs.
 //   bwd dK/dV: CTA per (kv block, head, batch), loop over q blocks >= kv block; dV += P^T dO, dK += dS^T Q in TMEM.
 //   bwd dQ   : CTA per (q block, head, batch), loop over kv blocks <= q block; dQ += dS K in TMEM (no atomics).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -247,6 +249,243 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     if (half == 0) lse_out[((long long)b * H + h) * S + qi] = m_run * scale + logf(l_tot);
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward, software-pipelined variant (EXPERIMENTAL: selected with DB200_ATTN_V2=1, not yet validated on hardware —
+// the default path is attn_fwd_kernel above).  Differences to attn_fwd_kernel:
+//   * S is double-buffered in TMEM: S_{j+1} = Q K_{j+1}^T is issued as soon as every thread has read S_j, so the
+//     tensor pipe computes the next logits while the CTA exponentiates the current ones;
+//   * the output accumulates in TMEM across key blocks (P V with the accumulate flag) instead of being pulled into
+//     registers every block; rows are rescaled in TMEM (tcgen05.ld -> scale -> tcgen05.st) only when their running
+//     maximum moved by more than 2^8 since the scale they use ("lazy rescaling"), which is rare after the first blocks;
+//   * V is double-buffered in shared memory; K and P stay single-buffered (their consumers are a full softmax behind).
+// 64 keys per block for both head sizes: 2 x 64 (S) + DH (O) <= 256 TMEM columns and <= 96 KiB smem -> 2 CTAs / SM.
+// ------------------------------------------------------------------------------------------------------------------
+template <int DH>
+struct Fwd2Cfg {
+  static constexpr int BNK = 64;
+  static constexpr uint32_t Q_BYTES = 128 * DH * 2;
+  static constexpr uint32_t KV_BYTES = BNK * DH * 2;
+  static constexpr uint32_t P_BYTES = 128 * BNK * 2;
+  static constexpr size_t SMEM = 1024 + Q_BYTES + 3 * KV_BYTES + P_BYTES + 64 + 2 * 128 * 4 + 64;
+};
+
+template <int DH>
+__global__ void __launch_bounds__(256, 2)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                 bf16* __restrict__ out, float* __restrict__ lse_out, int S, int H, float scale) {
+  using C = Fwd2Cfg<DH>;
+  constexpr int BNK = C::BNK;
+  constexpr int HC = BNK / 2;  // 32 key columns of S per thread
+  constexpr int HD = DH / 2;   // output columns per thread
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK = sQ + C::Q_BYTES, sV = sK + C::KV_BYTES, sP = sV + 2 * C::KV_BYTES;
+  const uint32_t bars = sP + C::P_BYTES;
+  const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16 /*2*/, bar_s = bars + 32 /*2*/, bar_o = bars + 48;
+  const uint32_t tmem_slot = bars + 56;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* xch = reinterpret_cast<float*>(smem_raw + (bars + 64 - raw));  // [2][128] row-max exchange
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int rowi = tid & 127, half = tid >> 7;
+  const int qb = gridDim.x - 1 - blockIdx.x;  // heavy (late) query blocks first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qb * 128;
+  const int kv_len = min(S, q0 + 128);
+  const int n_kv = (kv_len + BNK - 1) / BNK;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_v + 8, 1);
+    mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem /* 2 x 64 columns */, tO = tmem + 128;
+  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, BNK, 0, 0);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);
+
+  auto issue_s = [&](int buf) {  // S = Q K^T into tS[buf]; K from sK
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk) {
+      const uint64_t ad = umma_smem_desc_sw128(sQ + (kk / 4) * (128 * 128) + (kk % 4) * 32, 0, 1024);
+      const uint64_t bd = umma_smem_desc_sw128(sK + (kk / 4) * (BNK * 128) + (kk % 4) * 32, 0, 1024);
+      umma_bf16_ss(tS + buf * BNK, ad, bd, idesc_s, kk > 0);
+    }
+    umma_commit(bar_s + 8 * buf);
+  };
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, C::Q_BYTES);
+    tma_load_tile<DH>(sQ, 128 * 128, &tmQ, bar_q, 0 * H + h, q0, b);
+    mbar_expect_tx(bar_k, C::KV_BYTES);
+    tma_load_tile<DH>(sK, BNK * 128, &tmKV, bar_k, 1 * H + h, 0, b);
+    mbar_expect_tx(bar_v, C::KV_BYTES);
+    tma_load_tile<DH>(sV, BNK * 128, &tmKV, bar_v, 2 * H + h, 0, b);
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_k, 0);
+    tc_fence_after();
+    issue_s(0);
+  }
+
+  const int qi = q0 + rowi;
+  const float c1 = scale * LOG2E;
+  float m_run = -INFINITY;   // true running row maximum (of the raw logits)
+  float m_used = -INFINITY;  // the maximum the accumulated P / O / l are scaled by
+  float l_run = 0.f;         // partial row sum over this thread's key columns, relative to m_used
+
+  for (int j = 0; j < n_kv; ++j) {
+    const int sb = j & 1;
+    // ---- (A) S_j is in tS[sb]
+    mbar_wait(bar_s + 8 * sb, (j >> 1) & 1);
+    tc_fence_after();
+    if (tid == 0 && j + 1 < n_kv) {  // sK is free: S_j has consumed K_j
+      mbar_expect_tx(bar_k, C::KV_BYTES);
+      tma_load_tile<DH>(sK, BNK * 128, &tmKV, bar_k, 1 * H + h, (j + 1) * BNK, b);
+    }
+    // ---- (B) this thread's 32 logits and their maximum
+    const int k0 = j * BNK + half * HC;
+    const bool need_mask = (j * BNK + BNK - 1) > q0;
+    float sv[HC];
+    float mx = -INFINITY;
+    {
+      uint32_t r[32];
+      tmem_ld_x32(tS + sb * BNK + lane_off + half * HC, r);
+      tmem_ld_wait();
+      if (need_mask && (k0 + 31) > qi) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float s = __uint_as_float(r[i]);
+          if ((k0 + i) > qi) s = -INFINITY;
+          sv[i] = s;
+          mx = fmaxf(mx, s);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          sv[i] = __uint_as_float(r[i]);
+          mx = fmaxf(mx, sv[i]);
+        }
+      }
+    }
+    xch[half * 128 + rowi] = mx;
+    tc_fence_before();
+    __syncthreads();  // (1) maxima exchanged; every thread has read tS[sb]
+    // ---- (C) next block's logits go to the other S buffer while this block is exponentiated
+    if (tid == 0 && j + 1 < n_kv) {
+      mbar_wait(bar_k, (j + 1) & 1);
+      tc_fence_after();
+      issue_s(sb ^ 1);
+    }
+    const float m_new = fmaxf(m_run, fmaxf(mx, xch[(half ^ 1) * 128 + rowi]));  // finite for in-range rows: key 0 visible
+    // ---- (D)+(E) the previous P V must be finished before P / O are touched
+    if (j > 0) {
+      mbar_wait(bar_o, (j - 1) & 1);
+      tc_fence_after();
+    }
+    if (tid == 0 && j + 1 < n_kv) {  // sV[sb ^ 1] held V_{j-1}: free now
+      mbar_expect_tx(bar_v + 8 * (sb ^ 1), C::KV_BYTES);
+      tma_load_tile<DH>(sV + (sb ^ 1) * C::KV_BYTES, BNK * 128, &tmKV, bar_v + 8 * (sb ^ 1), 2 * H + h, (j + 1) * BNK, b);
+    }
+    if (j == 0) {
+      m_used = m_new;
+    } else {
+      const bool need = (m_new - m_used) * c1 > 8.f;  // identical for the two threads of a row
+      if (__any_sync(0xffffffffu, need)) {             // tcgen05.ld / st are warp-collective
+        const float alpha = need ? ex2((m_used - m_new) * c1) : 1.f;
+#pragma unroll
+        for (int c = 0; c < HD / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_x32(tO + lane_off + half * HD + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st_x32(tO + lane_off + half * HD + c * 32, r);
+        }
+        tmem_st_wait();
+        if (need) {
+          l_run *= alpha;
+          m_used = m_new;
+        }
+      }
+    }
+    // ---- (F) P_j = 2^(c1 (s - m_used)) -> bf16 -> swizzled smem tile
+    const float mc = m_used * c1;
+    float lsum = 0.f;
+    {
+      uint32_t pk[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ex2(fmaf(sv[i], c1, -mc)), p1 = ex2(fmaf(sv[i + 1], c1, -mc));
+        lsum += p0 + p1;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+      }
+      const int col = half * HC;  // column inside the [128][64] P tile (one 64-wide sub-tile)
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        st_shared_v4(sP + sw128_offset(rowi, col + g * 8), pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+    }
+    l_run += lsum;
+    m_run = m_new;
+    fence_proxy_async_smem();
+    tc_fence_before();  // orders the tcgen05.st of a rescale before the MMA issued after the barrier
+    __syncthreads();    // (2) P complete, O rescaled
+    // ---- (G) O (+)= P_j V_j
+    if (tid == 0) {
+      mbar_wait(bar_v + 8 * sb, (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < BNK / 16; ++kk) {
+        const uint64_t ad = umma_smem_desc_sw128(sP + (kk % 4) * 32, 0, 1024);
+        const uint64_t bd = umma_smem_desc_sw128(sV + sb * C::KV_BYTES + kk * 2048, BNK * 128, 1024);
+        umma_bf16_ss(tO, ad, bd, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+      }
+      umma_commit(bar_o);
+    }
+  }
+
+  // ---- epilogue: O / l
+  mbar_wait(bar_o, (n_kv - 1) & 1);
+  tc_fence_after();
+  xch[half * 128 + rowi] = l_run;
+  __syncthreads();
+  const float l_tot = l_run + xch[(half ^ 1) * 128 + rowi];
+  const float inv = 1.f / l_tot;
+  bf16* op = out + (((long long)b * S + qi) * H + h) * DH + half * HD;
+#pragma unroll
+  for (int c = 0; c < HD / 32; ++c) {
+    uint32_t r[32];
+    tmem_ld_x32(tO + lane_off + half * HD + c * 32, r);
+    tmem_ld_wait();
+    if (qi < S) {
+#pragma unroll
+      for (int e = 0; e < 32; e += 8) {
+        uint4 q;
+        q.x = pack_bf16x2(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
+        q.y = pack_bf16x2(__uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv);
+        q.z = pack_bf16x2(__uint_as_float(r[e + 4]) * inv, __uint_as_float(r[e + 5]) * inv);
+        q.w = pack_bf16x2(__uint_as_float(r[e + 6]) * inv, __uint_as_float(r[e + 7]) * inv);
+        *reinterpret_cast<uint4*>(op + c * 32 + e) = q;
+      }
+    }
+  }
+  if (qi < S && half == 0) lse_out[((long long)b * H + h) * S + qi] = m_used * scale + logf(l_tot);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -658,6 +897,20 @@ static int fwd_launch(cudaStream_t stream, const void* qkv, void* out, float* ls
     attr = true;
   }
   dim3 grid((S + 127) / 128, H, B);
+  static const bool v2 = [] { const char* e = getenv("DB200_ATTN_V2"); return e && e[0] == '1'; }();
+  if (v2) {  // experimental pipelined variant (see attn_fwd2_kernel); 64-key blocks for both head sizes
+    using C2 = Fwd2Cfg<DH>;
+    CUtensorMap tmKV2;
+    rc = make_qkv_map(&tmKV2, qkv, B, S, H, DH, C2::BNK);
+    if (rc != DB200_OK) return rc;
+    static bool attr2 = false;
+    if (!attr2) {
+      DB200_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::SMEM));
+      attr2 = true;
+    }
+    attn_fwd2_kernel<DH><<<grid, 256, C2::SMEM, stream>>>(tmQ, tmKV2, (bf16*)out, lse, S, H, scale);
+    return check_launch("attn_fwd2_kernel");
+  }
   attn_fwd_kernel<DH><<<grid, 256, C::SMEM, stream>>>(tmQ, tmKV, (bf16*)out, lse, S, H, scale);
   return check_launch("attn_fwd_kernel");
 }

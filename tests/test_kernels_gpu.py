@@ -4,6 +4,8 @@ Tolerances (stated per test): integer / index outputs bit-exact; fp32 kernels 1e
 are compared with fp32 math on the SAME bf16-rounded inputs, so the only error is the output rounding
 (2^-8 = 3.9e-3 relative) plus accumulation order -> max-norm-relative 1e-2.
 """
+import os
+
 import pytest
 import torch
 
@@ -327,3 +329,17 @@ def test_attention_is_causal_at_full_size(ops):
     q2[:, 700:, 1:] = bf(torch.randn(B, S - 700, 2, H, dh, generator=g, device=DEV))
     ops.attn_fwd(q2, o2, lse, B, S, H, dh, 1.0)
     assert torch.equal(o1[:, :700], o2[:, :700]) and not torch.equal(o1[:, 700:], o2[:, 700:])
+
+
+@pytest.mark.skipif(os.environ.get("DB200_TEST_ATTN_V2") != "1",
+                    reason="experimental pipelined attention forward (DB200_ATTN_V2=1): opt-in until validated on hardware")
+def test_experimental_attention_v2_in_a_subprocess():
+    """Runs the attention parity tests of this file in a child process with DB200_ATTN_V2=1 (the switch is read once
+    per process).  Enable with DB200_TEST_ATTN_V2=1."""
+    import subprocess
+    import sys
+    env = dict(os.environ, DB200_ATTN_V2="1")
+    env.pop("DB200_TEST_ATTN_V2")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "attention and not experimental"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
