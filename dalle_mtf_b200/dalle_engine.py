@@ -105,6 +105,7 @@ class DalleEngine:
         self.aux_off = lay.size
         n = lay.size + 64
         dev = self.device
+        self._views = {}
         self.master = torch.zeros(n, dtype=F32, device=dev)
         self.grads = torch.zeros(n, dtype=F32, device=dev)
         self.adam_m = torch.zeros(n, dtype=F32, device=dev)
@@ -115,14 +116,23 @@ class DalleEngine:
         self._buf_key = None
 
     # ------------------------------------------------------------------------------------------ parameters
+    # The flat buffers are allocated once and only ever written in place, so the per-name views are cached: building a
+    # slice + view costs a few microseconds of host time, and the decode loop asks for ~70 of them per position.
+    def _view(self, which, flat, name):
+        key = (which, name)
+        v = self._views.get(key)
+        if v is None:
+            v = self._views[key] = self.layout.view(flat, name)
+        return v
+
     def P(self, name):  # fp32 master view
-        return self.layout.view(self.master, name)
+        return self._view(0, self.master, name)
 
     def W(self, name):  # bf16 compute copy
-        return self.layout.view(self.shadow, name)
+        return self._view(1, self.shadow, name)
 
     def G(self, name):  # fp32 gradient view
-        return self.layout.view(self.grads, name)
+        return self._view(2, self.grads, name)
 
     def n_params(self):
         """Trainable parameter count as the reference would print it (src/utils/utils.py:55-70)."""
