@@ -868,8 +868,396 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// backward, software-pipelined variants (EXPERIMENTAL: DB200_ATTN_V2 bit 1, not yet validated on hardware).
+// Same two-kernel scheme (no atomics), but each inner block is 64 wide, S / dP are double-buffered in TMEM so the next
+// block's two logit MMAs run while the CTA computes P / dS of the current one, and the operand tiles that are needed
+// both early (logit MMAs) and late (gradient MMAs) live in 3-deep shared-memory rings fed by TMA two blocks ahead.
+//   dQ    : CTA = 128 queries; loop over 64-key blocks.  S = Q K^T, dP = dO V^T (128 x 64), dS -> smem, dQ += dS K.
+//   dK/dV : CTA = 128 keys; loop over 64-query blocks, in the TRANSPOSED orientation S^T = K Q^T, dP^T = V dO^T
+//           (TMEM lanes = keys), so P^T and dS^T are written K-major ([keys][64 queries]) and dV += P^T dO,
+//           dK += dS^T Q need no MN-major A operand; lse / delta of the 64 queries are staged in shared memory.
+// ------------------------------------------------------------------------------------------------------------------
+template <int DH>
+struct Bwd2Cfg {
+  static constexpr uint32_t TILE = 128 * DH * 2;  // [128][DH]
+  static constexpr uint32_t HT = 64 * DH * 2;     // [64][DH]
+  static constexpr uint32_t ST = 128 * 64 * 2;    // [128][64] P^T / dS^T / dS tile
+  static constexpr size_t SMEM_DQ = 1024 + 2 * TILE + 5 * HT + ST + 256;
+  static constexpr size_t SMEM_DKDV = 1024 + 2 * TILE + 6 * HT + 2 * ST + 256 + 2 * 2 * 64 * 4;
+};
+constexpr uint32_t T64 = 64 * 128;  // bytes of one [64 rows][64] sub-tile
+
+template <int DH>
+__global__ void __launch_bounds__(256, 1)
+attn_bwd2_dq_kernel(const __grid_constant__ CUtensorMap tmQ128, const __grid_constant__ CUtensorMap tmKV64,
+                    const __grid_constant__ CUtensorMap tmDO128, const float* __restrict__ lse,
+                    const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H, float scale) {
+  using C = Bwd2Cfg<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sQ = base, sdO = sQ + C::TILE, sK = sdO + C::TILE /*3*/, sV = sK + 3 * C::HT /*2*/,
+                 sdS = sV + 2 * C::HT;
+  const uint32_t bars = sdS + C::ST;
+  const uint32_t bar_q = bars, bar_k = bars + 8 /*3*/, bar_v = bars + 32 /*2*/, bar_a = bars + 48 /*2*/,
+                 bar_b = bars + 64;
+  const uint32_t tmem_slot = bars + 72;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int rowi = tid & 127, half = tid >> 7;
+  const int ib = gridDim.x - 1 - blockIdx.x;  // heavy query blocks first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = ib * 128;
+  const int n_kv = (min(S, q0 + 128) + 63) / 64;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQ128);
+    tma_prefetch_desc(&tmKV64);
+    tma_prefetch_desc(&tmDO128);
+    mbar_init(bar_q, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(bar_k + 8 * i, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_v + 8 * i, 1); mbar_init(bar_a + 8 * i, 1); }
+    mbar_init(bar_b, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem /*2 x 64*/, tdP = tmem + 128 /*2 x 64*/, tdQ = tmem + 256;
+  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);
+  constexpr uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);
+  auto load_k = [&](int j) {
+    const uint32_t bk = bar_k + 8 * (j % 3);
+    mbar_expect_tx(bk, C::HT);
+    tma_load_tile<DH>(sK + (j % 3) * C::HT, T64, &tmKV64, bk, 1 * H + h, j * 64, b);
+  };
+  auto load_v = [&](int j) {
+    const uint32_t bv = bar_v + 8 * (j & 1);
+    mbar_expect_tx(bv, C::HT);
+    tma_load_tile<DH>(sV + (j & 1) * C::HT, T64, &tmKV64, bv, 2 * H + h, j * 64, b);
+  };
+  auto issue_logits = [&](int j) {  // S_j, dP_j into TMEM buffers j & 1
+    const uint32_t kb = sK + (j % 3) * C::HT, vb = sV + (j & 1) * C::HT;
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk)
+      umma_bf16_ss(tS + (j & 1) * 64, umma_smem_desc_sw128(sQ + (kk / 4) * T128 + (kk % 4) * 32, 0, 1024),
+                   umma_smem_desc_sw128(kb + (kk / 4) * T64 + (kk % 4) * 32, 0, 1024), idesc_s, kk > 0);
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk)
+      umma_bf16_ss(tdP + (j & 1) * 64, umma_smem_desc_sw128(sdO + (kk / 4) * T128 + (kk % 4) * 32, 0, 1024),
+                   umma_smem_desc_sw128(vb + (kk / 4) * T64 + (kk % 4) * 32, 0, 1024), idesc_s, kk > 0);
+    umma_commit(bar_a + 8 * (j & 1));
+  };
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_q, 2 * C::TILE);
+    tma_load_tile<DH>(sQ, T128, &tmQ128, bar_q, 0 * H + h, q0, b);
+    tma_load_tile<DH>(sdO, T128, &tmDO128, bar_q, h, q0, b);
+    load_k(0); load_v(0);
+    if (n_kv > 1) { load_k(1); load_v(1); }
+    mbar_wait(bar_q, 0);
+    mbar_wait(bar_k, 0);
+    mbar_wait(bar_v, 0);
+    tc_fence_after();
+    issue_logits(0);
+  }
+  const float c1 = scale * LOG2E;
+  const int qi = q0 + rowi;
+  const bool row_ok = qi < S;
+  float lse_l2 = 0.f, dl = 0.f;
+  if (row_ok) {
+    lse_l2 = lse[((long long)b * H + h) * S + qi] * LOG2E;
+    dl = delta[((long long)b * H + h) * S + qi];
+  }
+
+  for (int j = 0; j < n_kv; ++j) {
+    const int sb = j & 1;
+    mbar_wait(bar_a + 8 * sb, (j >> 1) & 1);  // (A) S_j, dP_j ready; V buffer sb is free
+    tc_fence_after();
+    if (tid == 0 && j + 2 < n_kv) load_v(j + 2);
+    // (B) this thread's 32 columns -> dS (bf16 pairs in registers)
+    uint32_t dk[16];
+    {
+      const int col0 = half * 32, k0 = j * 64 + col0;
+      uint32_t rs[32], rd[32];
+      tmem_ld_x32(tS + sb * 64 + lane_off + col0, rs);
+      tmem_ld_x32(tdP + sb * 64 + lane_off + col0, rd);
+      tmem_ld_wait();
+      const bool diag = (j * 64 + 63) > q0;  // block reaches past the first query of the tile: mask per element
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = ex2(fmaf(__uint_as_float(rs[i]), c1, -lse_l2));
+        float p1 = ex2(fmaf(__uint_as_float(rs[i + 1]), c1, -lse_l2));
+        if (!row_ok || (diag && (k0 + i) > qi)) p0 = 0.f;
+        if (!row_ok || (diag && (k0 + i + 1) > qi)) p1 = 0.f;
+        dk[i >> 1] = pack_bf16x2((p0 * scale) * (__uint_as_float(rd[i]) - dl),
+                                 (p1 * scale) * (__uint_as_float(rd[i + 1]) - dl));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // (1) every thread has read tS / tdP [sb]
+    if (tid == 0 && j + 1 < n_kv) {  // (C) next block's logits under this block's epilogue math
+      mbar_wait(bar_k + 8 * ((j + 1) % 3), ((j + 1) / 3) & 1);
+      mbar_wait(bar_v + 8 * (sb ^ 1), ((j + 1) >> 1) & 1);
+      tc_fence_after();
+      issue_logits(j + 1);
+    }
+    if (j > 0) {  // (E) dQ MMAs of block j-1 done: sdS and K ring slot (j-1) % 3 are free
+      mbar_wait(bar_b, (j - 1) & 1);
+      tc_fence_after();
+    }
+    if (tid == 0 && j + 2 < n_kv) load_k(j + 2);
+    {  // (F) dS -> swizzled [128][64] tile
+      const int col = half * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        st_shared_v4(sdS + sw128_offset(rowi, col + g * 8), dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();  // (2)
+    if (tid == 0) {   // (G) dQ += dS K_j
+      tc_fence_after();
+      const uint32_t kb = sK + (j % 3) * C::HT;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_bf16_ss(tdQ, umma_smem_desc_sw128(sdS + kk * 32, 0, 1024), umma_smem_desc_sw128(kb + kk * 2048, T64, 1024),
+                     idesc_q, (j > 0 || kk > 0));
+      umma_commit(bar_b);
+    }
+  }
+  mbar_wait(bar_b, (n_kv - 1) & 1);
+  tc_fence_after();
+  bf16* dst = dqkv + ((((long long)b * S + qi) * 3 + 0) * H + h) * DH + half * (DH / 2);
+#pragma unroll 1
+  for (int c = 0; c < DH / 64; ++c) {
+    uint32_t r[32];
+    tmem_ld_x32(tdQ + lane_off + half * (DH / 2) + c * 32, r);
+    tmem_ld_wait();
+    if (row_ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 q;
+        q.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
+        q.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
+        q.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
+        q.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+        *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = q;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(256, 1)
+attn_bwd2_dkdv_kernel(const __grid_constant__ CUtensorMap tmKV128, const __grid_constant__ CUtensorMap tmQ64,
+                      const __grid_constant__ CUtensorMap tmDO64, const float* __restrict__ lse,
+                      const float* __restrict__ delta, bf16* __restrict__ dqkv, int S, int H, float scale) {
+  using C = Bwd2Cfg<DH>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sK = base, sV = sK + C::TILE, sQ = sV + C::TILE /*3*/, sdO = sQ + 3 * C::HT /*3*/,
+                 sPT = sdO + 3 * C::HT, sdST = sPT + C::ST;
+  const uint32_t bars = sdST + C::ST;
+  const uint32_t bar_kv = bars, bar_qd = bars + 8 /*3*/, bar_a = bars + 32 /*2*/, bar_b = bars + 48;
+  const uint32_t tmem_slot = bars + 56;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* stat = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));  // [2 buffers][2: lse*log2e, delta][64]
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int rowi = tid & 127, half = tid >> 7;
+  const int jb = blockIdx.x;  // kv block (block 0 has the most work and is scheduled first)
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int k0 = jb * 128;
+  const int i0 = 2 * jb;                 // first 64-query block that can see these keys
+  const int n_it = (S + 63) / 64 - i0;   // >= 1 because k0 < S
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmKV128);
+    tma_prefetch_desc(&tmQ64);
+    tma_prefetch_desc(&tmDO64);
+    mbar_init(bar_kv, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(bar_qd + 8 * i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_a + 8 * i, 1);
+    mbar_init(bar_b, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tST = tmem /*2 x 64*/, tdPT = tmem + 128 /*2 x 64*/, tdV = tmem + 256, tdK = tmem + 256 + DH;
+  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);   // S^T = K Q^T, dP^T = V dO^T
+  constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dV = P^T dO, dK = dS^T Q : A K-major, B MN-major
+  auto load_qd = [&](int it) {  // Q and dO rows of 64-query block i0 + it into ring slot it % 3
+    const uint32_t bq = bar_qd + 8 * (it % 3);
+    mbar_expect_tx(bq, 2 * C::HT);
+    tma_load_tile<DH>(sQ + (it % 3) * C::HT, T64, &tmQ64, bq, 0 * H + h, (i0 + it) * 64, b);
+    tma_load_tile<DH>(sdO + (it % 3) * C::HT, T64, &tmDO64, bq, h, (i0 + it) * 64, b);
+  };
+  auto issue_logits = [&](int it) {
+    const uint32_t qb = sQ + (it % 3) * C::HT, ob = sdO + (it % 3) * C::HT;
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk)
+      umma_bf16_ss(tST + (it & 1) * 64, umma_smem_desc_sw128(sK + (kk / 4) * T128 + (kk % 4) * 32, 0, 1024),
+                   umma_smem_desc_sw128(qb + (kk / 4) * T64 + (kk % 4) * 32, 0, 1024), idesc_s, kk > 0);
+#pragma unroll
+    for (int kk = 0; kk < DH / 16; ++kk)
+      umma_bf16_ss(tdPT + (it & 1) * 64, umma_smem_desc_sw128(sV + (kk / 4) * T128 + (kk % 4) * 32, 0, 1024),
+                   umma_smem_desc_sw128(ob + (kk / 4) * T64 + (kk % 4) * 32, 0, 1024), idesc_s, kk > 0);
+    umma_commit(bar_a + 8 * (it & 1));
+  };
+  auto stage_stats = [&](int it) {  // lse * log2(e) and delta of the block's 64 queries (+inf / 0 beyond S: p = 0)
+    if (tid < 64) {
+      const int q = (i0 + it) * 64 + tid;
+      float l2 = INFINITY, d = 0.f;
+      if (q < S) {
+        l2 = lse[((long long)b * H + h) * S + q] * LOG2E;
+        d = delta[((long long)b * H + h) * S + q];
+      }
+      stat[(it & 1) * 128 + tid] = l2;
+      stat[(it & 1) * 128 + 64 + tid] = d;
+    }
+  };
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_kv, 2 * C::TILE);
+    tma_load_tile<DH>(sK, T128, &tmKV128, bar_kv, 1 * H + h, k0, b);
+    tma_load_tile<DH>(sV, T128, &tmKV128, bar_kv, 2 * H + h, k0, b);
+    load_qd(0);
+    if (n_it > 1) load_qd(1);
+    mbar_wait(bar_kv, 0);
+    mbar_wait(bar_qd, 0);
+    tc_fence_after();
+    issue_logits(0);
+  }
+  stage_stats(0);
+  __syncthreads();
+  const float c1 = scale * LOG2E;
+  const int ki = k0 + rowi;
+
+  for (int it = 0; it < n_it; ++it) {
+    const int sb = it & 1;
+    const int qbase = (i0 + it) * 64;
+    mbar_wait(bar_a + 8 * sb, (it >> 1) & 1);  // (A)
+    tc_fence_after();
+    // (B) P^T, dS^T for this key row and 32 of the block's 64 queries
+    uint32_t pk[16], dk[16];
+    {
+      const int col0 = half * 32;
+      uint32_t rs[32], rd[32];
+      tmem_ld_x32(tST + sb * 64 + lane_off + col0, rs);
+      tmem_ld_x32(tdPT + sb * 64 + lane_off + col0, rd);
+      tmem_ld_wait();
+      const float* l2 = stat + sb * 128 + col0;
+      const float* dd = l2 + 64;
+      const bool diag = (k0 + 127) > qbase;  // some (key, query) pairs of this block are in the future
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = ex2(fmaf(__uint_as_float(rs[i]), c1, -l2[i]));
+        float p1 = ex2(fmaf(__uint_as_float(rs[i + 1]), c1, -l2[i + 1]));
+        if (diag && ki > (qbase + col0 + i)) p0 = 0.f;
+        if (diag && ki > (qbase + col0 + i + 1)) p1 = 0.f;
+        pk[i >> 1] = pack_bf16x2(p0, p1);
+        dk[i >> 1] = pack_bf16x2((p0 * scale) * (__uint_as_float(rd[i]) - dd[i]),
+                                 (p1 * scale) * (__uint_as_float(rd[i + 1]) - dd[i + 1]));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // (1) TMEM logits and this block's stats consumed
+    if (tid == 0 && it + 1 < n_it) {  // (C)
+      mbar_wait(bar_qd + 8 * ((it + 1) % 3), ((it + 1) / 3) & 1);
+      tc_fence_after();
+      issue_logits(it + 1);
+    }
+    if (it + 1 < n_it) stage_stats(it + 1);  // other stats buffer: last read in iteration it - 1
+    if (it > 0) {  // (E) gradient MMAs of block it-1 done: P^T / dS^T tiles and ring slot (it-1) % 3 are free
+      mbar_wait(bar_b, (it - 1) & 1);
+      tc_fence_after();
+    }
+    if (tid == 0 && it + 2 < n_it) load_qd(it + 2);
+    {  // (F)
+      const int col = half * 32;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const uint32_t off = sw128_offset(rowi, col + g * 8);
+        st_shared_v4(sPT + off, pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
+        st_shared_v4(sdST + off, dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();  // (2) tiles and next stats visible
+    if (tid == 0) {   // (G) dV += P^T dO_i ; dK += dS^T Q_i   (K dimension = the 64 queries)
+      tc_fence_after();
+      const uint32_t qb = sQ + (it % 3) * C::HT, ob = sdO + (it % 3) * C::HT;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_bf16_ss(tdV, umma_smem_desc_sw128(sPT + kk * 32, 0, 1024), umma_smem_desc_sw128(ob + kk * 2048, T64, 1024),
+                     idesc_g, (it > 0 || kk > 0));
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        umma_bf16_ss(tdK, umma_smem_desc_sw128(sdST + kk * 32, 0, 1024), umma_smem_desc_sw128(qb + kk * 2048, T64, 1024),
+                     idesc_g, (it > 0 || kk > 0));
+      umma_commit(bar_b);
+    }
+  }
+  mbar_wait(bar_b, (n_it - 1) & 1);
+  tc_fence_after();
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    const uint32_t tsrc = which == 0 ? tdK : tdV;
+    bf16* dst = dqkv + ((((long long)b * S + ki) * 3 + (which == 0 ? 1 : 2)) * H + h) * DH + half * (DH / 2);
+#pragma unroll 1
+    for (int c = 0; c < DH / 64; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(tsrc + lane_off + half * (DH / 2) + c * 32, r);
+      tmem_ld_wait();
+      if (ki < S) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 q;
+          q.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
+          q.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
+          q.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
+          q.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = q;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
+// DB200_ATTN_V2: bit 0 = pipelined forward, bit 1 = pipelined backward (experimental kernels; default 0)
+static int attn_v2_bits() {
+  static const int bits = [] { const char* e = getenv("DB200_ATTN_V2"); return e ? atoi(e) : 0; }();
+  return bits;
+}
+
 static int make_qkv_map(CUtensorMap* tm, const void* qkv, int B, int S, int H, int dh, uint32_t box_rows) {
   uint64_t dims[4] = {(uint64_t)dh, (uint64_t)3 * H, (uint64_t)S, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)dh * 2, (uint64_t)3 * H * dh * 2, (uint64_t)S * 3 * H * dh * 2};
@@ -897,8 +1285,7 @@ static int fwd_launch(cudaStream_t stream, const void* qkv, void* out, float* ls
     attr = true;
   }
   dim3 grid((S + 127) / 128, H, B);
-  static const bool v2 = [] { const char* e = getenv("DB200_ATTN_V2"); return e && e[0] == '1'; }();
-  if (v2) {  // experimental pipelined variant (see attn_fwd2_kernel); 64-key blocks for both head sizes
+  if (attn_v2_bits() & 1) {  // experimental pipelined variant (see attn_fwd2_kernel); 64-key blocks for both head sizes
     using C2 = Fwd2Cfg<DH>;
     CUtensorMap tmKV2;
     rc = make_qkv_map(&tmKV2, qkv, B, S, H, DH, C2::BNK);
@@ -933,6 +1320,29 @@ static int bwd_launch(cudaStream_t stream, const void* qkv, const void* dout, co
     attr = true;
   }
   dim3 grid((S + 127) / 128, H, B);
+  if (attn_v2_bits() & 2) {  // experimental pipelined backward kernels
+    using C2 = Bwd2Cfg<DH>;
+    CUtensorMap tmQKV64, tmDO64;
+    rc = make_qkv_map(&tmQKV64, qkv, B, S, H, DH, 64);
+    if (rc != DB200_OK) return rc;
+    rc = make_o_map(&tmDO64, dout, B, S, H, DH, 64);
+    if (rc != DB200_OK) return rc;
+    static bool attr2 = false;
+    if (!attr2) {
+      DB200_CUDA(cudaFuncSetAttribute(attn_bwd2_dkdv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)C2::SMEM_DKDV));
+      DB200_CUDA(cudaFuncSetAttribute(attn_bwd2_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)C2::SMEM_DQ));
+      attr2 = true;
+    }
+    attn_bwd2_dkdv_kernel<DH><<<grid, 256, C2::SMEM_DKDV, stream>>>(tmQKV, tmQKV64, tmDO64, lse, delta, (bf16*)dqkv, S, H,
+                                                                  scale);
+    rc = check_launch("attn_bwd2_dkdv_kernel");
+    if (rc != DB200_OK) return rc;
+    attn_bwd2_dq_kernel<DH><<<grid, 256, C2::SMEM_DQ, stream>>>(tmQKV, tmQKV64, tmDO, lse, delta, (bf16*)dqkv, S, H,
+                                                              scale);
+    return check_launch("attn_bwd2_dq_kernel");
+  }
   attn_bwd_dkdv_kernel<DH><<<grid, 256, C::SMEM_DKDV, stream>>>(tmQKV, tmDO, lse, delta, (bf16*)dqkv, S, H, scale);
   rc = check_launch("attn_bwd_dkdv_kernel");
   if (rc != DB200_OK) return rc;

@@ -332,14 +332,15 @@ def test_attention_is_causal_at_full_size(ops):
 
 
 @pytest.mark.skipif(os.environ.get("DB200_TEST_ATTN_V2") != "1",
-                    reason="experimental pipelined attention forward (DB200_ATTN_V2=1): opt-in until validated on hardware")
+                    reason="experimental pipelined attention kernels (DB200_ATTN_V2 bits: 1 fwd, 2 bwd): opt-in until validated")
 def test_experimental_attention_v2_in_a_subprocess():
-    """Runs the attention parity tests of this file in a child process with DB200_ATTN_V2=1 (the switch is read once
-    per process).  Enable with DB200_TEST_ATTN_V2=1."""
+    """Runs the attention parity tests of this file in child processes with DB200_ATTN_V2 = 1 (pipelined forward),
+    2 (pipelined backward) and 3 (both); the switch is read once per process.  Enable with DB200_TEST_ATTN_V2=1."""
     import subprocess
     import sys
-    env = dict(os.environ, DB200_ATTN_V2="1")
-    env.pop("DB200_TEST_ATTN_V2")
-    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k", "attention and not experimental"],
-                       env=env, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    for bits in ("1", "2", "3"):
+        env = dict(os.environ, DB200_ATTN_V2=bits)
+        env.pop("DB200_TEST_ATTN_V2")
+        r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-k",
+                            "attention and not experimental"], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, f"DB200_ATTN_V2={bits}\n" + r.stdout[-3000:] + r.stderr[-2000:]
