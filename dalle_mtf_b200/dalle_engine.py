@@ -152,11 +152,17 @@ class DalleEngine:
 
     def load_params(self, named):
         """Load a dict keyed by the reference's variable names; CPU or CUDA fp32 tensors."""
+        self.load_flat(self.master, named)
+        self.refresh_shadow()
+
+    def load_flat(self, flat, named):
+        """Fill one of the flat fp32 buffers (master | adam_m | adam_v) from a dict of reference-named tensors."""
         dev = self.device
-        self.master.zero_()
+        flat.zero_()
+        view = lambda n: self.layout.view(flat, n)
 
         def put(name, t):
-            dst = self.P(name)
+            dst = view(name)
             t = t.to(device=dev, dtype=F32)
             if tuple(t.shape) != tuple(dst.shape):
                 raise L.DB200Error(f"load_params: {name}: expected {tuple(dst.shape)}, got {tuple(t.shape)}")
@@ -172,9 +178,8 @@ class DalleEngine:
             pre = f"layer_{i}/attn/"
             put(p + "wqkv", torch.cat([named[pre + "q"], named[pre + "k"], named[pre + "v"]], dim=1))
         put("lnf_g", named["to_logits/layer_norm/g"]); put("lnf_b", named["to_logits/layer_norm/b"])
-        self.P("wout")[:, :self.V].copy_(named["to_logits/linear_out/kernel"].to(device=dev, dtype=F32))
-        self.P("bout")[:self.V].copy_(named["to_logits/linear_out/bias"].to(device=dev, dtype=F32))
-        self.refresh_shadow()
+        view("wout")[:, :self.V].copy_(named["to_logits/linear_out/kernel"].to(device=dev, dtype=F32))
+        view("bout")[:self.V].copy_(named["to_logits/linear_out/bias"].to(device=dev, dtype=F32))
 
     def export_params(self, source=None):
         """Inverse of load_params: dict of reference-named fp32 CPU tensors (source: master | grads | adam_m | adam_v)."""
@@ -369,8 +374,26 @@ class DalleEngine:
     def zero_grads(self):
         self.grads.zero_()
 
+    def _decay_segments(self):
+        """Contiguous [start, end, decays) runs of the flat buffer: mtf's AdamWeightDecayOptimizer is built with
+        exclude_from_weight_decay=["norm", "bias"] (src/optimizers.py:84-88), i.e. every variable whose NAME contains
+        "norm" or "bias" (LayerNorm g/b, all biases incl. compute_output_bias/o_b) is left undecayed."""
+        if getattr(self, "_segs", None) is None:
+            decays = lambda n: n in ("wte", "wpe", "wout") or n.split(".")[-1] in ("wqkv", "wo", "w1", "w2")
+            segs = []
+            for name in self.layout.order:
+                s, e = self.layout.span(name, name)
+                d = decays(name)
+                if segs and segs[-1][2] == d and segs[-1][1] == s:
+                    segs[-1][1] = e
+                else:
+                    segs.append([s, e, d])
+            self._segs = [tuple(x) for x in segs]
+        return self._segs
+
     def optimizer_step(self, lr, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0, clip=1.0):
-        """clip_by_global_norm + mtf AdamWeightDecayOptimizer (src/optimizers.py:11-16, 82-103); no host sync."""
+        """clip_by_global_norm + mtf AdamWeightDecayOptimizer (src/optimizers.py:11-16, 82-103); no host sync.
+        clip=None disables clipping (explicit `"gradient_clipping": null`, optimizers.py:101)."""
         n = self.n_params_padded
         if clip and clip > 0:
             self.gnorm_sq.zero_()
@@ -378,8 +401,10 @@ class DalleEngine:
             gn = self.gnorm_sq
         else:
             gn, clip = None, 0.0
-        if weight_decay:
-            raise L.DB200Error("weight_decay != 0 needs per-tensor exclusion of norm/bias (src/optimizers.py:84); "
-                               "not wired in the flat Adam yet")
-        ops.adam_step(self.master[:n], self.adam_m[:n], self.adam_v[:n], self.grads[:n], self.shadow[:n], lr, beta1,
-                      beta2, eps, 0.0, gn, clip, 1.0, False, 0)
+        if not weight_decay:
+            ops.adam_step(self.master[:n], self.adam_m[:n], self.adam_v[:n], self.grads[:n], self.shadow[:n], lr,
+                          beta1, beta2, eps, 0.0, gn, clip, 1.0, False, 0)
+            return
+        for s, e, d in self._decay_segments():     # `update += weight_decay * param` only on the kernels / embeddings
+            ops.adam_step(self.master[s:e], self.adam_m[s:e], self.adam_v[s:e], self.grads[s:e], self.shadow[s:e], lr,
+                          beta1, beta2, eps, weight_decay if d else 0.0, gn, clip, 1.0, False, 0)

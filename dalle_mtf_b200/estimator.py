@@ -5,7 +5,7 @@ train_vae_tf.py:51-93): build once via model_fn, restore the latest checkpoint, 
 import time
 
 from .model_fns import EVAL, TRAIN
-from .utils import latest_checkpoint, load_checkpoint, save_checkpoint
+from .utils import (latest_checkpoint, load_checkpoint, load_global_step_from_checkpoint_dir, save_checkpoint)
 
 
 class Estimator:
@@ -14,6 +14,31 @@ class Estimator:
         self.params = params
         self.logger = logger
         self._specs = {}
+        self._iters = {}      # mode -> (input_fn identity, live iterator)
+
+    def _batches(self, mode, input_fn):
+        """ONE persistent input iterator per mode.  train_dalle.py / train_vae_tf.py call train() once per
+        steps_per_checkpoint chunk; re-creating a (seeded) pipeline on every call would replay the same file order and
+        batches from the start each time and leave the previous producer thread alive (the reference's tf.data
+        pipelines are unseeded and simply continue).  A different input_fn replaces, and closes, the old stream."""
+        key = getattr(input_fn, "func", input_fn), repr(getattr(input_fn, "keywords", None))
+        cur = self._iters.get(mode)
+        if cur is None or cur[0] != key:
+            if cur is not None and hasattr(cur[1], "close"):
+                cur[1].close()
+            # a resumed run must not replay the first epoch's order either: the pipelines add this offset to their
+            # seeds (every rank reads the same checkpoint directory, so the offset is identical on all ranks)
+            if self.params.get("model_path"):
+                self.params["_data_seed_offset"] = load_global_step_from_checkpoint_dir(self.params["model_path"])
+            cur = (key, iter(input_fn(self.params)))
+            self._iters[mode] = cur
+        return cur[1]
+
+    def close(self):
+        for _, it in self._iters.values():
+            if hasattr(it, "close"):
+                it.close()
+        self._iters = {}
 
     def _log(self, msg):
         if self.logger is not None:
@@ -40,7 +65,7 @@ class Estimator:
         spec.dp.barrier()
 
     def train(self, input_fn, max_steps):
-        it = iter(input_fn(self.params))
+        it = self._batches(TRAIN, input_fn)
         features, labels = next(it)
         spec = self._spec(TRAIN, features, labels)
         log_every = self.params.get("iterations") or 100
@@ -64,7 +89,7 @@ class Estimator:
         return spec
 
     def evaluate(self, input_fn, steps):
-        it = iter(input_fn(self.params))
+        it = self._batches(EVAL, input_fn)
         features, labels = next(it)
         spec = self._spec(EVAL, features, labels)
         train_spec = self._specs.get(TRAIN)

@@ -48,6 +48,13 @@ def synthetic_captions(batch, text_seq_len, padding_id, generator, vocab=50257, 
     return ids
 
 
+def _seed(params, eval):
+    """1234 + rank for training data, a disjoint stream for eval; `_data_seed_offset` (set by the
+    Estimator to the step a run resumes from) keeps a resumed run from replaying the batches it already saw."""
+    rank = int(os.environ.get("RANK", "0"))
+    return 1234 + rank + (10_000 if eval else 0) + 7919 * int(params.get("_data_seed_offset") or 0)
+
+
 def _real_data(params, eval):
     """True when the configured path matches local files; warns (once per path) when a non-synthetic path matches none."""
     path = params["dataset"].get("eval_path" if eval else "train_path")
@@ -70,10 +77,9 @@ def vae_input_fn(params, eval=False):
     """src/input_fns.py:69-104."""
     if _real_data(params, eval):
         from .data_pipeline import real_input_fn
-        yield from real_input_fn(params, eval, labeled=False)
+        yield from real_input_fn(params, eval, labeled=False, seed=1234 + 7919 * int(params.get("_data_seed_offset") or 0))
         return
-    rank = int(os.environ.get("RANK", "0"))
-    g = torch.Generator().manual_seed(1234 + rank + (10_000 if eval else 0))
+    g = torch.Generator().manual_seed(_seed(params, eval))
     B = _local_batch(params, eval)
     size = params["dataset"]["image_size"]
     ch = params.get("n_channels") or 3
@@ -86,10 +92,9 @@ def dalle_input_fn(params, eval=False):
     """src/input_fns.py:106-120."""
     if _real_data(params, eval):
         from .data_pipeline import real_input_fn
-        yield from real_input_fn(params, eval, labeled=True)
+        yield from real_input_fn(params, eval, labeled=True, seed=1234 + 7919 * int(params.get("_data_seed_offset") or 0))
         return
-    rank = int(os.environ.get("RANK", "0"))
-    g = torch.Generator().manual_seed(1234 + rank + (10_000 if eval else 0))
+    g = torch.Generator().manual_seed(_seed(params, eval))
     B = _local_batch(params, eval)
     size = params["dataset"]["image_size"]
     ch = params.get("n_channels") or 3

@@ -178,13 +178,9 @@ def dalle_model_fn(features, labels, mode, params):
 
     def load_fn(st):
         names = [k for k in st if not k.endswith("/adam_m") and not k.endswith("/adam_v") and k != "global_step"]
-        model.load_params({k: st[k] for k in names})
+        model.load_params({k: st[k] for k in names})                                # master + bf16 shadow
         for suffix, flat in (("/adam_m", model.adam_m), ("/adam_v", model.adam_v)):
-            saved = model.master.clone()
-            model.load_params({k: st[k + suffix] for k in names})
-            flat.copy_(model.master)
-            model.master.copy_(saved)
-        model.refresh_shadow()
+            model.load_flat(flat, {k: st[k + suffix] for k in names})
         spec.global_step = int(st.get("global_step", 0))
 
     spec.train_op = train_op if mode == TRAIN else None
@@ -278,13 +274,12 @@ def vae_model_fn(features, labels, mode, params):
         return st
 
     def load_fn(st):
+        # master weights (+ the bf16 shadow / split codebook derived from them), then the Adam slots straight into
+        # their flat buffers: the compute copies must never be refreshed from anything but the weights
         model.load_params({k[len("vae/"):]: v for k, v in st.items()
                            if k.startswith("vae/") and not k.endswith("/Adam") and not k.endswith("/Adam_1")})
-        saved = model.master.clone()
         for suffix, flat in (("/Adam", model.adam_m), ("/Adam_1", model.adam_v)):
-            model.load_params({k[len("vae/"):-len(suffix)]: v for k, v in st.items() if k.endswith(suffix)})
-            flat.copy_(model.master)
-        model.master.copy_(saved)
+            model.load_flat(flat, {k[len("vae/"):-len(suffix)]: v for k, v in st.items() if k.endswith(suffix)})
         spec.global_step = int(st.get("global_step", 0))
 
     spec.train_op = train_op if mode == TRAIN else None

@@ -15,13 +15,16 @@ class OptimizerConfig:
         self.lr_decay = params.get("lr_decay") or "cosine"                    # optimizers.py:25
         ws = params.get("warmup_steps")
         self.warmup_steps = 3000 if ws is None else ws                        # optimizers.py:26
-        gc = params.get("gradient_clipping")
-        self.gradient_clipping = 1.0 if gc is None else gc                    # optimizers.py:27
+        # optimizers.py:27,101: a MISSING key means 1.0, an explicit `null` disables clipping (`params.get(k, 1.0)` on the
+        # reference's defaultdict returns the default only when the key is absent)
+        self.gradient_clipping = params["gradient_clipping"] if "gradient_clipping" in params else 1.0
         self.optimizer = (params.get("optimizer") or "adam").lower()          # optimizers.py:28
         self.weight_decay = params.get("weight_decay") or 0.0                 # optimizers.py:84
         self.beta_1 = params.get("beta_1") or 0.9
         self.beta_2 = params.get("beta_2") or 0.999
         self.epsilon = params.get("epsilon") or 1e-6
+        if not (isinstance(self.weight_decay, (int, float)) and self.weight_decay >= 0):
+            raise ValueError(f"weight_decay must be a non-negative number, got {self.weight_decay!r}")
         if self.optimizer != "adam":
             # the Adafactor branch (optimizers.py:90-97) is selected by no reference config
             raise ValueError(f"{self.optimizer} not recognized (only 'adam' is implemented on B200)")
@@ -42,15 +45,26 @@ class OptimizerConfig:
         return lr
 
 
-def get_optimizer(engine, params):
-    """Mirror of get_optimizer(mesh, loss, params, variable_dtype) (src/optimizers.py:19): returns
-    (learning_rate_fn, update_op) where update_op(step) applies clip + Adam to `engine` on the device."""
-    cfg = OptimizerConfig(params)
+def get_optimizer(mesh, loss, params, variable_dtype=None, inp_var_grads=None):
+    """Same signature as the reference's get_optimizer(mesh, loss, params, variable_dtype, inp_var_grads=None)
+    (src/optimizers.py:19) and the same 3-tuple back: (learning_rate, update_ops, var_grads).
 
-    def update_op(step):
+    What the arguments are here: `mesh` is the engine that owns the variables (the mtf mesh's role: it holds the flat
+    fp32 master / gradient / Adam buffers); `loss` is the device scalar the engine's forward produced — gradients
+    already sit in the engine's flat buffer after backward(), so it is not differentiated again (mtf.gradients,
+    optimizers.py:34); `variable_dtype` is accepted for signature parity (slices are always fp32, ops.py:76-82);
+    `inp_var_grads`, when given, is a dict of reference-named gradient tensors that replaces the engine's own.
+    learning_rate is a function of the integer global step (host scalar math, no device sync); update_ops(step)
+    applies clip-by-global-norm + Adam on the device and returns the learning rate it used."""
+    engine = mesh
+    cfg = OptimizerConfig(params)
+    if inp_var_grads is not None:
+        engine.load_flat(engine.grads, inp_var_grads)
+
+    def update_ops(step):
         lr = cfg.learning_rate(step)
         engine.optimizer_step(lr, beta1=cfg.beta_1, beta2=cfg.beta_2, eps=cfg.epsilon,
                               weight_decay=cfg.weight_decay, clip=cfg.gradient_clipping)
         return lr
 
-    return cfg.learning_rate, update_op
+    return cfg.learning_rate, update_ops, engine.grads

@@ -138,14 +138,18 @@ class VaeEngine:
         else:
             ops.conv2d_wgrad(dsc, x, dy, self.G(name + "/kernel"), self.G(name + "/bias"))
 
-    def load_params(self, named):
-        self.master.zero_()
+    def load_flat(self, flat, named):
+        """Fill one of the flat fp32 buffers (master | adam_m | adam_v) from a dict of reference-named tensors."""
+        flat.zero_()
         for name in self.layout.order:
-            dst = self.P(name)
+            dst = self.layout.view(flat, name)
             t = named[name].to(device=self.device, dtype=F32)
             if tuple(t.shape) != tuple(dst.shape):
                 raise L.DB200Error(f"load_params: {name}: expected {tuple(dst.shape)}, got {tuple(t.shape)}")
             dst.copy_(t)
+
+    def load_params(self, named):
+        self.load_flat(self.master, named)
         self.refresh_shadow()
 
     def export_params(self, source=None):

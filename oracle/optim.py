@@ -56,8 +56,7 @@ def adam_tf_step(p, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
 def dalle_train_step(params, m, v, grads, step, hp):
     """get_optimizer (src/optimizers.py:19-104): schedule -> clip (default 1.0) -> mtf Adam.  Returns new state."""
     lr = learning_rate(step, hp)
-    clip = hp.get("gradient_clipping")
-    clip = 1.0 if clip is None else clip                                  # optimizers.py:27
+    clip = hp["gradient_clipping"] if "gradient_clipping" in hp else 1.0  # optimizers.py:27 (explicit null: no clip)
     gn = None
     if clip is not None:
         grads, gn = clip_by_global_norm(grads, clip)                      # optimizers.py:101-102

@@ -193,3 +193,15 @@ def test_golden_fixtures_freeze_the_oracle(name):
         assert torch.allclose(loss, fx["loss"], rtol=1e-5)
         assert torch.equal(logits.argmax(-1), fx["tokens"])
         assert torch.allclose(out[0, 0, 0], fx["out_px"], atol=1e-5)
+
+
+@pytest.mark.parametrize("flip", ["attn_scale", "mask_value", "ln_eps"])
+def test_golden_fixture_detects_a_flipped_quirk(flip):
+    """Mutation check of the ‡ switches: the frozen golden outputs must NOT be reproduced when one recalled
+    mesh-tensorflow behaviour is flipped — otherwise the fixture would not pin that behaviour at all."""
+    fx = torch.load(os.path.join(GOLDEN, "dalle_tiny.pt"), weights_only=False)
+    cfg = O.DalleConfig(**fx["cfg"])
+    q = {"attn_scale": O.Quirks(attn_scale=cfg.head_dim ** -0.5), "mask_value": O.Quirks(mask_value=0.0),
+         "ln_eps": O.Quirks(ln_eps=1e-2)}[flip]
+    _, _, logits = O.forward(O.init_params(cfg, fx["seed"]), fx["tokens"], cfg, quirks=q)
+    assert not torch.allclose(logits[0, :, :8], fx["logits_slice"], atol=1e-5)
