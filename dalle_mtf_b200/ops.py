@@ -203,11 +203,29 @@ def split_f32(src, hi, lo=None):
 
 
 # ----------------------------------------------------------------------------------------------- attention
+# bench.py sets ATTN_PROFILE to a list to time every attention launch like GEMM_PROFILE: entries are
+# (start_event, end_event, causal-algorithmic flops, "fwd" | "bwd").  Forward = 2 products over the visible half of the
+# S x S logits: 4 S^2 dh B H / 2; backward = 2.5 x that (5 products).
+ATTN_PROFILE = None
+
+
+def _attn_timed(kind, B, S, H, dh, call):
+    prof = ATTN_PROFILE
+    if prof is None:
+        return call()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    call()
+    ev1.record()
+    prof.append((ev0, ev1, 2.0 * S * S * dh * B * H * (1.0 if kind == "fwd" else 2.5), kind))
+
+
 def attn_fwd(qkv, out, lse, B, S, H, dh, scale=1.0):
     L.require_device()
     _chk(qkv, BF16, "qkv"); _chk(out, BF16, "out"); _chk(lse, F32, "lse")
-    check(L.load().db200_attn_causal_fwd(stream_ptr(), ptr(qkv), ptr(out), ptr(lse), B, S, H, dh, scale),
-          "attn_causal_fwd")
+    _attn_timed("fwd", B, S, H, dh, lambda: check(
+        L.load().db200_attn_causal_fwd(stream_ptr(), ptr(qkv), ptr(out), ptr(lse), B, S, H, dh, scale),
+        "attn_causal_fwd"))
     return out
 
 
@@ -215,8 +233,9 @@ def attn_bwd(qkv, out, dout, lse, dq_accum, delta, dqkv, B, S, H, dh, scale=1.0)
     L.require_device()
     _chk(qkv, BF16, "qkv"); _chk(out, BF16, "out"); _chk(dout, BF16, "dout"); _chk(dqkv, BF16, "dqkv")
     _chk(lse, F32, "lse"); _chk(dq_accum, F32, "dq_accum"); _chk(delta, F32, "delta")
-    check(L.load().db200_attn_causal_bwd(stream_ptr(), ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dq_accum),
-                                         ptr(delta), ptr(dqkv), B, S, H, dh, scale), "attn_causal_bwd")
+    _attn_timed("bwd", B, S, H, dh, lambda: check(
+        L.load().db200_attn_causal_bwd(stream_ptr(), ptr(qkv), ptr(out), ptr(dout), ptr(lse), ptr(dq_accum),
+                                       ptr(delta), ptr(dqkv), B, S, H, dh, scale), "attn_causal_bwd"))
     return dqkv
 
 

@@ -106,13 +106,16 @@ def _dalle_parity(name, d, L, H, tv, iv, ts, isl, B, recompute, seed):
     del lg, logits16, logits32
 
     grads = eng.export_params(eng.grads)
-    worst = ("", 0.0, 0.0)
+    worst, ratios = ("", 0.0, 0.0, -1.0), []
     for k in g32:
         ee, er = relfro(grads[k], g32[k]), relfro(g16[k], g32[k])
-        if ee - 1.25 * er > worst[1] - 1.25 * worst[2]:
-            worst = (k, ee, er)
+        ratios.append(ee / (er + 1e-12))
+        if ee / (1.25 * er + 1e-2) > worst[3]:      # closest to the bound
+            worst = (k, ee, er, ee / (1.25 * er + 1e-2))
         assert ee <= 1.25 * er + 1e-2, (k, ee, er)
-    record(name + "/gradients", n_tensors=len(g32), worst_tensor=worst[0], worst_engine=worst[1], worst_refbf16=worst[2])
+    ratios.sort()
+    record(name + "/gradients", n_tensors=len(g32), closest_to_bound=worst[0], its_engine_err=worst[1],
+           its_refbf16_err=worst[2], median_engine_over_refbf16=ratios[len(ratios) // 2], max_engine_over_refbf16=ratios[-1])
     assert (eng.G("wout")[:, eng.V:] == 0).all() and (eng.G("bout")[eng.V:] == 0).all()   # padded vocabulary tail
 
     hp = {"lr": 1e-3, "train_steps": 1000, "warmup_steps": 10}
@@ -172,14 +175,16 @@ def test_vae_coco_geometry_k8192_bf16_matches_oracle():
     assert loss_rel < 2e-2
     assert e_log <= 1.5 * r_log + 1e-2 and e_rec <= 1.5 * r_rec + 1e-2
     eg = eng.export_params(eng.grads)
-    worst = ("", 0.0, 0.0)
+    worst, ratios = ("", 0.0, 0.0, -1.0), []
     for k in grads:
         ee, er = relfro(eg[k], grads[k]), relfro(g16[k], grads[k])
-        if ee - 1.5 * er > worst[1] - 1.5 * worst[2]:
-            worst = (k, ee, er)
+        ratios.append(ee / (er + 1e-12))
+        if ee / (1.5 * er + 2e-2) > worst[3]:
+            worst = (k, ee, er, ee / (1.5 * er + 2e-2))
         assert ee <= 1.5 * er + 2e-2, (k, ee, er)
-    record("VC 256px K8192 bf16 B1/gradients", n_tensors=len(grads), worst_tensor=worst[0], worst_engine=worst[1],
-           worst_refbf16=worst[2])
+    ratios.sort()
+    record("VC 256px K8192 bf16 B1/gradients", n_tensors=len(grads), closest_to_bound=worst[0], its_engine_err=worst[1],
+           its_refbf16_err=worst[2], median_engine_over_refbf16=ratios[len(ratios) // 2], max_engine_over_refbf16=ratios[-1])
 
 
 def test_bench_tokenizer_config_token_match_rate_and_near_tie_margins():

@@ -52,6 +52,10 @@ def run(report, guarded):
     case(1, 300, 3, 64, 0.125, 1.0, 3)
     case(1, 333, 2, 128, 0.0884, 1.0, 4)
     case(2, 1280, 4, 128, 1.0, 0.25, 5)
+    case(1, 640, 2, 128, 1.0, 1.2, 6)      # peaked softmax: the running maximum moves by > 2^8 (lazy rescale path)
+    case(1, 520, 3, 64, 1.0, 1.5, 7)
+    case(1, 129, 1, 128, 1.0, 0.5, 8)      # second tile has a single valid row
+    case(2, 1280, 3, 64, 0.125, 1.0, 9)
 
     @guarded
     def perf(B, S, H, dh):
