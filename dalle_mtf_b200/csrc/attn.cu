@@ -260,28 +260,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // ------------------------------------------------------------------------------------------------------------------
 // backward: delta = rowsum(dO * O)
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout,
-                                  float* __restrict__ delta, int B, int S, int H, int dh) {
-  // one warp per (b, s, h) row of dh elements
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// DH / 8 lanes share one (b, s, h) row (16-byte loads), so a warp covers 32 * 8 / DH consecutive rows = 512 contiguous
+// bytes of O and of dO per instruction: HBM-bound (the thread-per-2-elements version was issue-bound at 4x the time).
+template <int DH>
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, float* __restrict__ delta, int B, int S,
+                  int H) {
+  constexpr int LPR = DH / 8;  // lanes per row
   const long long rows = (long long)B * S * H;
-  if (row >= rows) return;
-  const bf16* op = o + row * dh;
-  const bf16* dp = dout + row * dh;
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long row = gt / LPR;
+  const int sub = (int)(gt % LPR);
   float acc = 0.f;
-  for (int e = lane * 2; e < dh; e += 64) {
-    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(op + e));
-    const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dp + e));
-    acc += a.x * d.x + a.y * d.y;
+  if (row < rows) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o + row * DH) + sub);
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(dout + row * DH) + sub);
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpack_bf16x2(av[i]), y = unpack_bf16x2(dv[i]);
+      acc = fmaf(x.x, y.x, acc);
+      acc = fmaf(x.y, y.y, acc);
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) {
+#pragma unroll
+  for (int ofs = LPR / 2; ofs > 0; ofs >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, ofs);
+  if (row < rows && sub == 0) {
     const int hh = (int)(row % H);
     const long long bs = row / H;
-    const int s = (int)(bs % S);
-    const int b = (int)(bs / S);
-    delta[((long long)b * H + hh) * S + s] = acc;
+    delta[((long long)(bs / S) * H + hh) * S + (bs % S)] = acc;
   }
 }
 
@@ -729,8 +736,14 @@ extern "C" int db200_attn_causal_bwd(db200_stream_t stream_, const void* qkv, co
   DB200_REQUIRE(scale > 0.f, DB200_E_INVALID, "attn_bwd: scale must be > 0");
   DB200_REQUIRE(dh == 64 || dh == 128, DB200_E_UNSUPPORTED, "attn: head_dim %d not in {64,128}", dh);
   const long long rows = (long long)B * S * H;
-  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, B, S,
-                                                                    H, dh);
+  {
+    const long long threads = rows * (dh / 8);
+    const unsigned blocks = (unsigned)((threads + 255) / 256);
+    if (dh == 128)
+      attn_delta_kernel<128><<<blocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, B, S, H);
+    else
+      attn_delta_kernel<64><<<blocks, 256, 0, stream>>>((const bf16*)out, (const bf16*)dout, delta, B, S, H);
+  }
   int rc = check_launch("attn_delta_kernel");
   if (rc != DB200_OK) return rc;
   if (!(attn_v1_bits() & 2)) return attn_bwd_ws_launch(stream, qkv, dout, lse, delta, dqkv, B, S, H, dh, scale);

@@ -10,32 +10,74 @@ earlier layers are still back-propagating.  The loss scalar rides in the first b
 handles; clip-by-global-norm is computed after the reduce, identically on every rank (src/optimizers.py:101-102), so
 there is no second collective.
 """
+import ctypes
 import os
 
 import torch
 import torch.distributed as dist
 
 
+def _libnccl_path():
+    """The libnccl.so.2 that ships next to torch (nvidia-nccl wheel); None -> the dynamic loader's default."""
+    try:
+        import nvidia.nccl
+        p = os.path.join(list(nvidia.nccl.__path__)[0], "lib", "libnccl.so.2")
+        return p if os.path.exists(p) else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class DataParallel:
+    """Rank bookkeeping + the gradient collectives.
+
+    Data plane on a GPU box: the communicator of libdalle_b200.so (db200_comm_*: ncclCommInitRankConfig, a dedicated
+    high-priority stream, event hand-offs, CTA cap) — torch.distributed is only the side channel that ships the NCCL
+    unique id and provides barrier / scalar reductions for logging (control plane, "gloo" for CPU tensors).
+    Without a GPU (the world-size-2 CPU tests of the bucket logic) the collectives go through torch.distributed/gloo.
+    """
+
+    # CTAs NCCL may occupy while the persistent 148-CTA tcgen05 grids of backward are running (0 = NCCL's default).
+    MAX_CTAS = int(os.environ.get("DB200_NCCL_MAX_CTAS", "8"))
+
     def __init__(self):
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.handles = []
         self.enabled = self.world > 1
+        self.comm = None          # db200_comm* (ctypes void pointer) when the C-ABI communicator is in use
+        self.registered = False
 
     def init(self, backend=None):
-        if torch.cuda.is_available():
+        cuda = torch.cuda.is_available()
+        if cuda:
             torch.cuda.set_device(self.local_rank)
         if self.enabled and not dist.is_initialized():
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29500")
-            backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
-            kw = {}
-            if backend == "nccl":
-                kw["device_id"] = torch.device("cuda", self.local_rank)
-            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world, **kw)
+            # control plane: gloo for host tensors; torch's own NCCL group is declared for CUDA tensors but stays
+            # uninitialised unless somebody uses it (the data plane below does not)
+            backend = backend or ("cpu:gloo,cuda:nccl" if cuda else "gloo")
+            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
+        if self.enabled and cuda and self.comm is None and os.environ.get("DB200_DP_BACKEND", "cabi") == "cabi":
+            self._create_comm()
         return self
+
+    def _create_comm(self):
+        from . import lib as L
+        lib = L.load()
+        path = _libnccl_path()
+        L.check(lib.db200_comm_load_nccl(path.encode() if path else None), "comm_load_nccl")
+        uid = ctypes.create_string_buffer(128)
+        if self.rank == 0:
+            L.check(lib.db200_comm_unique_id(uid, 128), "comm_unique_id")
+        box = [uid.raw]
+        dist.broadcast_object_list(box, src=0)            # side channel (gloo): 128 bytes
+        uid = ctypes.create_string_buffer(box[0], 128)
+        comm = ctypes.c_void_p()
+        L.check(lib.db200_comm_create(torch.cuda.current_device(), self.rank, self.world, uid, self.MAX_CTAS,
+                                      ctypes.byref(comm)), "comm_create")
+        self.comm = comm
 
     def shard(self, global_batch):
         """Rows [rank*B/N, (rank+1)*B/N) of the global batch."""
@@ -45,40 +87,71 @@ class DataParallel:
         return self.rank * per, per
 
     # --- gradient buckets ------------------------------------------------------------------------------
+    def _launch(self, t):
+        """Asynchronous in-place SUM all-reduce of a contiguous fp32 / bf16 tensor (a slice of a flat buffer)."""
+        if self.comm is not None:
+            from . import lib as L
+            dt = {torch.float32: 0, torch.bfloat16: 1}[t.dtype]
+            L.check(L.load().db200_bucket_allreduce_launch(self.comm, L.stream_ptr(), t.data_ptr(), t.numel(), dt),
+                    "bucket_allreduce_launch")
+        else:
+            self.handles.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
+
+    def register(self, flat):
+        """ncclCommRegister of a long-lived flat buffer (best effort; once)."""
+        if self.comm is not None and not self.registered:
+            from . import lib as L
+            ok = ctypes.c_int(0)
+            L.check(L.load().db200_comm_register(self.comm, flat.data_ptr(), flat.numel() * flat.element_size(),
+                                                 ctypes.byref(ok)), "comm_register")
+            self.registered = True
+
     def make_bucket_hook(self, flat):
-        """Returns on_bucket_ready(start, end) for DalleEngine.backward: async all-reduce(SUM) of flat[start:end]."""
+        """Returns on_bucket_ready(start, end) for the engines' backward: async all-reduce(SUM) of flat[start:end],
+        ordered after the kernels already enqueued on the current stream, overlapping with whatever comes next."""
         if not self.enabled:
             return None
+        self.register(flat)
 
         def hook(start, end):
             end = min(end, flat.numel())
-            self.handles.append(dist.all_reduce(flat[start:end], op=dist.ReduceOp.SUM, async_op=True))
+            self._launch(flat[start:end])
 
         return hook
 
     def all_reduce_now(self, t):
         if self.enabled:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            self._launch(t)
+            self.wait()
         return t
 
     def wait(self):
-        """Make the current stream wait for every outstanding bucket (no host block with NCCL)."""
+        """Make the current stream wait for every outstanding bucket (on the device; no host block with NCCL)."""
+        if self.comm is not None:
+            from . import lib as L
+            L.check(L.load().db200_bucket_allreduce_wait(self.comm, L.stream_ptr()), "bucket_allreduce_wait")
         for h in self.handles:
             h.wait()
         self.handles = []
 
     def barrier(self):
         if self.enabled:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
             dist.barrier()
 
     def max_over_ranks(self, value):
         if not self.enabled:
             return value
-        dev = "cuda" if torch.cuda.is_available() else "cpu"
-        t = torch.tensor([value], dtype=torch.float64, device=dev)
+        t = torch.tensor([value], dtype=torch.float64)       # host tensor: control plane (gloo)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def shutdown(self):
+        if self.comm is not None:
+            from . import lib as L
+            torch.cuda.synchronize()
+            L.load().db200_comm_destroy(self.comm)
+            self.comm = None
         if self.enabled and dist.is_initialized():
             dist.destroy_process_group()

@@ -86,6 +86,16 @@ _SIGNATURES = {
     "db200_gumbel_softmax_bwd": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32],
     "db200_argmax_rows_f32": [c_vp, c_vp, c_vp, c_int, c_int],
     "db200_mse_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_f32],
+    "db200_comm_load_nccl": [ctypes.c_char_p],
+    "db200_comm_unique_id": [c_vp, c_sz],
+    "db200_comm_create": [c_int, c_int, c_int, c_vp, c_int, ctypes.POINTER(c_vp)],
+    "db200_comm_destroy": [c_vp],
+    "db200_comm_register": [c_vp, c_vp, c_sz, ctypes.POINTER(c_int)],
+    "db200_comm_info": [c_vp, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
+    "db200_bucket_allreduce_launch": [c_vp, c_vp, c_vp, c_sz, c_int],
+    "db200_bucket_reduce_scatter_launch": [c_vp, c_vp, c_vp, c_vp, c_sz, c_int],
+    "db200_bucket_all_gather_launch": [c_vp, c_vp, c_vp, c_vp, c_sz, c_int],
+    "db200_bucket_allreduce_wait": [c_vp, c_vp],
 }
 EXPORTED_SYMBOLS = ["db200_last_error", "db200_launch_count"] + sorted(_SIGNATURES)
 

@@ -268,6 +268,40 @@ int db200_sample_rows(db200_stream_t stream, const float* logits, const float* u
                       long long ld, int lo, int hi, float inv_temp);
 int db200_onehot_rows_f32(db200_stream_t stream, const int32_t* idx, float* y, int rows, int K, int offset);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * D1  data-parallel collectives: hand-driven NCCL over NVLink / NVSwitch behind the C ABI.
+ *     Replaces the all-reduce mesh-tensorflow inserts for every weight gradient when it lowers the graph
+ *     (src/optimizers.py:34 mtf.gradients + src/model_fns.py:189 mtf.Lowering; layout "batch_dim:data",
+ *     configs/dalle_example.json:20-21) and tf.tpu.CrossShardOptimizer's gradient mean (src/model_fns_tf.py:61).
+ *   One process per GPU.  db200_comm owns an ncclComm_t, a high-priority communication stream and two events.
+ *   comm_load_nccl    : dlopen libnccl (path of the library to use, or NULL for "libnccl.so.2"); called implicitly.
+ *   comm_unique_id    : ncclGetUniqueId into a caller buffer (>= 128 bytes); rank 0 creates it, the host code ships it
+ *                       to the other ranks (any side channel), every rank then calls comm_create.
+ *   comm_create       : ncclCommInitRankConfig on `device`; max_ctas > 0 caps the CTAs NCCL may occupy so that the
+ *                       persistent tcgen05 GEMM grids running concurrently keep their SMs (0 = NCCL's default).
+ *   comm_register     : ncclCommRegister of a long-lived buffer (the flat gradient buffer); best effort.
+ *   bucket_allreduce_launch : in-place SUM all-reduce of buf[0..count) (dtype DB200_F32 / DB200_BF16) on the comm
+ *                       stream, ordered after everything already enqueued on compute_stream; does not block it.
+ *   bucket_reduce_scatter_launch / bucket_all_gather_launch : the ZeRO-1 pair (optimiser-state sharding): recv/send
+ *                       hold count_per_rank elements per rank.
+ *   bucket_allreduce_wait   : compute_stream waits (on the device; no host block) for every collective launched so far.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define DB200_F32 0
+#define DB200_BF16 1
+typedef struct db200_comm db200_comm;
+int db200_comm_load_nccl(const char* libnccl_path);
+int db200_comm_unique_id(void* id_out, size_t bytes);
+int db200_comm_create(int device, int rank, int world, const void* unique_id, int max_ctas, db200_comm** out);
+int db200_comm_destroy(db200_comm* comm);
+int db200_comm_register(db200_comm* comm, void* buf, size_t bytes, int* registered);
+int db200_comm_info(db200_comm* comm, int* rank, int* world, int* nccl_version);
+int db200_bucket_allreduce_launch(db200_comm* comm, db200_stream_t compute_stream, void* buf, size_t count, int dtype);
+int db200_bucket_reduce_scatter_launch(db200_comm* comm, db200_stream_t compute_stream, const void* send, void* recv,
+                                       size_t count_per_rank, int dtype);
+int db200_bucket_all_gather_launch(db200_comm* comm, db200_stream_t compute_stream, const void* send, void* recv,
+                                   size_t count_per_rank, int dtype);
+int db200_bucket_allreduce_wait(db200_comm* comm, db200_stream_t compute_stream);
+
 #ifdef __cplusplus
 }
 #endif
