@@ -42,6 +42,9 @@ WORKLOADS = {
     # name: (config file, sequences per GPU, d, layers, vocab)
     "dalle_example": ("dalle_example_b200.json", 32, 512, 6, 50771),
     "dalle_coco": ("dalle_coco_b200.json", 16, 1024, 24, 50258 + 8192 + 1),
+    # BASELINE.json configs[4]: 12 B parameters, optimiser state sharded over the data-parallel ranks (needs >= 2 GPUs,
+    # quoted at 8), per-block recompute, synthetic inputs, throughput only
+    "dalle_12b": ("dalle_12b_b200.json", 4, 4096, 64, 50258 + 8192 + 1),
 }
 
 

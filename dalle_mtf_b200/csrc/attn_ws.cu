@@ -1,27 +1,33 @@
-// K4 (warp-specialised) — causal flash attention forward on tcgen05 / TMEM / TMA for sm_100a.
+// K4 (warp-specialised) — causal flash attention, forward and backward, on tcgen05 / TMEM / TMA for sm_100a.
 //
 // Replaces mtf_transformer.attention.attention + the [S,S] additive -1e10 mask the reference materialises
-// (src/dalle_mtf/models.py:221-227, 287-299): logits fp32 (TMEM accumulators), softmax fp32, P rounded to bf16 for the
-// P.V product (what mtf does when it casts the weights to v's dtype), nothing of size S x S reaches HBM or even shared
-// memory.  `scale` multiplies q.k (reference: 1.0 — mtf folds 1/sqrt(dh) into the q initialiser).
+// (src/dalle_mtf/models.py:221-227, 287-299) and their gradients (mtf.gradients, src/optimizers.py:34): logits fp32
+// (TMEM accumulators), softmax fp32, P rounded to bf16 for the P.V product (what mtf does when it casts the weights to
+// v's dtype), nothing of size S x S reaches HBM or even shared memory.  `scale` multiplies q.k (reference: 1.0 — mtf
+// folds 1/sqrt(dh) into the q initialiser).
 //
-// Layout: qkv bf16 [B][S][3][H][dh] (the fused q|k|v projection output), out bf16 [B][S][H][dh],
-//         lse f32 [B][H][S] (natural log of sum exp(scale*s)).
+// Layout: qkv bf16 [B][S][3][H][dh] (the fused q|k|v projection output), out / dout bf16 [B][S][H][dh],
+//         lse f32 [B][H][S] (natural log of sum exp(scale*s)), delta f32 [B][H][S] = rowsum(dO * O), dqkv like qkv.
 //
-// One CTA = two neighbouring 128-query tiles of one (batch, head) that share every K / V block they both need
-// ("ping-pong": while one tile's softmax warpgroup exponentiates, the tensor pipe works for the other tile).
-//   warps 0-3  softmax warpgroup of tile 0: thread r owns query row r = TMEM lane r (no cross-thread reductions);
-//   warps 4-7  softmax warpgroup of tile 1;
-//   warp  8    TMA producer (one lane): Q tiles once, then a ring of K / V blocks (128 keys each);
-//   warp  9    MMA issuer (one lane):  S_t = Q_t K_j^T (SS form)  and  O_t += P_t V_j  (TS form: P is read from TMEM).
-// TMEM (512 columns): S_0 | S_1 (128 fp32 columns each) | O_0 | O_1 (dh columns each).  P_t (bf16, 64 columns) is
-// written by the softmax threads over the first half of S_t with tcgen05.st and consumed in place as the A operand of
-// the P.V product, so S_t's next logits can only be issued behind that product — the tensor pipe executes in issue
-// order, which is exactly the dependency needed.  Issue order: S0_0 S1_0 | PV0_0 S0_1 PV1_0 S1_1 | PV0_1 S0_2 ...
-// The output stays in TMEM across key blocks; a row is rescaled (tcgen05.ld -> scale -> tcgen05.st by its own softmax
-// thread) only when its running maximum has moved by more than 2^8 since the scale it uses (lazy rescaling).
-// All hand-offs are mbarriers: TMA -> MMA (k_full / v_full), MMA -> TMA (tcgen05.commit on k_empty / v_empty),
-// MMA -> softmax (commit on s_ready, o_done), softmax -> MMA (p_ready, one arrive per warp).
+// Common structure of the three kernels (one CTA per 128-row tile of one (batch, head), 1-D grid ordered heaviest tile
+// first): warps 0-3 and 4-7 = two "math" warpgroups (thread r of either group owns TMEM lane r; group g owns columns
+// [64g, 64g+64) of every 128-wide block), warp 8 = TMA producer (one lane), warp 9 = MMA issuer (one lane), warp 10 =
+// lse / delta stager where needed.  All hand-offs are mbarriers: TMA -> MMA (complete_tx), MMA -> TMA and MMA -> math
+// (tcgen05.commit), math -> MMA (one arrive per warp).  Probabilities / logit gradients are handed to the next product
+// THROUGH TENSOR MEMORY: the math threads write them as packed bf16 with tcgen05.st and the product reads them as its A
+// operand (tcgen05.mma TS form) — no shared-memory round trip, no proxy fence.  Each group writes its half of such an
+// operand into the first 32 columns of ITS OWN 64-column slice, so the two groups never touch each other's columns and
+// the operand's K-steps are addressed as slice 0 (columns +0..+31) then slice 1 (+64..+95).
+//
+//   forward : S double-buffered (2 x 128 columns); issue order  S0 S1 | PV0 S2 | PV1 S3 | ...  so the logits of block
+//             j+1 are always ready when the softmax of block j ends; O accumulates in TMEM across blocks and a row is
+//             rescaled (tcgen05.ld -> scale -> tcgen05.st) only when its running maximum moved by more than 2^8 since
+//             the scale it uses (lazy rescaling); the two groups exchange their half-row maxima through shared memory.
+//   dK / dV : TMEM lanes = keys, transposed orientation S^T = K Q_i^T, dP^T = V dO_i^T.  Two-phase pipeline per query
+//             block:  phase A  P^T = exp(S^T - lse)  runs under the dP^T product, phase B  dS^T = P^T (dP^T - delta)
+//             under the next block's S^T product:   S0 dP0 | [A0] dV0 S1 | [B0] dK0 dP1 | [A1] dV1 S2 | ...
+//   dQ      : lanes = queries; the groups release S / dP as soon as they are in registers, so the next block's two logit
+//             products run under the dS arithmetic; dS goes to its own double-buffered TMEM slot:  dQ += dS K_j.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -30,6 +36,7 @@ namespace db200 {
 namespace {
 
 constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr uint32_t T128B = 128 * 128;  // bytes of one [128 rows][64] swizzled sub-tile
 
 // MUFU.EX2 directly: arguments are <= 8 after the running-max subtraction; ex2.approx(-inf) = +0.
 __device__ __forceinline__ float ex2f(float x) {
@@ -38,19 +45,56 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// the 256 threads of the two math warpgroups (named barrier 1; barrier 0 is __syncthreads)
+__device__ __forceinline__ void math_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <int DH>
 __device__ __forceinline__ void ws_load_tile(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int chan, int row0,
                                              int b) {
 #pragma unroll
-  for (int t = 0; t < DH / 64; ++t) tma_load_4d(dst + t * (128 * 128), tm, bar, 64 * t, chan, row0, b);
+  for (int t = 0; t < DH / 64; ++t) tma_load_4d(dst + t * T128B, tm, bar, 64 * t, chan, row0, b);
 }
 
+// K-major [128][DH] tile, K-step kk (16 elements of dh)
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kk) {
+  return umma_smem_desc_sw128(tile + (kk / 4) * T128B + (kk % 4) * 32, 0, 1024);
+}
+// the same tile read as an MN-major operand (K = its 128 rows, N = dh), K-step kk (16 rows)
+__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) {
+  return umma_smem_desc_sw128(tile + kk * 2048, T128B, 1024);
+}
+// column of K-step kk (16 bf16 = 8 packed columns) of a TMEM A operand stored as two 32-column halves, one per group slice
+__device__ __forceinline__ uint32_t ts_split_col(int kk) { return (kk < 4) ? kk * 8 : 64 + (kk - 4) * 8; }
+
+__device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+__device__ __forceinline__ void store_row_bf16(bf16* dst, const uint32_t* r, float mul) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 8) {
+    uint4 q;
+    q.x = pack_bf16x2(__uint_as_float(r[e]) * mul, __uint_as_float(r[e + 1]) * mul);
+    q.y = pack_bf16x2(__uint_as_float(r[e + 2]) * mul, __uint_as_float(r[e + 3]) * mul);
+    q.z = pack_bf16x2(__uint_as_float(r[e + 4]) * mul, __uint_as_float(r[e + 5]) * mul);
+    q.w = pack_bf16x2(__uint_as_float(r[e + 6]) * mul, __uint_as_float(r[e + 7]) * mul);
+    *reinterpret_cast<uint4*>(dst + e) = q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------------
 template <int DH>
 struct FwdWs {
-  static constexpr int NS = (DH == 128) ? 2 : 4;           // K / V ring depth (128-key blocks)
-  static constexpr uint32_t TILE = 128 * DH * 2;           // one [128][DH] bf16 operand tile
+  static constexpr int NK = (DH == 128) ? 3 : 4;   // K ring depth (128-key blocks): logits run two blocks ahead
+  static constexpr int NV = (DH == 128) ? 2 : 4;   // V ring depth
+  static constexpr uint32_t TILE = 128 * DH * 2;   // one [128][DH] bf16 operand tile
+  static constexpr uint32_t XCH_BYTES = 2 * 2 * 128 * 4;
   static constexpr uint32_t BAR_BYTES = 256;
-  static constexpr size_t SMEM = 1024 + 2 * TILE + 2 * NS * TILE + BAR_BYTES;
+  static constexpr size_t SMEM = 1024 + TILE + (NK + NV) * TILE + XCH_BYTES + BAR_BYTES;
   static constexpr int THREADS = 320;
 };
 
@@ -61,49 +105,41 @@ __global__ void __launch_bounds__(320, 1)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out,
                    int S, int H, float scale) {
   using C = FwdWs<DH>;
-  constexpr int NS = C::NS;
+  constexpr int NK = C::NK, NV = C::NV;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = sQ + 2 * C::TILE, sV = sK + NS * C::TILE;
-  const uint32_t bars = sV + NS * C::TILE;
-  // barrier map (8 bytes each)
-  const uint32_t q_full = bars;                    // [2]
-  const uint32_t k_full = bars + 16;               // [NS]
-  const uint32_t v_full = k_full + 8 * NS;         // [NS]
-  const uint32_t k_empty = v_full + 8 * NS;        // [NS]
-  const uint32_t v_empty = k_empty + 8 * NS;       // [NS]
-  const uint32_t s_ready = v_empty + 8 * NS;       // [2]
+  const uint32_t sQ = base, sK = sQ + C::TILE, sV = sK + NK * C::TILE;
+  const uint32_t sX = sV + NV * C::TILE;                 // [2 parities][2 groups][128 rows] f32 maxima / sums
+  const uint32_t bars = sX + C::XCH_BYTES;
+  const uint32_t q_full = bars;
+  const uint32_t k_full = bars + 8;                // [NK]
+  const uint32_t k_empty = k_full + 8 * NK;        // [NK]
+  const uint32_t v_full = k_empty + 8 * NK;        // [NV]
+  const uint32_t v_empty = v_full + 8 * NV;        // [NV]
+  const uint32_t s_ready = v_empty + 8 * NV;       // [2]  S buffer b holds block j (j & 1 == b)
   const uint32_t p_ready = s_ready + 16;           // [2]
-  const uint32_t o_done = p_ready + 16;            // [2]
-  const uint32_t tmem_slot = o_done + 16;
+  const uint32_t o_done = p_ready + 16;            // P.V of block j has landed in O
+  const uint32_t tmem_slot = o_done + 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* xch = reinterpret_cast<float*>(smem_raw + (sX - raw));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // 1-D grid ordered by work: CTAs are dispatched in linear order, so ALL (batch, head) instances of the heaviest tile
-  // pair (the latest queries: most key blocks) come first and the light ones fill the tail (LPT scheduling)
+  // 1-D grid ordered by work: CTAs are dispatched in linear order, so ALL (batch, head) instances of the latest query
+  // tile (the most key blocks) come first and the light tiles fill the tail (LPT scheduling)
   const int n_qt = (S + 127) >> 7;
-  const int n_bh = gridDim.x / ((n_qt + 1) >> 1);
-  const int pair = ((n_qt + 1) >> 1) - 1 - (int)blockIdx.x / n_bh;
+  const int n_bh = gridDim.x / n_qt;
+  const int qt = n_qt - 1 - (int)blockIdx.x / n_bh;
   const int h = ((int)blockIdx.x % n_bh) % H, b = ((int)blockIdx.x % n_bh) / H;
-  // tile t of this CTA = query tile 2*pair + t; it needs key blocks 0 .. 2*pair + t (the last one is its diagonal)
-  const int n_kv0 = 2 * pair + 1;
-  const int n_kv1 = (2 * pair + 1 < n_qt) ? 2 * pair + 2 : 0;
-  const int n_j = n_kv1 > n_kv0 ? n_kv1 : n_kv0;
-  const int last_user = n_kv1 > 0 ? 1 : 0;  // the tile that issues the last product on every ring slot it shares
+  const int n_kv = qt + 1;  // key blocks 0 .. qt; block qt is the diagonal one
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(q_full + 8 * i, 1);
-      mbar_init(s_ready + 8 * i, 1);
-      mbar_init(p_ready + 8 * i, 4);  // one arrive per softmax warp
-      mbar_init(o_done + 8 * i, 1);
-    }
-    for (int i = 0; i < NS; ++i) {
-      mbar_init(k_full + 8 * i, 1); mbar_init(v_full + 8 * i, 1);
-      mbar_init(k_empty + 8 * i, 1); mbar_init(v_empty + 8 * i, 1);
-    }
+    mbar_init(q_full, 1);
+    for (int i = 0; i < NK; ++i) { mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1); }
+    for (int i = 0; i < NV; ++i) { mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(s_ready + 8 * i, 1); mbar_init(p_ready + 8 * i, 8); }
+    mbar_init(o_done, 1);
     fence_mbar_init();
   }
   if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -111,25 +147,21 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tO = tmem + 256;
 
   if (warp == 8) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
       mbar_expect_tx(q_full, C::TILE);
-      ws_load_tile<DH>(sQ, &tmQKV, q_full, 0 * H + h, (2 * pair) * 128, b);
-      if (n_kv1 > 0) {
-        mbar_expect_tx(q_full + 8, C::TILE);
-        ws_load_tile<DH>(sQ + C::TILE, &tmQKV, q_full + 8, 0 * H + h, (2 * pair + 1) * 128, b);
-      }
-      for (int j = 0; j < n_j; ++j) {
-        const int st = j % NS;
-        const uint32_t ph = (uint32_t)(j / NS) & 1u;
-        mbar_wait(k_empty + 8 * st, ph ^ 1u);
-        mbar_expect_tx(k_full + 8 * st, C::TILE);
-        ws_load_tile<DH>(sK + st * C::TILE, &tmQKV, k_full + 8 * st, 1 * H + h, j * 128, b);
-        mbar_wait(v_empty + 8 * st, ph ^ 1u);
-        mbar_expect_tx(v_full + 8 * st, C::TILE);
-        ws_load_tile<DH>(sV + st * C::TILE, &tmQKV, v_full + 8 * st, 2 * H + h, j * 128, b);
+      ws_load_tile<DH>(sQ, &tmQKV, q_full, 0 * H + h, qt * 128, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int sk = j % NK, sv = j % NV;
+        mbar_wait(k_empty + 8 * sk, ((uint32_t)(j / NK) & 1u) ^ 1u);
+        mbar_expect_tx(k_full + 8 * sk, C::TILE);
+        ws_load_tile<DH>(sK + sk * C::TILE, &tmQKV, k_full + 8 * sk, 1 * H + h, j * 128, b);
+        mbar_wait(v_empty + 8 * sv, ((uint32_t)(j / NV) & 1u) ^ 1u);
+        mbar_expect_tx(v_full + 8 * sv, C::TILE);
+        ws_load_tile<DH>(sV + sv * C::TILE, &tmQKV, v_full + 8 * sv, 2 * H + h, j * 128, b);
       }
     }
   } else if (warp == 9) {
@@ -137,147 +169,130 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T : both K-major (K = dh)
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);   // O = P V   : A from TMEM, B MN-major (K = keys)
-      auto issue_s = [&](int t, int j) {
-        const int st = j % NS;
-        if (j == 0) mbar_wait(q_full + 8 * t, 0);
-        mbar_wait(k_full + 8 * st, (uint32_t)(j / NS) & 1u);
+      auto issue_s = [&](int j) {
+        const int sk = j % NK;
+        mbar_wait(k_full + 8 * sk, (uint32_t)(j / NK) & 1u);
         tc_fence_after();
-        const uint32_t qb = sQ + t * C::TILE, kb = sK + st * C::TILE;
+        const uint32_t kb = sK + sk * C::TILE, tS = tmem + (j & 1) * 128;
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) {
-          const uint32_t o = (kk / 4) * (128 * 128) + (kk % 4) * 32;
-          umma_bf16_ss(tmem + t * 128, umma_smem_desc_sw128(qb + o, 0, 1024), umma_smem_desc_sw128(kb + o, 0, 1024),
-                       idesc_s, kk > 0);
-        }
-        umma_commit(s_ready + 8 * t);
-        if (t == last_user) umma_commit(k_empty + 8 * st);
+        for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tS, desc_kmajor(sQ, kk), desc_kmajor(kb, kk), idesc_s, kk > 0);
+        umma_commit(s_ready + 8 * (j & 1));
+        umma_commit(k_empty + 8 * sk);
       };
-      auto issue_pv = [&](int t, int j) {
-        const int st = j % NS;
-        mbar_wait(v_full + 8 * st, (uint32_t)(j / NS) & 1u);
-        mbar_wait(p_ready + 8 * t, (uint32_t)j & 1u);
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      if (n_kv > 1) issue_s(1);
+      for (int j = 0; j < n_kv; ++j) {
+        const int sv = j % NV;
+        mbar_wait(v_full + 8 * sv, (uint32_t)(j / NV) & 1u);
+        mbar_wait(p_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
         tc_fence_after();
-        const uint32_t vb = sV + st * C::TILE;
+        const uint32_t vb = sV + sv * C::TILE, tP = tmem + (j & 1) * 128;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // K = 128 keys, 16 per instruction = 8 packed TMEM columns of P
-          umma_bf16_ts(tmem + 256 + t * DH, tmem + t * 128 + kk * 8, umma_smem_desc_sw128(vb + kk * 2048, 128 * 128, 1024),
-                       idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(o_done + 8 * t);
-        if (t == last_user) umma_commit(v_empty + 8 * st);
-      };
-      issue_s(0, 0);
-      if (n_kv1 > 0) issue_s(1, 0);
-      for (int j = 0; j < n_j; ++j) {
-        if (j < n_kv0) issue_pv(0, j);
-        if (j + 1 < n_kv0) issue_s(0, j + 1);
-        if (j < n_kv1) issue_pv(1, j);
-        if (j + 1 < n_kv1) issue_s(1, j + 1);
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ts(tO, tP + ts_split_col(kk), desc_mnmajor(vb, kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(o_done);
+        umma_commit(v_empty + 8 * sv);
+        if (j + 2 < n_kv) issue_s(j + 2);  // into the buffer whose P the product above has just been queued to consume
       }
     }
   } else {
     // ------------------------------------------------------------------------------------------- softmax warpgroups
-    const int t = warp >> 2;                       // tile of this warpgroup
-    const int n_kv = t == 0 ? n_kv0 : n_kv1;
-    if (n_kv > 0) {
-      const int row = tid & 127;                   // query row inside the tile = TMEM lane
-      const int qt = 2 * pair + t;
-      const int qi = qt * 128 + row;
-      const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
-      const uint32_t tS = tmem + t * 128 + lane_off, tO = tmem + 256 + t * DH + lane_off;
-      const float c1 = scale * LOG2E_F;
-      float m_used = -INFINITY;  // the maximum the accumulated P / O / l are scaled by
-      float l_run = 0.f;
-      for (int j = 0; j < n_kv; ++j) {
-        mbar_wait(s_ready + 8 * t, (uint32_t)j & 1u);
-        tc_fence_after();
-        uint32_t sv[128];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld_x32(tS + c * 32, sv + c * 32);
-        tmem_ld_wait();
-        if (j == qt) {  // diagonal block: keys after the query are masked (src/dalle_mtf/models.py:221-227)
-#pragma unroll
-          for (int c = 0; c < 128; ++c)
-            if (c > row) sv[c] = 0xff800000u;  // -inf
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < 128; c += 4) {
-          mx0 = fmaxf(mx0, __uint_as_float(sv[c]));
-          mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
-          mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2]));
-          mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
-        }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));  // finite: key 0 is visible to every query
-        if (j == 0) {
-          m_used = mx;
-        } else {
-          const bool need = (mx - m_used) * c1 > 8.f;
-          if (__any_sync(0xffffffffu, need)) {  // tcgen05.ld / st are warp-collective
-            // the previous P.V of this tile must have landed in O before it is rescaled
-            mbar_wait(o_done + 8 * t, (uint32_t)(j - 1) & 1u);
-            tc_fence_after();
-            const float alpha = need ? ex2f((m_used - mx) * c1) : 1.f;
-#pragma unroll
-            for (int c = 0; c < DH / 32; ++c) {
-              uint32_t r[32];
-              tmem_ld_x32(tO + c * 32, r);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-              tmem_st_x32(tO + c * 32, r);
-            }
-            if (need) {
-              l_run *= alpha;
-              m_used = mx;
-            }
-          }
-        }
-        // P_j = 2^(c1 (s - m_used)) -> bf16 pairs -> the first 64 columns of S_t (A operand of the P.V product)
-        const float mc = m_used * c1;
-        float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2f(fmaf(__uint_as_float(sv[c * 32 + i]), c1, -mc));
-            const float p1 = ex2f(fmaf(__uint_as_float(sv[c * 32 + i + 1]), c1, -mc));
-            l0 += p0;
-            l1 += p1;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-          }
-          tmem_st_x16(tS + c * 16, pk);
-        }
-        l_run += l0 + l1;
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_ready + 8 * t);
-      }
-      // ---- epilogue: O / l -> bf16, lse
-      mbar_wait(o_done + 8 * t, (uint32_t)(n_kv - 1) & 1u);
+    const int g = warp >> 2;                       // column half of every key block / of the output
+    const int row = tid & 127;                     // query row inside the tile = TMEM lane
+    const int qi = qt * 128 + row;
+    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+    const float c1 = scale * LOG2E_F;
+    float m_used = -INFINITY;  // the maximum the accumulated P / O / l are scaled by (identical in both groups)
+    float l_run = 0.f;         // partial row sum over this group's key columns
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t tS = tmem + (j & 1) * 128 + 64 * g + lane_off;
+      mbar_wait(s_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
-      const float inv = 1.f / l_run;
-      bf16* op = out + (((long long)b * S + qi) * H + h) * DH;
+      uint32_t sv[64];
+      tmem_ld_x32(tS, sv);
+      tmem_ld_x32(tS + 32, sv + 32);
+      tmem_ld_wait();
+      if (j == qt) {  // diagonal block: keys after the query are masked (src/dalle_mtf/models.py:221-227)
+        const int lim = row - 64 * g;  // columns c > lim of this slice are in the future
 #pragma unroll
-      for (int c = 0; c < DH / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld_x32(tO + c * 32, r);
-        tmem_ld_wait();
-        if (qi < S) {
+        for (int c = 0; c < 64; ++c)
+          if (c > lim) sv[c] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            uint4 q;
-            q.x = pack_bf16x2(__uint_as_float(r[e]) * inv, __uint_as_float(r[e + 1]) * inv);
-            q.y = pack_bf16x2(__uint_as_float(r[e + 2]) * inv, __uint_as_float(r[e + 3]) * inv);
-            q.z = pack_bf16x2(__uint_as_float(r[e + 4]) * inv, __uint_as_float(r[e + 5]) * inv);
-            q.w = pack_bf16x2(__uint_as_float(r[e + 6]) * inv, __uint_as_float(r[e + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + c * 32 + e) = q;
+      for (int c = 0; c < 64; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
+      }
+      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      float* xp = xch + (j & 1) * 256;
+      xp[g * 128 + row] = mx;
+      math_bar_sync();  // both halves' maxima visible; both groups hold their S values in registers
+      mx = fmaxf(mx, xp[(g ^ 1) * 128 + row]);  // finite: key 0 is visible to every query
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = (mx - m_used) * c1 > 8.f;  // same decision in both threads of a row
+        if (__any_sync(0xffffffffu, need)) {         // tcgen05.ld / st are warp-collective
+          mbar_wait(o_done, (uint32_t)(j - 1) & 1u);  // the previous P.V has landed in O
+          tc_fence_after();
+          const float alpha = need ? ex2f((m_used - mx) * c1) : 1.f;
+#pragma unroll
+          for (int c = 0; c < DH / 64; ++c) {  // this group's half of the output columns
+            uint32_t r[32];
+            const uint32_t ta = tO + lane_off + g * (DH / 2) + c * 32;
+            tmem_ld_x32(ta, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_x32(ta, r);
+          }
+          if (need) {
+            l_run *= alpha;
+            m_used = mx;
           }
         }
       }
-      if (qi < S) lse_out[((long long)b * H + h) * S + qi] = m_used * scale + logf(l_run);
+      // P_j = 2^(c1 (s - m_used)) -> bf16 pairs -> the first 32 columns of this group's slice of the S buffer
+      const float mc = m_used * c1;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2f(fmaf(__uint_as_float(sv[c * 32 + i]), c1, -mc));
+          const float p1 = ex2f(fmaf(__uint_as_float(sv[c * 32 + i + 1]), c1, -mc));
+          l0 += p0;
+          l1 += p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_x16(tS + c * 16, pk);
+      }
+      l_run += l0 + l1;
+      tmem_st_wait();
+      warp_arrive(p_ready + 8 * (j & 1), lane);
     }
+    // ---- epilogue: O / l -> bf16 (this group's half of the columns), lse
+    float* xp = xch + (n_kv & 1) * 256;  // the parity the last block did not use
+    xp[g * 128 + row] = l_run;
+    mbar_wait(o_done, (uint32_t)(n_kv - 1) & 1u);
+    tc_fence_after();
+    math_bar_sync();
+    const float l_tot = l_run + xp[(g ^ 1) * 128 + row];
+    const float inv = 1.f / l_tot;
+    bf16* op = out + (((long long)b * S + qi) * H + h) * DH + g * (DH / 2);
+#pragma unroll
+    for (int c = 0; c < DH / 64; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(tO + lane_off + g * (DH / 2) + c * 32, r);
+      tmem_ld_wait();
+      if (qi < S) store_row_bf16(op + c * 32, r, inv);
+    }
+    if (qi < S && g == 0) lse_out[((long long)b * H + h) * S + qi] = m_used * scale + logf(l_tot);
   }
   tc_fence_before();
   __syncthreads();
@@ -288,96 +303,69 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// backward (warp-specialised).  Two launches of ONE kernel template, no atomics:
-//   MODE 0  dK / dV : CTA = 128 keys (TMEM lanes = keys), loops over 64-query blocks i >= the first block that sees
-//                     them, in the TRANSPOSED orientation:  S^T = K Q_i^T,  dP^T = V dO_i^T  (128 x 64, SS form);
-//                     P^T / dS^T are written by the gradient warpgroups as bf16 over the first halves of S^T / dP^T and
-//                     consumed from TMEM:  dV += P^T dO_i,  dK += dS^T Q_i  (TS form, B = the same Q_i / dO_i tiles
-//                     read as MN-major operands).  lse / delta of the block's 64 queries are staged in shared memory.
-//   MODE 1  dQ      : CTA = 128 queries (lanes = queries), loops over 64-key blocks j:  S = Q K_j^T,  dP = dO V_j^T,
-//                     dS over dP in TMEM,  dQ += dS K_j  (TS form, K_j read MN-major).
+// backward
 //   p  = exp(scale*s - lse)   (0 where key > query or the query is out of range)
 //   ds = p * (dp - delta) * scale
-// Roles (384 threads): warps 0-3 / 4-7 = two gradient warpgroups that take alternate blocks (each owns one of the two
-// S / dP buffers in TMEM), warp 8 = TMA producer (resident tiles, then a 4-deep ring of block tiles), warp 9 = MMA
-// issuer, warp 10 = lse / delta stager (MODE 0).  Issue order  L0 L1 | G0 L2 | G1 L3 | ...  (L = the two logit
-// products of a block, G = its gradient products): the tensor pipe computes block i+1's logits while a warpgroup
-// turns block i's into P / dS.  TMEM: accumulators [0, 2 dh), buffers at 256 + 128 buf (S at +0, dP at +64).
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
 template <int DH>
 struct BwdWs {
-  static constexpr int NS = 4;
-  static constexpr uint32_t TILE = 128 * DH * 2;  // resident [128][DH] tile
-  static constexpr uint32_t HT = 64 * DH * 2;     // ring [64][DH] tile
-  static constexpr uint32_t STAT_BYTES = NS * 128 * 4;
+  static constexpr int NS = 2;                     // ring depth of the streamed [128][DH] tile pairs
+  static constexpr uint32_t TILE = 128 * DH * 2;
+  static constexpr uint32_t STAT_BYTES = NS * 256 * 4;
   static constexpr uint32_t BAR_BYTES = 256;
-  static constexpr size_t SMEM = 1024 + 2 * TILE + NS * 2 * HT + STAT_BYTES + BAR_BYTES;
+  static constexpr size_t SMEM = 1024 + 2 * TILE + NS * 2 * TILE + STAT_BYTES + BAR_BYTES;
   static constexpr int THREADS = 384;
 };
-constexpr uint32_t T64B = 64 * 128;    // bytes of one [64 rows][64] swizzled sub-tile
-constexpr uint32_t T128B = 128 * 128;  // bytes of one [128 rows][64] swizzled sub-tile
-
-template <int DH>
-__device__ __forceinline__ void ws_load_tile64(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int chan, int row0,
-                                               int b) {
-#pragma unroll
-  for (int t = 0; t < DH / 64; ++t) tma_load_4d(dst + t * T64B, tm, bar, 64 * t, chan, row0, b);
-}
 }  // namespace
 
-template <int DH, int MODE>
+// dK / dV: CTA = 128 keys (TMEM lanes), loop over the 128-query blocks i >= its own.  TMEM: dV [0,dh) dK [dh,2dh)
+// S^T [256,384) dP^T [384,512).
+template <int DH>
 __global__ void __launch_bounds__(384, 1)
-attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_constant__ CUtensorMap tmQKV64,
-                   const __grid_constant__ CUtensorMap tmDO128, const __grid_constant__ CUtensorMap tmDO64,
-                   const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S,
-                   int H, float scale) {
+attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                        const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
+                        int S, int H, float scale) {
   using C = BwdWs<DH>;
   constexpr int NS = C::NS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sX = base, sY = sX + C::TILE, sR = sY + C::TILE;  // ring stage st: B1 at sR + st*2*HT, B2 right behind
-  const uint32_t sStat = sR + NS * 2 * C::HT;
+  const uint32_t sK = base, sV = sK + C::TILE, sR = sV + C::TILE;  // ring stage st: Q_i at sR + st*2*TILE, dO_i behind it
+  const uint32_t sStat = sR + NS * 2 * C::TILE;
   const uint32_t bars = sStat + C::STAT_BYTES;
-  const uint32_t x_full = bars;                 // resident tiles
+  const uint32_t x_full = bars;
   const uint32_t r_full = bars + 8;             // [NS]
   const uint32_t r_empty = r_full + 8 * NS;     // [NS]
   const uint32_t stat_full = r_empty + 8 * NS;  // [NS]
-  const uint32_t s_ready = stat_full + 8 * NS;  // [2]
-  const uint32_t p_ready = s_ready + 16;        // [2]
-  const uint32_t acc_done = p_ready + 16;
+  const uint32_t sa_ready = stat_full + 8 * NS; // S^T of block it in TMEM
+  const uint32_t sb_ready = sa_ready + 8;       // dP^T
+  const uint32_t pa_ready = sb_ready + 8;       // P^T written (8 warps)
+  const uint32_t pb_ready = pa_ready + 8;       // dS^T written
+  const uint32_t acc_done = pb_ready + 8;
   const uint32_t tmem_slot = acc_done + 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   const float* stat = reinterpret_cast<const float*>(smem_raw + (sStat - raw));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // 1-D grid ordered by work (LPT): MODE 0: key block 0 sees every query block -> all its (batch, head) instances first;
-  // MODE 1: the last query tile has the most key blocks -> first
+  // 1-D grid, heaviest first: key block 0 is seen by every query block
   const int n_blk = (S + 127) >> 7;
   const int n_bh = gridDim.x / n_blk;
-  const int blk = MODE == 0 ? (int)blockIdx.x / n_bh : n_blk - 1 - (int)blockIdx.x / n_bh;
+  const int jb = (int)blockIdx.x / n_bh;
   const int h = ((int)blockIdx.x % n_bh) % H, b = ((int)blockIdx.x % n_bh) / H;
-  const int r0 = blk * 128;  // first key (MODE 0) / query (MODE 1) of this CTA
-  const int it0 = MODE == 0 ? 2 * blk : 0;                                               // first 64-row block of the loop
-  const int n_it = MODE == 0 ? (S + 63) / 64 - it0 : (min(S, r0 + 128) + 63) / 64;       // >= 1
+  const int r0 = jb * 128;
+  const int n_it = n_blk - jb;
   const long long bh = (long long)b * H + h;
 
   if (tid == 0) {
-    tma_prefetch_desc(&tmQKV128);
-    tma_prefetch_desc(&tmQKV64);
-    tma_prefetch_desc(&tmDO128);
-    tma_prefetch_desc(&tmDO64);
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
     mbar_init(x_full, 1);
     for (int i = 0; i < NS; ++i) {
-      mbar_init(r_full + 8 * i, 1);
-      mbar_init(r_empty + 8 * i, 1);
-      mbar_init(stat_full + 8 * i, 1);
+      mbar_init(r_full + 8 * i, 1); mbar_init(r_empty + 8 * i, 1); mbar_init(stat_full + 8 * i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(s_ready + 8 * i, 1);
-      mbar_init(p_ready + 8 * i, 4);  // one arrive per warp of the warpgroup
-    }
+    mbar_init(sa_ready, 1); mbar_init(sb_ready, 1);
+    mbar_init(pa_ready, 8); mbar_init(pb_ready, 8);
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
@@ -386,196 +374,332 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tST = tmem + 256, tdPT = tmem + 384;
 
   if (warp == 8) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
       mbar_expect_tx(x_full, 2 * C::TILE);
-      if (MODE == 0) {
-        ws_load_tile<DH>(sX, &tmQKV128, x_full, 1 * H + h, r0, b);   // K
-        ws_load_tile<DH>(sY, &tmQKV128, x_full, 2 * H + h, r0, b);   // V
-      } else {
-        ws_load_tile<DH>(sX, &tmQKV128, x_full, 0 * H + h, r0, b);   // Q
-        ws_load_tile<DH>(sY, &tmDO128, x_full, h, r0, b);            // dO
-      }
+      ws_load_tile<DH>(sK, &tmQKV, x_full, 1 * H + h, r0, b);
+      ws_load_tile<DH>(sV, &tmQKV, x_full, 2 * H + h, r0, b);
       for (int it = 0; it < n_it; ++it) {
         const int st = it % NS;
         mbar_wait(r_empty + 8 * st, ((uint32_t)(it / NS) & 1u) ^ 1u);
-        const uint32_t fb = r_full + 8 * st, d1 = sR + st * 2 * C::HT, d2 = d1 + C::HT;
-        const int c0 = (it0 + it) * 64;
-        mbar_expect_tx(fb, 2 * C::HT);
-        if (MODE == 0) {
-          ws_load_tile64<DH>(d1, &tmQKV64, fb, 0 * H + h, c0, b);    // Q_i
-          ws_load_tile64<DH>(d2, &tmDO64, fb, h, c0, b);             // dO_i
-        } else {
-          ws_load_tile64<DH>(d1, &tmQKV64, fb, 1 * H + h, c0, b);    // K_j
-          ws_load_tile64<DH>(d2, &tmQKV64, fb, 2 * H + h, c0, b);    // V_j
-        }
+        const uint32_t fb = r_full + 8 * st, dq = sR + st * 2 * C::TILE;
+        mbar_expect_tx(fb, 2 * C::TILE);
+        ws_load_tile<DH>(dq, &tmQKV, fb, 0 * H + h, (jb + it) * 128, b);          // Q_i
+        ws_load_tile<DH>(dq + C::TILE, &tmDO, fb, h, (jb + it) * 128, b);         // dO_i
       }
     }
   } else if (warp == 9) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 64, 0, 0);   // logits: both operands K-major (K = dh)
-      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // gradients: A from TMEM, B MN-major (K = 64 rows)
-      auto issue_l = [&](int it) {
-        const int st = it % NS, buf = it & 1;
+      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);  // logits: both operands K-major (K = dh)
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // gradients: A from TMEM, B MN-major (K = queries)
+      auto issue_s = [&](int it) {   // S^T = K Q_i^T
+        const int st = it % NS;
         mbar_wait(r_full + 8 * st, (uint32_t)(it / NS) & 1u);
         tc_fence_after();
-        const uint32_t b1 = sR + st * 2 * C::HT, b2 = b1 + C::HT;
-        const uint32_t tS = tmem + 256 + buf * 128, tdP = tS + 64;
+        const uint32_t q = sR + st * 2 * C::TILE;
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16_ss(tS, umma_smem_desc_sw128(sX + (kk / 4) * T128B + (kk % 4) * 32, 0, 1024),
-                       umma_smem_desc_sw128(b1 + (kk / 4) * T64B + (kk % 4) * 32, 0, 1024), idesc_l, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk)
-          umma_bf16_ss(tdP, umma_smem_desc_sw128(sY + (kk / 4) * T128B + (kk % 4) * 32, 0, 1024),
-                       umma_smem_desc_sw128(b2 + (kk / 4) * T64B + (kk % 4) * 32, 0, 1024), idesc_l, kk > 0);
-        umma_commit(s_ready + 8 * buf);
+        for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tST, desc_kmajor(sK, kk), desc_kmajor(q, kk), idesc_l, kk > 0);
+        umma_commit(sa_ready);
       };
-      auto issue_g = [&](int it) {
-        const int st = it % NS, buf = it & 1;
-        mbar_wait(p_ready + 8 * buf, (uint32_t)(it >> 1) & 1u);
+      auto issue_dp = [&](int it) {  // dP^T = V dO_i^T
+        const int st = it % NS;
+        mbar_wait(r_full + 8 * st, (uint32_t)(it / NS) & 1u);
         tc_fence_after();
-        const uint32_t b1 = sR + st * 2 * C::HT, b2 = b1 + C::HT;
-        const uint32_t tS = tmem + 256 + buf * 128, tdP = tS + 64;
-        const uint32_t acc = (it > 0) ? 1u : 0u;
-        if (MODE == 0) {
+        const uint32_t o = sR + st * 2 * C::TILE + C::TILE;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO_i
-            umma_bf16_ts(tmem, tS + kk * 8, umma_smem_desc_sw128(b2 + kk * 2048, T64B, 1024), idesc_g, acc | (kk > 0));
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q_i
-            umma_bf16_ts(tmem + DH, tdP + kk * 8, umma_smem_desc_sw128(b1 + kk * 2048, T64B, 1024), idesc_g,
-                         acc | (kk > 0));
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk)  // dQ += dS K_j
-            umma_bf16_ts(tmem, tdP + kk * 8, umma_smem_desc_sw128(b1 + kk * 2048, T64B, 1024), idesc_g, acc | (kk > 0));
-        }
-        umma_commit(r_empty + 8 * st);
-        if (it == n_it - 1) umma_commit(acc_done);
+        for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tdPT, desc_kmajor(sV, kk), desc_kmajor(o, kk), idesc_l, kk > 0);
+        umma_commit(sb_ready);
       };
       mbar_wait(x_full, 0);
-      issue_l(0);
-      if (n_it > 1) issue_l(1);
+      issue_s(0);
+      issue_dp(0);
       for (int it = 0; it < n_it; ++it) {
-        issue_g(it);
-        if (it + 2 < n_it) issue_l(it + 2);
+        const int st = it % NS;
+        const uint32_t q = sR + st * 2 * C::TILE, o = q + C::TILE;
+        const uint32_t acc = it > 0 ? 1u : 0u;
+        mbar_wait(pa_ready, (uint32_t)it & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i
+          umma_bf16_ts(tmem, tST + ts_split_col(kk), desc_mnmajor(o, kk), idesc_g, acc | (kk > 0));
+        if (it + 1 < n_it) issue_s(it + 1);    // runs under phase B of this block
+        mbar_wait(pb_ready, (uint32_t)it & 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
+          umma_bf16_ts(tmem + DH, tdPT + ts_split_col(kk), desc_mnmajor(q, kk), idesc_g, acc | (kk > 0));
+        umma_commit(r_empty + 8 * st);
+        if (it + 1 < n_it) issue_dp(it + 1);   // runs under phase A of the next block
       }
+      umma_commit(acc_done);
     }
   } else if (warp == 10) {
     // ------------------------------------------------------------------------------------------- lse / delta stager
-    if (MODE == 0) {
-      float* stat_w = reinterpret_cast<float*>(smem_raw + (sStat - raw));
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it % NS;
-        mbar_wait(r_empty + 8 * st, ((uint32_t)(it / NS) & 1u) ^ 1u);
-        const int c0 = (it0 + it) * 64;
+    float* stat_w = reinterpret_cast<float*>(smem_raw + (sStat - raw));
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it % NS;
+      mbar_wait(r_empty + 8 * st, ((uint32_t)(it / NS) & 1u) ^ 1u);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int q = c0 + lane + 32 * u;
-          float l2 = INFINITY, d = 0.f;  // out-of-range query: p = 2^(-inf) = 0
-          if (q < S) {
-            l2 = lse[bh * S + q] * LOG2E_F;
-            d = delta[bh * S + q];
-          }
-          stat_w[st * 128 + lane + 32 * u] = l2;
-          stat_w[st * 128 + 64 + lane + 32 * u] = d;
+      for (int u = 0; u < 4; ++u) {
+        const int c = lane + 32 * u, q = (jb + it) * 128 + c;
+        float l2 = INFINITY, d = 0.f;  // out-of-range query: p = 2^(-inf) = 0
+        if (q < S) {
+          l2 = lse[bh * S + q] * LOG2E_F;
+          d = delta[bh * S + q];
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(stat_full + 8 * st);
+        stat_w[st * 256 + c] = l2;
+        stat_w[st * 256 + 128 + c] = d;
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stat_full + 8 * st);
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------------------------------------- gradient warpgroups
-    const int g = warp >> 2;
-    const int row = tid & 127;                 // TMEM lane: key (MODE 0) / query (MODE 1) inside the tile
-    const int ri = r0 + row;
+    const int g = warp >> 2;            // query columns [64g, 64g+64) of every block
+    const int row = tid & 127;          // key row = TMEM lane
+    const int ki = r0 + row;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
-    const uint32_t tS = tmem + 256 + g * 128 + lane_off, tdP = tS + 64;
+    const uint32_t tS = tST + 64 * g + lane_off, tdP = tdPT + 64 * g + lane_off;
     const float c1 = scale * LOG2E_F;
-    float lse2 = INFINITY, dl = 0.f;           // MODE 1: this query's statistics
-    if (MODE == 1 && ri < S) {
-      lse2 = lse[bh * S + ri] * LOG2E_F;
-      dl = delta[bh * S + ri];
-    }
-    for (int it = g; it < n_it; it += 2) {
+    for (int it = 0; it < n_it; ++it) {
       const int st = it % NS;
-      const int c0 = (it0 + it) * 64;
-      mbar_wait(s_ready + 8 * g, (uint32_t)(it >> 1) & 1u);
+      const float4* sl = reinterpret_cast<const float4*>(stat + st * 256 + 64 * g);
+      const float4* sd = reinterpret_cast<const float4*>(stat + st * 256 + 128 + 64 * g);
+      // ---- phase A: P^T = 2^(c1 s - lse2[query]); pair dropped where key > query (only the first block is diagonal)
+      mbar_wait(stat_full + 8 * st, (uint32_t)(it / NS) & 1u);
+      mbar_wait(sa_ready, (uint32_t)it & 1u);
       tc_fence_after();
-      if (MODE == 0) mbar_wait(stat_full + 8 * st, (uint32_t)(it / NS) & 1u);
-      // causal mask (src/dalle_mtf/models.py:221-227): the pair is dropped where key > query.
-      //   MODE 0: key = ri, query = c0 + c  -> dropped where c < ri - c0;   MODE 1: query = ri, key = c0 + c -> c > ri - c0
-      const int dgl = ri - c0;
-      const bool diag = MODE == 0 ? (dgl > 0) : (dgl < 63);
-      const float4* sl = reinterpret_cast<const float4*>(stat + st * 128);
-      const float4* sd = reinterpret_cast<const float4*>(stat + st * 128 + 64);
+      uint32_t pk[32];
+      const int lim = (it == 0) ? row - 64 * g : -1;  // columns c < lim are queries before this key
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t rs[32], rd[32], pk[16], dk[16];
+        uint32_t rs[32];
         tmem_ld_x32(tS + c * 32, rs);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 a = sl[(c * 32 + i) >> 2];
+          float p0 = ex2f(fmaf(__uint_as_float(rs[i]), c1, -a.x)), p1 = ex2f(fmaf(__uint_as_float(rs[i + 1]), c1, -a.y));
+          float p2 = ex2f(fmaf(__uint_as_float(rs[i + 2]), c1, -a.z)), p3 = ex2f(fmaf(__uint_as_float(rs[i + 3]), c1, -a.w));
+          const int cc = c * 32 + i;
+          if (cc < lim) p0 = 0.f;
+          if (cc + 1 < lim) p1 = 0.f;
+          if (cc + 2 < lim) p2 = 0.f;
+          if (cc + 3 < lim) p3 = 0.f;
+          pk[(cc >> 1)] = pack_bf16x2(p0, p1);
+          pk[(cc >> 1) + 1] = pack_bf16x2(p2, p3);
+        }
+      }
+      tmem_st_x32(tS, pk);
+      tmem_st_wait();
+      warp_arrive(pa_ready, lane);
+      // ---- phase B: dS^T = (P^T * scale) (dP^T - delta[query])
+      mbar_wait(sb_ready, (uint32_t)it & 1u);
+      tc_fence_after();
+      uint32_t dk[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t rd[32];
         tmem_ld_x32(tdP + c * 32, rd);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
-          float l2[4], dd[4];
-          if (MODE == 0) {
-            const float4 a = sl[(c * 32 + i) >> 2], d4 = sd[(c * 32 + i) >> 2];
-            l2[0] = a.x; l2[1] = a.y; l2[2] = a.z; l2[3] = a.w;
-            dd[0] = d4.x; dd[1] = d4.y; dd[2] = d4.z; dd[3] = d4.w;
-          } else {
-            l2[0] = l2[1] = l2[2] = l2[3] = lse2;
-            dd[0] = dd[1] = dd[2] = dd[3] = dl;
-          }
-          float p[4], ds[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            p[e] = ex2f(fmaf(__uint_as_float(rs[i + e]), c1, -l2[e]));
-            if (diag) {
-              const int cc = c * 32 + i + e;
-              if (MODE == 0 ? (cc < dgl) : (cc > dgl)) p[e] = 0.f;
-            }
-            ds[e] = (p[e] * scale) * (__uint_as_float(rd[i + e]) - dd[e]);
-          }
-          pk[i >> 1] = pack_bf16x2(p[0], p[1]);
-          pk[(i >> 1) + 1] = pack_bf16x2(p[2], p[3]);
-          dk[i >> 1] = pack_bf16x2(ds[0], ds[1]);
-          dk[(i >> 1) + 1] = pack_bf16x2(ds[2], ds[3]);
+          const float4 d4 = sd[(c * 32 + i) >> 2];
+          const int cc = c * 32 + i;
+          const float2 pa = unpack_bf16x2(pk[cc >> 1]), pb = unpack_bf16x2(pk[(cc >> 1) + 1]);
+          dk[cc >> 1] = pack_bf16x2((pa.x * scale) * (__uint_as_float(rd[i]) - d4.x),
+                                    (pa.y * scale) * (__uint_as_float(rd[i + 1]) - d4.y));
+          dk[(cc >> 1) + 1] = pack_bf16x2((pb.x * scale) * (__uint_as_float(rd[i + 2]) - d4.z),
+                                          (pb.y * scale) * (__uint_as_float(rd[i + 3]) - d4.w));
         }
-        if (MODE == 0) tmem_st_x16(tS + c * 16, pk);
-        tmem_st_x16(tdP + c * 16, dk);
       }
+      tmem_st_x32(tdP, dk);
       tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready + 8 * g);
+      warp_arrive(pb_ready, lane);
     }
-    // ---- epilogue: accumulators -> bf16 rows of dqkv.  MODE 0: warpgroup 0 writes dV, 1 writes dK; MODE 1: half of dQ each
+    // ---- epilogue: group 0 writes dV, group 1 dK (bf16 rows of dqkv)
     mbar_wait(acc_done, 0);
     tc_fence_after();
-    constexpr int NCH = MODE == 0 ? DH / 32 : DH / 64;
-    const int which = MODE == 0 ? (g == 0 ? 2 : 1) : 0;
-    const uint32_t tsrc = tmem + lane_off + (MODE == 0 ? g * DH : g * (DH / 2));
-    bf16* dst = dqkv + ((((long long)b * S + ri) * 3 + which) * H + h) * DH + (MODE == 0 ? 0 : g * (DH / 2));
+    bf16* dst = dqkv + ((((long long)b * S + ki) * 3 + (g == 0 ? 2 : 1)) * H + h) * DH;
 #pragma unroll 1
-    for (int c = 0; c < NCH; ++c) {
+    for (int c = 0; c < DH / 32; ++c) {
       uint32_t r[32];
-      tmem_ld_x32(tsrc + c * 32, r);
+      tmem_ld_x32(tmem + lane_off + g * DH + c * 32, r);
       tmem_ld_wait();
-      if (ri < S) {
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 q;
-          q.x = pack_bf16x2(__uint_as_float(r[q4 * 8 + 0]), __uint_as_float(r[q4 * 8 + 1]));
-          q.y = pack_bf16x2(__uint_as_float(r[q4 * 8 + 2]), __uint_as_float(r[q4 * 8 + 3]));
-          q.z = pack_bf16x2(__uint_as_float(r[q4 * 8 + 4]), __uint_as_float(r[q4 * 8 + 5]));
-          q.w = pack_bf16x2(__uint_as_float(r[q4 * 8 + 6]), __uint_as_float(r[q4 * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + c * 32 + q4 * 8) = q;
-        }
+      if (ki < S) store_row_bf16(dst + c * 32, r, 1.f);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// dQ: CTA = 128 queries (TMEM lanes), loop over the 128-key blocks j <= its own.  TMEM: dQ [0,dh) S [128,256)
+// dP [256,384) dS [384,448) [448,512).
+template <int DH>
+__global__ void __launch_bounds__(384, 1)
+attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                      const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S,
+                      int H, float scale) {
+  using C = BwdWs<DH>;
+  constexpr int NS = C::NS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sQ = base, sdO = sQ + C::TILE, sR = sdO + C::TILE;  // ring stage st: K_j at sR + st*2*TILE, V_j behind
+  const uint32_t bars = sR + NS * 2 * C::TILE + C::STAT_BYTES;
+  const uint32_t x_full = bars;
+  const uint32_t r_full = bars + 8;              // [NS]
+  const uint32_t r_empty = r_full + 8 * NS;      // [NS]
+  const uint32_t sd_ready = r_empty + 8 * NS;    // S, dP of block j in TMEM
+  const uint32_t sd_loaded = sd_ready + 8;       // both groups hold them in registers (8 warps)
+  const uint32_t ds_ready = sd_loaded + 8;       // [2] dS of block j written (8 warps)
+  const uint32_t ds_free = ds_ready + 16;        // [2] the dQ product has consumed that dS slot
+  const uint32_t acc_done = ds_free + 16;
+  const uint32_t tmem_slot = acc_done + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // 1-D grid, heaviest first: the last query tile sees every key block
+  const int n_blk = (S + 127) >> 7;
+  const int n_bh = gridDim.x / n_blk;
+  const int ib = n_blk - 1 - (int)blockIdx.x / n_bh;
+  const int h = ((int)blockIdx.x % n_bh) % H, b = ((int)blockIdx.x % n_bh) / H;
+  const int r0 = ib * 128;
+  const int n_it = ib + 1;
+  const long long bh = (long long)b * H + h;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(x_full, 1);
+    for (int i = 0; i < NS; ++i) { mbar_init(r_full + 8 * i, 1); mbar_init(r_empty + 8 * i, 1); }
+    mbar_init(sd_ready, 1);
+    mbar_init(sd_loaded, 8);
+    for (int i = 0; i < 2; ++i) { mbar_init(ds_ready + 8 * i, 8); mbar_init(ds_free + 8 * i, 1); }
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tSb = tmem + 128, tdPb = tmem + 256, tdSb = tmem + 384;
+
+  if (warp == 8) {
+    // ------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(x_full, 2 * C::TILE);
+      ws_load_tile<DH>(sQ, &tmQKV, x_full, 0 * H + h, r0, b);
+      ws_load_tile<DH>(sdO, &tmDO, x_full, h, r0, b);
+      for (int j = 0; j < n_it; ++j) {
+        const int st = j % NS;
+        mbar_wait(r_empty + 8 * st, ((uint32_t)(j / NS) & 1u) ^ 1u);
+        const uint32_t fb = r_full + 8 * st, dk = sR + st * 2 * C::TILE;
+        mbar_expect_tx(fb, 2 * C::TILE);
+        ws_load_tile<DH>(dk, &tmQKV, fb, 1 * H + h, j * 128, b);                  // K_j
+        ws_load_tile<DH>(dk + C::TILE, &tmQKV, fb, 2 * H + h, j * 128, b);        // V_j
       }
+    }
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dQ = dS K : A from TMEM, B MN-major (K = keys)
+      auto issue_l = [&](int j) {  // S = Q K_j^T, dP = dO V_j^T
+        const int st = j % NS;
+        mbar_wait(r_full + 8 * st, (uint32_t)(j / NS) & 1u);
+        tc_fence_after();
+        const uint32_t k = sR + st * 2 * C::TILE, v = k + C::TILE;
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tSb, desc_kmajor(sQ, kk), desc_kmajor(k, kk), idesc_l, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tdPb, desc_kmajor(sdO, kk), desc_kmajor(v, kk), idesc_l, kk > 0);
+        umma_commit(sd_ready);
+      };
+      mbar_wait(x_full, 0);
+      issue_l(0);
+      for (int j = 0; j < n_it; ++j) {
+        const int st = j % NS;
+        if (j + 1 < n_it) {  // the groups hold block j in registers: the next logits run under their arithmetic
+          mbar_wait(sd_loaded, (uint32_t)j & 1u);
+          issue_l(j + 1);
+        }
+        mbar_wait(ds_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t k = sR + st * 2 * C::TILE, tdS = tdSb + 64 * (j & 1);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16_ts(tmem, tdS + kk * 8, desc_mnmajor(k, kk), idesc_g, (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(r_empty + 8 * st);
+        umma_commit(ds_free + 8 * (j & 1));
+      }
+      umma_commit(acc_done);
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------------------------------- gradient warpgroups
+    const int g = warp >> 2;            // key columns [64g, 64g+64) of every block
+    const int row = tid & 127;          // query row = TMEM lane
+    const int qi = r0 + row;
+    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t tS = tSb + 64 * g + lane_off, tdP = tdPb + 64 * g + lane_off;
+    const float c1 = scale * LOG2E_F;
+    float lse2 = INFINITY, dl = 0.f;    // out-of-range query row: p = 0
+    if (qi < S) {
+      lse2 = lse[bh * S + qi] * LOG2E_F;
+      dl = delta[bh * S + qi];
+    }
+    for (int j = 0; j < n_it; ++j) {
+      mbar_wait(sd_ready, (uint32_t)j & 1u);
+      tc_fence_after();
+      uint32_t rs[64], rd[64];
+      tmem_ld_x32(tS, rs);
+      tmem_ld_x32(tS + 32, rs + 32);
+      tmem_ld_x32(tdP, rd);
+      tmem_ld_x32(tdP + 32, rd + 32);
+      tmem_ld_wait();
+      warp_arrive(sd_loaded, lane);      // S / dP may be overwritten by the next block's logits
+      const int lim = (j == ib) ? row - 64 * g : 64;  // columns c > lim are keys after this query (diagonal block)
+      if (j >= 2) {                      // the dQ product of block j-2 has consumed this dS slot
+        mbar_wait(ds_free + 8 * (j & 1), (uint32_t)((j - 2) >> 1) & 1u);
+        tc_fence_after();
+      }
+      const uint32_t tdS = tdSb + 64 * (j & 1) + 32 * g + lane_off;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t dk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const int cc = c * 32 + i;
+          float p0 = ex2f(fmaf(__uint_as_float(rs[cc]), c1, -lse2)), p1 = ex2f(fmaf(__uint_as_float(rs[cc + 1]), c1, -lse2));
+          if (cc > lim) p0 = 0.f;
+          if (cc + 1 > lim) p1 = 0.f;
+          dk[i >> 1] = pack_bf16x2((p0 * scale) * (__uint_as_float(rd[cc]) - dl),
+                                   (p1 * scale) * (__uint_as_float(rd[cc + 1]) - dl));
+        }
+        tmem_st_x16(tdS + c * 16, dk);
+      }
+      tmem_st_wait();
+      warp_arrive(ds_ready + 8 * (j & 1), lane);
+    }
+    // ---- epilogue: each group writes half of the dQ columns
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    bf16* dst = dqkv + ((((long long)b * S + qi) * 3 + 0) * H + h) * DH + g * (DH / 2);
+#pragma unroll 1
+    for (int c = 0; c < DH / 64; ++c) {
+      uint32_t r[32];
+      tmem_ld_x32(tmem + lane_off + g * (DH / 2) + c * 32, r);
+      tmem_ld_wait();
+      if (qi < S) store_row_bf16(dst + c * 32, r, 1.f);
     }
   }
   tc_fence_before();
@@ -589,11 +713,17 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV128, const __grid_co
 // ------------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------------
-static int ws_qkv_map(CUtensorMap* tm, const void* qkv, int B, int S, int H, int dh, uint32_t box_rows) {
+static int ws_qkv_map(CUtensorMap* tm, const void* qkv, int B, int S, int H, int dh) {
   uint64_t dims[4] = {(uint64_t)dh, (uint64_t)3 * H, (uint64_t)S, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)dh * 2, (uint64_t)3 * H * dh * 2, (uint64_t)S * 3 * H * dh * 2};
-  uint32_t box[4] = {64, 1, box_rows, 1};
+  uint32_t box[4] = {64, 1, 128, 1};
   return make_tmap_bf16(tm, qkv, 4, dims, strides, box);
+}
+static int ws_o_map(CUtensorMap* tm, const void* o, int B, int S, int H, int dh) {
+  uint64_t dims[4] = {(uint64_t)dh, (uint64_t)H, (uint64_t)S, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)dh * 2, (uint64_t)H * dh * 2, (uint64_t)S * H * dh * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  return make_tmap_bf16(tm, o, 4, dims, strides, box);
 }
 
 template <int DH>
@@ -601,13 +731,12 @@ static int fwd_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, floa
                            float scale) {
   using C = FwdWs<DH>;
   CUtensorMap tm;
-  int rc = ws_qkv_map(&tm, qkv, B, S, H, DH, 128);
+  int rc = ws_qkv_map(&tm, qkv, B, S, H, DH);
   if (rc != DB200_OK) return rc;
   static const cudaError_t attr = cudaFuncSetAttribute(attn_fwd_ws_kernel<DH>,
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   DB200_CUDA(attr);
-  const int n_qt = (S + 127) / 128;
-  dim3 grid(((n_qt + 1) / 2) * H * B);
+  dim3 grid(((S + 127) / 128) * H * B);
   attn_fwd_ws_kernel<DH><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, scale);
   return check_launch("attn_fwd_ws_kernel");
 }
@@ -618,37 +747,26 @@ int attn_fwd_ws_launch(cudaStream_t stream, const void* qkv, void* out, float* l
   return fwd_ws_launch_t<64>(stream, qkv, out, lse, B, S, H, scale);
 }
 
-static int ws_o_map(CUtensorMap* tm, const void* o, int B, int S, int H, int dh, uint32_t box_rows) {
-  uint64_t dims[4] = {(uint64_t)dh, (uint64_t)H, (uint64_t)S, (uint64_t)B};
-  uint64_t strides[3] = {(uint64_t)dh * 2, (uint64_t)H * dh * 2, (uint64_t)S * H * dh * 2};
-  uint32_t box[4] = {64, 1, box_rows, 1};
-  return make_tmap_bf16(tm, o, 4, dims, strides, box);
-}
-
 template <int DH>
 static int bwd_ws_launch_t(cudaStream_t stream, const void* qkv, const void* dout, const float* lse,
                            const float* delta, void* dqkv, int B, int S, int H, float scale) {
   using C = BwdWs<DH>;
-  CUtensorMap q128, q64, o128, o64;
-  int rc = ws_qkv_map(&q128, qkv, B, S, H, DH, 128);
-  if (rc == DB200_OK) rc = ws_qkv_map(&q64, qkv, B, S, H, DH, 64);
-  if (rc == DB200_OK) rc = ws_o_map(&o128, dout, B, S, H, DH, 128);
-  if (rc == DB200_OK) rc = ws_o_map(&o64, dout, B, S, H, DH, 64);
+  CUtensorMap tq, to;
+  int rc = ws_qkv_map(&tq, qkv, B, S, H, DH);
+  if (rc == DB200_OK) rc = ws_o_map(&to, dout, B, S, H, DH);
   if (rc != DB200_OK) return rc;
-  static const cudaError_t a0 = cudaFuncSetAttribute(attn_bwd_ws_kernel<DH, 0>,
+  static const cudaError_t a0 = cudaFuncSetAttribute(attn_bwd_dkdv_ws_kernel<DH>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-  static const cudaError_t a1 = cudaFuncSetAttribute(attn_bwd_ws_kernel<DH, 1>,
+  static const cudaError_t a1 = cudaFuncSetAttribute(attn_bwd_dq_ws_kernel<DH>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   DB200_CUDA(a0);
   DB200_CUDA(a1);
   dim3 grid(((S + 127) / 128) * H * B);
-  attn_bwd_ws_kernel<DH, 0><<<grid, C::THREADS, C::SMEM, stream>>>(q128, q64, o128, o64, lse, delta, (bf16*)dqkv, S, H,
-                                                                 scale);
-  rc = check_launch("attn_bwd_ws_kernel<dkdv>");
+  attn_bwd_dkdv_ws_kernel<DH><<<grid, C::THREADS, C::SMEM, stream>>>(tq, to, lse, delta, (bf16*)dqkv, S, H, scale);
+  rc = check_launch("attn_bwd_dkdv_ws_kernel");
   if (rc != DB200_OK) return rc;
-  attn_bwd_ws_kernel<DH, 1><<<grid, C::THREADS, C::SMEM, stream>>>(q128, q64, o128, o64, lse, delta, (bf16*)dqkv, S, H,
-                                                                 scale);
-  return check_launch("attn_bwd_ws_kernel<dq>");
+  attn_bwd_dq_ws_kernel<DH><<<grid, C::THREADS, C::SMEM, stream>>>(tq, to, lse, delta, (bf16*)dqkv, S, H, scale);
+  return check_launch("attn_bwd_dq_ws_kernel");
 }
 
 int attn_bwd_ws_launch(cudaStream_t stream, const void* qkv, const void* dout, const float* lse, const float* delta,

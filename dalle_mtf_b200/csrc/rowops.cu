@@ -237,6 +237,145 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
   }
 }
 
+// Wide rows (d = 4096, the 12 B configuration): ONE CTA of 128 threads per row, thread t owns columns
+// {(c*128 + t)*8 .. +7 : c < NCW} (16-byte accesses, 2 KiB contiguous per c across the CTA).  Row statistics go through
+// a two-level (warp shuffle + 4-float shared) reduction; in backward every thread owns its columns for the whole row
+// walk, so dgamma / dbeta / dxsum need no cross-thread reduction at all: one atomicAdd per column per CTA at the end.
+__device__ __forceinline__ float2 block128_sum2(float a, float b, float* red /*[8]*/) {
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const int warp = threadIdx.x >> 5;
+  __syncthreads();  // previous use of `red` is over
+  if ((threadIdx.x & 31) == 0) { red[warp] = a; red[4 + warp] = b; }
+  __syncthreads();
+  return make_float2(red[0] + red[1] + red[2] + red[3], red[4] + red[5] + red[6] + red[7]);
+}
+
+template <int NCW>
+__global__ void __launch_bounds__(128)
+layernorm_fwd_wide_kernel(const bf16* __restrict__ x, const float* __restrict__ g, const float* __restrict__ b,
+                          bf16* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows,
+                          float eps) {
+  constexpr int d = NCW * 1024;
+  __shared__ float red[8];
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const bf16* xr = x + (long long)row * d;
+    float v[NCW][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCW; ++c) {
+      unpack8(*reinterpret_cast<const uint4*>(xr + (c * 128 + threadIdx.x) * 8), v[c]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[c][j];
+    }
+    const float mean = block128_sum2(sum, 0.f, red).x * (1.f / d);
+    float sq = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCW; ++c)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = v[c][j] - mean;
+        sq += t * t;
+      }
+    const float rstd = rsqrtf(block128_sum2(sq, 0.f, red).x * (1.f / d) + eps);
+    if (threadIdx.x == 0) {
+      mean_out[row] = mean;
+      rstd_out[row] = rstd;
+    }
+    bf16* yr = y + (long long)row * d;
+#pragma unroll
+    for (int c = 0; c < NCW; ++c) {
+      const int col = (c * 128 + threadIdx.x) * 8;
+      const float4 g0 = *reinterpret_cast<const float4*>(g + col), g1 = *reinterpret_cast<const float4*>(g + col + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(b + col), b1 = *reinterpret_cast<const float4*>(b + col + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[c][j] - mean) * rstd * gg[j] + bb[j];
+      *reinterpret_cast<uint4*>(yr + col) = pack8(o);
+    }
+  }
+}
+
+template <int NCW>
+__global__ void __launch_bounds__(128)
+layernorm_bwd_wide_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ g,
+                          const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                          const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dg,
+                          float* __restrict__ db, float* __restrict__ dxsum, int rows) {
+  constexpr int d = NCW * 1024;
+  __shared__ float red[8];
+  float gg[NCW][8], adg[NCW][8], adb[NCW][8], adx[NCW][8];
+#pragma unroll
+  for (int c = 0; c < NCW; ++c) {
+    const int col = (c * 128 + threadIdx.x) * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(g + col), g1 = *reinterpret_cast<const float4*>(g + col + 4);
+    gg[c][0] = g0.x; gg[c][1] = g0.y; gg[c][2] = g0.z; gg[c][3] = g0.w;
+    gg[c][4] = g1.x; gg[c][5] = g1.y; gg[c][6] = g1.z; gg[c][7] = g1.w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) adg[c][j] = adb[c][j] = adx[c][j] = 0.f;
+  }
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    const bf16* xr = x + (long long)row * d;
+    const bf16* dyr = dy + (long long)row * d;
+    float xh[NCW][8], dg_[NCW][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCW; ++c) {
+      const int col = (c * 128 + threadIdx.x) * 8;
+      float xv[8], dv[8];
+      unpack8(*reinterpret_cast<const uint4*>(xr + col), xv);
+      unpack8(*reinterpret_cast<const uint4*>(dyr + col), dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float h = (xv[j] - mean) * rstd;
+        const float t = dv[j] * gg[c][j];
+        xh[c][j] = h;
+        dg_[c][j] = t;
+        s1 += t;
+        s2 += t * h;
+        adg[c][j] += dv[j] * h;
+        adb[c][j] += dv[j];
+      }
+    }
+    const float2 ss = block128_sum2(s1, s2, red);
+    const float c1 = ss.x * (1.f / d), c2 = ss.y * (1.f / d);
+    bf16* dxr = dx + (long long)row * d;
+#pragma unroll
+    for (int c = 0; c < NCW; ++c) {
+      const int col = (c * 128 + threadIdx.x) * 8;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (dg_[c][j] - c1 - xh[c][j] * c2) * rstd;
+      if (dres) {
+        float r[8];
+        unpack8(*reinterpret_cast<const uint4*>(dres + (long long)row * d + col), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      const uint4 packed = pack8(o);
+      *reinterpret_cast<uint4*>(dxr + col) = packed;
+      if (dxsum) {
+        float ro[8];
+        unpack8(packed, ro);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) adx[c][j] += ro[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NCW; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = (c * 128 + threadIdx.x) * 8 + j;
+      atomicAdd(dg + col, adg[c][j]);
+      atomicAdd(db + col, adb[c][j]);
+      if (dxsum) atomicAdd(dxsum + col, adx[c][j]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ column sums
 // grid: (ceil(cols/256), row_splits).  lane -> 8 columns, warps stride over rows.
 __global__ void __launch_bounds__(256)
@@ -437,8 +576,9 @@ extern "C" int db200_layernorm_fwd(db200_stream_t stream_, const void* x, const 
     case 768:  layernorm_fwd_kernel<3><<<grid, 128, 0, stream>>>(xp, g, b, yp, mean, rstd, rows, eps); break;
     case 1024: layernorm_fwd_kernel<4><<<grid, 128, 0, stream>>>(xp, g, b, yp, mean, rstd, rows, eps); break;
     case 2048: layernorm_fwd_kernel<8><<<grid, 128, 0, stream>>>(xp, g, b, yp, mean, rstd, rows, eps); break;
+    case 4096: layernorm_fwd_wide_kernel<4><<<min(rows, sm_count() * 16), 128, 0, stream>>>(xp, g, b, yp, mean, rstd, rows, eps); break;
     default:
-      return set_error(DB200_E_UNSUPPORTED, "layernorm: d=%d not in {256,512,768,1024,2048}", d);
+      return set_error(DB200_E_UNSUPPORTED, "layernorm: d=%d not in {256,512,768,1024,2048,4096}", d);
   }
   return check_launch("layernorm_fwd_kernel");
 }
@@ -461,8 +601,9 @@ extern "C" int db200_layernorm_bwd_ex(db200_stream_t stream_, const void* dy, co
     case 768:  layernorm_bwd_kernel<3><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, dxsum, rows); break;
     case 1024: layernorm_bwd_kernel<4><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, dxsum, rows); break;
     case 2048: layernorm_bwd_kernel<8><<<grid, 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, dxsum, rows); break;
+    case 4096: layernorm_bwd_wide_kernel<4><<<min(rows, sm_count() * 4), 128, 0, stream>>>(dyp, xp, g, mean, rstd, drp, dxp, dg, db, dxsum, rows); break;
     default:
-      return set_error(DB200_E_UNSUPPORTED, "layernorm: d=%d not in {256,512,768,1024,2048}", d);
+      return set_error(DB200_E_UNSUPPORTED, "layernorm: d=%d not in {256,512,768,1024,2048,4096}", d);
   }
   return check_launch("layernorm_bwd_kernel");
 }
@@ -507,6 +648,26 @@ extern "C" int db200_cast_bf16_to_f32(db200_stream_t stream_, const void* src, f
   if (blocks < 1) blocks = 1;
   cast_bf16_f32_kernel<<<(int)blocks, 256, 0, stream>>>((const bf16*)src, dst, n);
   return check_launch("cast_bf16_f32_kernel");
+}
+
+// Segmented bf16 -> f32 gather: segment i copies len[i] elements from src + src_off[i] to dst + dst_off[i]
+// (table = int64 triples {src_off, dst_off, len} in device memory).  One CTA per segment (grid-stride inside).
+// Used by the optimiser-state-sharded (ZeRO-1) mode: after the all-gather of the bf16 parameters every rank rebuilds
+// its compact fp32 copy of the vector parameters (LayerNorm gains / biases, all biases) in ONE launch.
+__global__ void __launch_bounds__(256)
+gather_cast_kernel(const bf16* __restrict__ src, float* __restrict__ dst, const long long* __restrict__ table) {
+  const long long so = table[3 * blockIdx.x], d0 = table[3 * blockIdx.x + 1], n = table[3 * blockIdx.x + 2];
+  for (long long i = threadIdx.x; i < n; i += 256) dst[d0 + i] = __bfloat162float(src[so + i]);
+}
+
+extern "C" int db200_gather_cast_bf16_f32(db200_stream_t stream_, const void* src, float* dst, const int64_t* table_dev,
+                                          int n_segments) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (n_segments == 0) return DB200_OK;
+  DB200_REQUIRE(src && dst && table_dev && n_segments > 0, DB200_E_INVALID, "gather_cast: bad arguments");
+  gather_cast_kernel<<<n_segments, 256, 0, stream>>>((const bf16*)src, dst,
+                                                      reinterpret_cast<const long long*>(table_dev));
+  return check_launch("gather_cast_kernel");
 }
 
 extern "C" int db200_split_f32_to_bf16x2(db200_stream_t stream_, const float* src, void* hi, void* lo_or_null, size_t n) {

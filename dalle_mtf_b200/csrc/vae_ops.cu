@@ -108,9 +108,41 @@ mse_kernel(const float* __restrict__ pred, const float* __restrict__ target, flo
   }
 }
 
+// tf.space_to_depth / tf.depth_to_space (NHWC, block size s) used by stack_factor > 1 (src/vae_tf/models.py:85-86,
+// 155-161): deep[n, y, x, (dy*s + dx)*C + c] = flat[n, y*s + dy, x*s + dx, c].  One thread per element, coalesced on
+// the deep side (the flat side is read / written in runs of C consecutive floats).
+template <bool TO_DEPTH>
+__global__ void __launch_bounds__(256)
+space_depth_kernel(const float* __restrict__ in, float* __restrict__ out, long long n_elem, int Hd, int Wd, int C, int s) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // index on the deep side
+  if (i >= n_elem) return;
+  const int Cd = C * s * s;
+  const int cd = (int)(i % Cd);
+  long long t = i / Cd;
+  const int x = (int)(t % Wd); t /= Wd;
+  const int y = (int)(t % Hd);
+  const long long n = t / Hd;
+  const int c = cd % C, dx = (cd / C) % s, dy = cd / (C * s);
+  const long long flat = ((n * (Hd * s) + (y * s + dy)) * (long long)(Wd * s) + (x * s + dx)) * C + c;
+  if (TO_DEPTH) out[i] = in[flat];
+  else          out[flat] = in[i];
+}
+
 }  // namespace db200
 
 using namespace db200;
+
+extern "C" int db200_space_to_depth_f32(db200_stream_t stream_, const float* in, float* out, int N, int H, int W, int C,
+                                        int s, int inverse) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(in && out && N > 0 && s >= 1 && H % s == 0 && W % s == 0 && C > 0, DB200_E_INVALID,
+                "space_to_depth: H, W must be multiples of the block size");
+  const long long n = (long long)N * H * W * C;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (inverse) space_depth_kernel<false><<<blocks, 256, 0, stream>>>(in, out, n, H / s, W / s, C, s);
+  else         space_depth_kernel<true><<<blocks, 256, 0, stream>>>(in, out, n, H / s, W / s, C, s);
+  return check_launch("space_depth_kernel");
+}
 
 extern "C" int db200_gumbel_softmax_fwd(db200_stream_t stream_, const float* logits, const float* u, float* y_soft,
                                         float* y_out, int32_t* idx, int rows, int K, float tau, int hard) {

@@ -63,8 +63,14 @@ class ParamLayout:
 class DalleEngine:
     """One data-parallel replica of the DALL-E decoder (src/dalle_mtf/models.py:141-416)."""
 
+    VECTOR_PARAMS = ("ln1_g", "ln1_b", "o_b", "ln2_g", "ln2_b", "b1", "b2", "lnf_g", "lnf_b", "bout")
+
     def __init__(self, n_embd, n_layers, n_heads, text_vocab_size, image_vocab_size, text_seq_len, image_seq_len,
-                 device="cuda", recompute_grad=False, attn_scale=1.0, ln_eps=1e-5):
+                 device="cuda", recompute_grad=False, attn_scale=1.0, ln_eps=1e-5, zero=None):
+        """zero: a DataParallel with world > 1 turns on optimiser-state sharding (ZeRO-1, SURVEY.md §7 "12 B in pure
+        DP"): fp32 master / Adam m / Adam v exist only for this rank's 1/N slice of the flat buffer, the bf16 compute
+        copy and the fp32 gradients stay full; after the (all-reduced) gradients are final every rank updates its
+        slice and the bf16 parameters are all-gathered in place.  Still data parallel: same batch split, same maths."""
         L.require_device()
         self.d, self.L, self.H = n_embd, n_layers, n_heads
         assert n_embd % n_heads == 0, "n_state must be divisible by n_heads"  # src/dalle_mtf/models.py:232
@@ -106,11 +112,34 @@ class DalleEngine:
         n = lay.size + 64
         dev = self.device
         self._views = {}
-        self.master = torch.zeros(n, dtype=F32, device=dev)
+        self.zero = zero if (zero is not None and getattr(zero, "world", 1) > 1) else None
         self.grads = torch.zeros(n, dtype=F32, device=dev)
-        self.adam_m = torch.zeros(n, dtype=F32, device=dev)
-        self.adam_v = torch.zeros(n, dtype=F32, device=dev)
-        self.shadow = torch.zeros(n, dtype=BF16, device=dev)
+        if self.zero is None:
+            self.master = torch.zeros(n, dtype=F32, device=dev)
+            self.adam_m = torch.zeros(n, dtype=F32, device=dev)
+            self.adam_v = torch.zeros(n, dtype=F32, device=dev)
+            self.shadow = torch.zeros(n, dtype=BF16, device=dev)
+            self.shard = (0, lay.size)
+        else:
+            w, r = self.zero.world, self.zero.rank
+            self.chunk = _round_up(-(-lay.size // w), 64)                 # elements per rank (equal: in-place all-gather)
+            self.shard = (min(r * self.chunk, lay.size), min((r + 1) * self.chunk, lay.size))
+            self.master = torch.zeros(self.chunk, dtype=F32, device=dev)  # this rank's slice only
+            self.adam_m = torch.zeros(self.chunk, dtype=F32, device=dev)
+            self.adam_v = torch.zeros(self.chunk, dtype=F32, device=dev)
+            self.shadow = torch.zeros(max(w * self.chunk, n), dtype=BF16, device=dev)
+            # compact fp32 copy of the vector parameters (LayerNorm g / b, biases) the kernels read in fp32: rebuilt
+            # from the bf16 parameters after every all-gather — mtf casts every variable to the activation dtype when
+            # it is used (src/dalle_mtf/ops.py:76-82), so this is the reference's own bf16 policy
+            self._vec_off, table, off = {}, [], 0
+            for name in lay.order:
+                if name.split(".")[-1] in self.VECTOR_PARAMS:
+                    o, shp = lay.entries[name]
+                    self._vec_off[name] = (off, shp)
+                    table += [o, off, shp[0]]
+                    off += _round_up(shp[0], 64)
+            self.vec32 = torch.zeros(off, dtype=F32, device=dev)
+            self._vec_table = torch.tensor(table, dtype=torch.int64, device=dev)
         self.gnorm_sq = torch.zeros(1, dtype=F32, device=dev)
         self._bufs = None
         self._buf_key = None
@@ -125,7 +154,16 @@ class DalleEngine:
             v = self._views[key] = self.layout.view(flat, name)
         return v
 
-    def P(self, name):  # fp32 master view
+    def P(self, name):  # fp32 view of a parameter (ZeRO-1: only the vector parameters exist in full fp32)
+        if self.zero is not None:
+            if name not in self._vec_off:
+                raise L.DB200Error(f"{name}: the fp32 master of a matrix is sharded across ranks in ZeRO-1 mode")
+            key = (3, name)
+            v = self._views.get(key)
+            if v is None:
+                off, shp = self._vec_off[name]
+                v = self._views[key] = self.vec32[off:off + shp[0]]
+            return v
         return self._view(0, self.master, name)
 
     def W(self, name):  # bf16 compute copy
@@ -155,9 +193,47 @@ class DalleEngine:
         self.load_flat(self.master, named)
         self.refresh_shadow()
 
+    def _scatter_full(self, name, t, cols=None):
+        """ZeRO-1: place a full fp32 parameter tensor: bf16 copy (full) + the part of it inside this rank's slice."""
+        off, shape = self.layout.entries[name]
+        dst16 = self.layout.view(self.shadow, name)
+        if cols is not None:
+            dst16 = dst16[:, :cols] if dst16.dim() == 2 else dst16[:cols]
+        dst16.copy_(t)
+        full = torch.zeros(shape, dtype=F32, device=self.device)
+        (full[:, :cols] if (cols is not None and full.dim() == 2) else (full[:cols] if cols is not None else full)).copy_(t)
+        lo, hi = self.shard
+        n = full.numel()
+        a, b = max(lo, off), min(hi, off + n)
+        if a < b:
+            self.master[a - lo:b - lo].copy_(full.view(-1)[a - off:b - off])
+
+    def _refresh_vecs(self):
+        ops.gather_cast(self.shadow, self.vec32, self._vec_table, self._vec_table.numel() // 3)
+
     def load_flat(self, flat, named):
         """Fill one of the flat fp32 buffers (master | adam_m | adam_v) from a dict of reference-named tensors."""
         dev = self.device
+        if self.zero is not None:
+            if flat is not self.master:
+                raise L.DB200Error("ZeRO-1 mode: loading sharded Adam slots is not implemented (throughput configuration)")
+            self.master.zero_(); self.shadow.zero_()
+            f32 = lambda x: x.to(device=dev, dtype=F32)
+            self._scatter_full("wte", f32(named["embedding/wte"]))
+            self._scatter_full("wpe", f32(named["positional_embedding/wpe"]))
+            for i in range(self.L):
+                p = f"l{i}."
+                for k, rn in self._ref_names(i).items():
+                    self._scatter_full(p + k, f32(named[rn]))
+                pre = f"layer_{i}/attn/"
+                self._scatter_full(p + "wqkv", torch.cat([f32(named[pre + "q"]), f32(named[pre + "k"]),
+                                                          f32(named[pre + "v"])], dim=1))
+            self._scatter_full("lnf_g", f32(named["to_logits/layer_norm/g"]))
+            self._scatter_full("lnf_b", f32(named["to_logits/layer_norm/b"]))
+            self._scatter_full("wout", f32(named["to_logits/linear_out/kernel"]), cols=self.V)
+            self._scatter_full("bout", f32(named["to_logits/linear_out/bias"]), cols=self.V)
+            self._refresh_vecs()
+            return
         flat.zero_()
         view = lambda n: self.layout.view(flat, n)
 
@@ -182,7 +258,13 @@ class DalleEngine:
         view("bout")[:self.V].copy_(named["to_logits/linear_out/bias"].to(device=dev, dtype=F32))
 
     def export_params(self, source=None):
-        """Inverse of load_params: dict of reference-named fp32 CPU tensors (source: master | grads | adam_m | adam_v)."""
+        """Inverse of load_params: dict of reference-named fp32 CPU tensors (source: master | grads | adam_m | adam_v).
+        ZeRO-1: parameters are exported from the full bf16 copy (the reference checkpoints bf16 "master" values under
+        bf_16 too, src/dalle_mtf/ops.py:79-80); the sharded Adam slots cannot be exported from one rank."""
+        if self.zero is not None and (source is None or source is self.master):
+            source = self.shadow
+        elif self.zero is not None and source is not self.grads:
+            raise L.DB200Error("ZeRO-1 mode: the Adam slots are sharded across ranks")
         flat = self.master if source is None else source
         view = lambda n: self.layout.view(flat, n).detach().float().cpu().clone()
         out = {"embedding/wte": view("wte"), "positional_embedding/wpe": view("wpe")}
@@ -204,6 +286,8 @@ class DalleEngine:
         """Reference initialisers, drawn on the device; identical on every rank for a seed."""
         g = torch.Generator(device=self.device).manual_seed(seed)
         d, H, dh, Lyr = self.d, self.H, self.dh, self.L
+        if self.zero is not None:
+            return self._init_params_sharded(g)
         self.master.zero_()
 
         def normal(name, std, cols=None):
@@ -226,7 +310,29 @@ class DalleEngine:
         normal("wout", 0.02, cols=self.V)
         self.refresh_shadow()
 
+    def _init_params_sharded(self, g):
+        """Same initialisers and the same random stream as init_params, one tensor at a time (ZeRO-1: no full fp32 buffer)."""
+        d, H, dh, Lyr = self.d, self.H, self.dh, self.L
+        self.master.zero_(); self.shadow.zero_()
+        rn = lambda shape, std: torch.randn(shape, generator=g, device=self.device, dtype=F32) * std
+        ones = lambda n: torch.ones(n, dtype=F32, device=self.device)
+        self._scatter_full("wte", rn((self.V, d), 0.02)); self._scatter_full("wpe", rn((self.S, d), 0.01))
+        for i in range(Lyr):
+            p = f"l{i}."
+            self._scatter_full(p + "ln1_g", ones(d)); self._scatter_full(p + "ln2_g", ones(d))
+            wq = torch.randn(d, d, generator=g, device=self.device) * (d ** -0.5 * dh ** -0.5)
+            wkv = torch.randn(d, 2 * d, generator=g, device=self.device) * (d ** -0.5)
+            self._scatter_full(p + "wqkv", torch.cat([wq, wkv], dim=1))
+            self._scatter_full(p + "wo", rn((d, d), (H * dh) ** -0.5))
+            self._scatter_full(p + "w1", rn((d, 4 * d), 0.02))
+            self._scatter_full(p + "w2", rn((4 * d, d), 0.02 / math.sqrt(Lyr)))
+        self._scatter_full("lnf_g", ones(d))
+        self._scatter_full("wout", rn((d, self.V), 0.02), cols=self.V)
+        self._refresh_vecs()
+
     def refresh_shadow(self):
+        if self.zero is not None:
+            return self._refresh_vecs()
         ops.cast_f32_to_bf16(self.master[:self.n_params_padded], self.shadow[:self.n_params_padded])
 
     # ------------------------------------------------------------------------------------------ buffers
@@ -397,10 +503,21 @@ class DalleEngine:
         n = self.n_params_padded
         if clip and clip > 0:
             self.gnorm_sq.zero_()
-            ops.sqnorm(self.grads[:n], self.gnorm_sq)
+            ops.sqnorm(self.grads[:n], self.gnorm_sq)       # the reduced gradient is identical on every rank
             gn = self.gnorm_sq
         else:
             gn, clip = None, 0.0
+        if self.zero is not None:
+            if weight_decay:
+                raise L.DB200Error("ZeRO-1 mode: weight_decay != 0 is not wired (no reference config uses it)")
+            lo, hi = self.shard
+            m = hi - lo
+            if m > 0:   # this rank's slice: fp32 master + Adam slots, bf16 result written into the full copy
+                ops.adam_step(self.master[:m], self.adam_m[:m], self.adam_v[:m], self.grads[lo:hi], self.shadow[lo:hi],
+                              lr, beta1, beta2, eps, 0.0, gn, clip, 1.0, False, 0)
+            self.zero.all_gather_inplace(self.shadow, self.chunk)   # bf16 parameters of every slice
+            self._refresh_vecs()
+            return
         if not weight_decay:
             ops.adam_step(self.master[:n], self.adam_m[:n], self.adam_v[:n], self.grads[:n], self.shadow[:n], lr,
                           beta1, beta2, eps, 0.0, gn, clip, 1.0, False, 0)

@@ -125,6 +125,22 @@ class DataParallel:
             self.wait()
         return t
 
+    def all_gather_inplace(self, buf, count_per_rank):
+        """In-place all-gather of equal slices: rank r's data is buf[r*count : (r+1)*count] (ZeRO-1 parameter refresh);
+        the current stream waits for it."""
+        if not self.enabled:
+            return buf
+        mine = buf[self.rank * count_per_rank:(self.rank + 1) * count_per_rank]
+        if self.comm is not None:
+            from . import lib as L
+            dt = {torch.float32: 0, torch.bfloat16: 1}[buf.dtype]
+            L.check(L.load().db200_bucket_all_gather_launch(self.comm, L.stream_ptr(), mine.data_ptr(), buf.data_ptr(),
+                                                            count_per_rank, dt), "bucket_all_gather_launch")
+            self.wait()
+        else:
+            dist.all_gather_into_tensor(buf[:self.world * count_per_rank], mine.clone())
+        return buf
+
     def wait(self):
         """Make the current stream wait for every outstanding bucket (on the device; no host block with NCCL)."""
         if self.comm is not None:

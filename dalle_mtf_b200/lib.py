@@ -86,6 +86,8 @@ _SIGNATURES = {
     "db200_gumbel_softmax_bwd": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_f32],
     "db200_argmax_rows_f32": [c_vp, c_vp, c_vp, c_int, c_int],
     "db200_mse_fwd_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_f32],
+    "db200_gather_cast_bf16_f32": [c_vp, c_vp, c_vp, c_vp, c_int],
+    "db200_space_to_depth_f32": [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int],
     "db200_comm_load_nccl": [ctypes.c_char_p],
     "db200_comm_unique_id": [c_vp, c_sz],
     "db200_comm_create": [c_int, c_int, c_int, c_vp, c_int, ctypes.POINTER(c_vp)],

@@ -103,7 +103,10 @@ def dalle_model_fn(features, labels, mode, params):
     model = DalleEngine(n_embd=params["n_embd"], n_layers=params["n_layers"], n_heads=params["n_heads"],
                         text_vocab_size=params["text_vocab_size"], image_vocab_size=params["image_vocab_size"],
                         text_seq_len=params["text_seq_len"], image_seq_len=image_seq_len, device=device,
-                        recompute_grad=bool(params.get("recompute_grad")) and mode == TRAIN)   # models.py:342
+                        recompute_grad=bool(params.get("recompute_grad")) and mode == TRAIN,   # models.py:342
+                        # B200 extension key: shard fp32 master + Adam slots across the data-parallel ranks (ZeRO-1) —
+                        # what lets the 12 B configuration (README.md:5) fit 180 GB GPUs in pure data parallelism
+                        zero=dp if (params.get("optimizer_state_sharding") and dp.enabled) else None)
     if params["bf_16"] is False and dp.rank == 0:
         print("note: bf_16=false — the B200 engine still runs activations and matmul operands in bf16 with fp32 "
               "accumulation, fp32 master weights / optimiser state (there is no fp32 tensor-core path yet)")
@@ -130,7 +133,7 @@ def dalle_model_fn(features, labels, mode, params):
     spec = StepSpec(mode, model, dp=dp, extra={"vae": vae})
 
     def assemble(features, labels):
-        img = _to_device(features, torch.float32, device).view(local_batch, vae.H, vae.W, vae.C)
+        img = _to_device(features, torch.float32, device).view(local_batch, vae.img_H, vae.img_W, vae.img_C)
         text = _to_device(labels, torch.int32, device).view(local_batch, params["text_seq_len"])
         img_ids = vae.encode_tokens(img)                                        # model_fns.py:72-77
         ops.assemble_tokens(text, img_ids, tokens, model.text_vocab_size)       # model_fns.py:117-122
@@ -171,6 +174,9 @@ def dalle_model_fn(features, labels, mode, params):
 
     def state_fn():
         st = {k: v for k, v in model.export_params().items()}
+        if model.zero is not None:      # sharded Adam slots are not gathered into rank 0's checkpoint (throughput config)
+            st["global_step"] = spec.global_step
+            return st
         st.update({k + "/adam_m": v for k, v in model.export_params(model.adam_m).items()})   # optimizers.py:139
         st.update({k + "/adam_v": v for k, v in model.export_params(model.adam_v).items()})   # optimizers.py:147
         st["global_step"] = spec.global_step
@@ -222,6 +228,9 @@ def vae_model_fn(features, labels, mode, params):
     model.init_params(seed=params.get("seed") or 0)
     if dp.rank == 0:
         print_n_params(model.n_params())
+        if params.get("recompute_grad"):
+            print("note: recompute_grad=true (src/vae_tf/models.py:8-43) — the B200 engine keeps the residual-pair "
+                  "activations instead of recomputing them (they fit in HBM many times over); gradients are identical")
     tg = params.get("train_gumbel_hard")
     eg = params.get("eval_gumbel_hard")
     train_gumbel = True if tg is None else tg                                 # model_fns_tf.py:32
@@ -231,7 +240,7 @@ def vae_model_fn(features, labels, mode, params):
     noise = torch.empty(rows, model.K, dtype=torch.float32, device=device)
     gen = torch.Generator(device=device).manual_seed(1234 + dp.rank)
     spec = StepSpec(mode, model, dp=dp)
-    n_global = global_batch * H * H * model.C
+    n_global = global_batch * H * H * model.img_C
 
     def draw_noise():
         # tf.random_uniform(minval=1e-9, maxval=1.) (src/vae_tf/layers.py:8-13); RNG stream is ours
@@ -239,7 +248,7 @@ def vae_model_fn(features, labels, mode, params):
         return noise
 
     def run(features, train):
-        img = _to_device(features, torch.float32, device).view(local_batch, H, H, model.C)
+        img = _to_device(features, torch.float32, device).view(local_batch, H, H, model.img_C)
         temp = vae_temperature(spec.global_step, params)
         u = params.get("_gumbel_u")
         u = draw_noise() if u is None else u
@@ -249,10 +258,10 @@ def vae_model_fn(features, labels, mode, params):
 
     def train_op(features, labels=None):
         run(features, True)
-        model.backward()
-        if dp.enabled:
-            # CrossShardOptimizer: cross-replica MEAN of the gradients (model_fns_tf.py:61) = SUM then 1/N in Adam
-            dp.all_reduce_now(model.grads)
+        # CrossShardOptimizer: cross-replica MEAN of the gradients (model_fns_tf.py:61) = bucketed SUM all-reduce that
+        # overlaps with the rest of backward (decoder, codebook, encoder ranges), then 1/N inside the Adam kernel
+        model.backward(on_bucket_ready=dp.make_bucket_hook(model.grads))
+        dp.wait()
         spec.global_step += 1
         model.optimizer_step(params["lr"], spec.global_step, grad_scale=1.0 / dp.world)   # model_fns_tf.py:58-60
         spec.loss_sum = model.grads[model.aux_off:model.aux_off + 1]

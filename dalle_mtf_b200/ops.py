@@ -272,6 +272,22 @@ def conv_desc(N, H, W, Cin, Cout, KH, KW, stride, transposed=False, act_f32=True
     return c
 
 
+def gather_cast(src_bf16, dst_f32, table_dev, n_segments):
+    L.require_device()
+    check(L.load().db200_gather_cast_bf16_f32(stream_ptr(), ptr(src_bf16), ptr(dst_f32), ptr(table_dev), n_segments),
+          "gather_cast")
+
+
+def space_to_depth(x, out, s, inverse=False):
+    """tf.space_to_depth / depth_to_space on f32 NHWC.  `x` is the flat image [N,H,W,C] (inverse: the deep one)."""
+    L.require_device()
+    flat = out if inverse else x
+    N, H, W, C = flat.shape
+    check(L.load().db200_space_to_depth_f32(stream_ptr(), ptr(x), ptr(out), N, H, W, C, int(s), int(inverse)),
+          "space_to_depth")
+    return out
+
+
 def conv2d_fwd(c, x, w, bias, residual, y):
     L.require_device()
     check(L.load().db200_conv2d_fwd(stream_ptr(), ctypes.byref(c), ptr(x), ptr(w), ptr(bias), ptr(residual),

@@ -23,14 +23,24 @@ class VaeEngine:
                  stack_factor=1, device="cuda"):
         L.require_device()
         assert math.log2(stack_factor).is_integer()                      # src/vae_tf/models.py:78
-        if stack_factor != 1:
-            raise L.DB200Error("stack_factor > 1 (space_to_depth) is not wired in the B200 engine yet")
         self.K = int(num_tokens)
-        self.H = self.W = int(image_size)
+        # stack_factor (src/vae_tf/models.py:85-86, 155-161): the image is space_to_depth'ed on the way in and the
+        # reconstruction depth_to_space'd on the way out; everything in between (and the MSE, which is a mean over the
+        # same elements) works on the packed [H/s, W/s, C*s*s] tensor.  img_* = what callers see, H/W/C = packed.
+        self.stack_factor = int(stack_factor)
+        self.img_H = self.img_W = int(image_size)
+        self.img_C = int(input_channels)
+        if self.img_H % self.stack_factor != 0:
+            raise L.DB200Error("image_size must be divisible by stack_factor")
+        self.H = self.W = self.img_H // self.stack_factor
         self.convblocks = [(int(s), int(c)) for s, c in convblocks]
-        self.C = int(input_channels)
+        self.C = self.img_C * self.stack_factor ** 2
         self.use_bf16 = bool(use_bf16)
-        self.recompute_grad = bool(recompute_grad)  # accepted; activations are simply kept (they fit in 180 GB)
+        # src/vae_tf/models.py:8-43 re-runs every residual pair inside backward to save activation memory.  Here the
+        # activations are simply kept: at vae_coco (256 px, 16 images per GPU, bf16) they take ~6 GB of the 180 GB, and
+        # recomputing would add a forward pass of FLOPs for nothing.  Gradients are identical either way (the
+        # recomputation is deterministic), so the flag only changes memory, never numbers; model_fns says so at start-up.
+        self.recompute_grad = bool(recompute_grad)
         self.device = torch.device(device)
         self.act = BF16 if self.use_bf16 else F32
         if self.H % (2 ** len(self.convblocks)) != 0:
@@ -69,6 +79,7 @@ class VaeEngine:
                     self.dec.append(("res", pre, ch, ch, res))
             cin = ch
         lay.add("decoder/conv2d/kernel", (1, 1, cin, self.C)); lay.add("decoder/conv2d/bias", (self.C,))
+        self._first_dec = next(n for n in lay.order if n.startswith("decoder/"))
         self.dec_out_cin = cin
         self.layout = lay
         n = lay.size + 64
@@ -206,6 +217,9 @@ class VaeEngine:
             "dy": e(rows, self.K, dtype=F32), "dlogits": e(rows, self.K, dtype=F32),
             "dz_f32": e(rows, self.n_hid, dtype=F32), "denc_f32": e(rows, self.n_hid, dtype=F32),
         })
+        if self.stack_factor > 1:
+            b["img_packed"] = e(B, self.H, self.W, self.C, dtype=F32)
+            b["recon_flat"] = e(B, self.img_H, self.img_W, self.img_C, dtype=F32)
         # gradient scratch: two buffers per distinct activation shape
         shapes = {}
         for lst in (b["enc"], b["dec"]):
@@ -243,6 +257,7 @@ class VaeEngine:
         B = img.shape[0]
         self._alloc(B)
         b = self._b
+        img = self._pack(img)
         # bf16 inference path: the first layer reads the fp32 image directly (dedicated kernel, cast fused)
         first_direct = (self.use_bf16 and not for_training and self.C == 3 and self.enc[0][0] == "down" and
                         self.enc[0][3] % 64 == 0 and self.H % 2 == 0)
@@ -292,6 +307,19 @@ class VaeEngine:
                        self.P("decoder/conv2d/bias"), None, b["recon_act"])                   # models.py:155
         return self._to_f32(b["recon_act"], b["recon"])
 
+    def _pack(self, img):
+        """space_to_depth of the caller's image (no-op for stack_factor 1)."""
+        if self.stack_factor == 1:
+            return img
+        return ops.space_to_depth(img.view(-1, self.img_H, self.img_W, self.img_C), self._b["img_packed"],
+                                  self.stack_factor)
+
+    def _unpack(self, recon):
+        """depth_to_space of the packed reconstruction for the caller (no-op for stack_factor 1)."""
+        if self.stack_factor == 1:
+            return recon
+        return ops.space_to_depth(recon, self._b["recon_flat"], self.stack_factor, inverse=True)
+
     def _codebook_lookup(self, B):
         """z = y @ codebook^T for b["y_out"] (src/vae_tf/models.py:127, tied weight)."""
         b = self._b
@@ -312,7 +340,7 @@ class VaeEngine:
         rows = B * self.hw * self.hw
         ops.onehot_rows(idx.reshape(rows).contiguous(), self._b["y_out"], offset)
         self._codebook_lookup(B)
-        return self._decode_from_z(B)
+        return self._unpack(self._decode_from_z(B))
 
     def forward(self, img, u, temperature=1.0, hard=True, loss_accum=None):
         """DiscreteVAE.forward(return_recon_loss=True) (src/vae_tf/models.py:165-184).  u: fp32 uniform noise
@@ -330,8 +358,9 @@ class VaeEngine:
             loss_accum = self.grads[self.aux_off:self.aux_off + 1]
         n = img.numel()
         self._loss_scale = 1.0 / n
-        ops.mse_fwd_bwd(recon, img, b["drecon"], loss_accum, 1.0 / n)                          # layers.py:24-25
-        return recon
+        packed = self._b["img_packed"] if self.stack_factor > 1 else img   # written by encode_logits
+        ops.mse_fwd_bwd(recon, packed, b["drecon"], loss_accum, 1.0 / n)                       # layers.py:24-25
+        return self._unpack(recon)
 
     # ------------------------------------------------------------------------------------------ backward
     def _res_bwd(self, B, pre, ch, res, x_in, sv, dx, scratch):
@@ -345,8 +374,11 @@ class VaeEngine:
         self._conv_dgrad(d_out, dt, pre + "conv_in", None, dx, dx)
         return dx
 
-    def backward(self, grad_scale=1.0):
-        """Back-propagates d(loss) * grad_scale; gradients ACCUMULATE into self.grads."""
+    def backward(self, grad_scale=1.0, on_bucket_ready=None):
+        """Back-propagates d(loss) * grad_scale; gradients ACCUMULATE into self.grads.
+        on_bucket_ready(start, end) is called as soon as the flat range [start, end) is final (data-parallel hook):
+        decoder (+ the aux loss slot) first, then the codebook, then the encoder — the flat buffer is in forward
+        order, so backward completes it from the tail and each range is reduced while the rest still runs."""
         b = self._b
         B = self._img.shape[0]
         rows = B * self.hw * self.hw
@@ -371,6 +403,10 @@ class VaeEngine:
                 pair = b["gscratch"][tuple(x_in.shape)]
                 scratch = pair[1] if dx is pair[0] else pair[0]
                 dx = self._res_bwd(B, name, ch, res, x_in, sv, dx, scratch)
+        if on_bucket_ready:
+            s0, _ = self.layout.span(self._first_dec, self._first_dec)
+            _, e0 = self.layout.span("decoder/conv2d/bias", "decoder/conv2d/bias")
+            on_bucket_ready(s0, e0 + 64)      # + the aux scalars (loss) behind the last parameter
         # quantiser
         cb = self.P("codebook/codebook")
         gcb = self.G("codebook/codebook")
@@ -391,6 +427,8 @@ class VaeEngine:
             ops.gumbel_softmax_bwd(b["y_soft"], b["dy"], b["dlogits"], rows, self.K, self._tau)   # straight-through
             ops.rowmatmul_tn(self._enc_f32, b["dlogits"], gcb, rows, self.n_hid, self.K)
             ops.rowmatmul(b["dlogits"], cb, b["denc_f32"], rows, self.K, self.n_hid, b_transposed=True)
+        if on_bucket_ready:
+            on_bucket_ready(*self.layout.span("codebook/codebook", "codebook/codebook"))
         dx = self._to_act(b["denc_f32"], pair[0].view(rows, self.n_hid)).view(B, self.hw, self.hw, self.n_hid)
         if not self.use_bf16:
             dx = b["denc_f32"].view(B, self.hw, self.hw, self.n_hid)
@@ -411,6 +449,10 @@ class VaeEngine:
                     dx = pair[0]
                 scratch = pair[1] if dx is pair[0] else pair[0]
                 dx = self._res_bwd(B, name, ch, res, x_in, sv, dx, scratch)
+        if on_bucket_ready:
+            s0, _ = self.layout.span(self.layout.order[0], self.layout.order[0])
+            e0, _ = self.layout.span("codebook/codebook", "codebook/codebook")
+            on_bucket_ready(s0, e0)
 
     # ------------------------------------------------------------------------------------------ optimiser
     def zero_grads(self):

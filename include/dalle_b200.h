@@ -268,6 +268,19 @@ int db200_sample_rows(db200_stream_t stream, const float* logits, const float* u
                       long long ld, int lo, int hi, float inv_temp);
 int db200_onehot_rows_f32(db200_stream_t stream, const int32_t* idx, float* y, int rows, int K, int offset);
 
+/* Segmented bf16 -> f32 gather (one launch): segment i copies table[3i+2] elements from src + table[3i] to
+ * dst + table[3i+1]; `table_dev` is an int64 array in device memory.  ZeRO-1 mode: rebuilds the compact fp32 copy of the
+ * vector parameters (LayerNorm g/b, biases) from the all-gathered bf16 parameters (mtf casts every variable to the
+ * activation dtype when it is used, src/dalle_mtf/ops.py:76-82). */
+int db200_gather_cast_bf16_f32(db200_stream_t stream, const void* src_bf16, float* dst, const int64_t* table_dev,
+                               int n_segments);
+
+/* tf.space_to_depth (inverse = 0) / tf.depth_to_space (inverse = 1), f32 NHWC, block size s: the `stack_factor`
+ * re-packing of the VAE's input and output (src/vae_tf/models.py:85-86, 155-161).  H, W, C describe the FLAT image:
+ * deep[n, y, x, (dy*s + dx)*C + c] = flat[n, y*s + dy, x*s + dx, c]. */
+int db200_space_to_depth_f32(db200_stream_t stream, const float* in, float* out, int N, int H, int W, int C, int s,
+                             int inverse);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * D1  data-parallel collectives: hand-driven NCCL over NVLink / NVSwitch behind the C ABI.
  *     Replaces the all-reduce mesh-tensorflow inserts for every weight gradient when it lowers the graph

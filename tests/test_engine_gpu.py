@@ -371,3 +371,37 @@ def test_full_size_step_is_finite_and_starts_near_log_vocab():
     for _ in range(3):
         eng.zero_grads(); acc = eng.forward(tok); eng.backward(1.0 / tok.numel()); eng.optimizer_step(1e-3)
     assert acc.item() / tok.numel() < loss0
+
+
+def test_vae_stack_factor_2_matches_oracle():
+    """stack_factor > 1 (src/vae_tf/models.py:85-86, 155-161): space_to_depth on the way in, depth_to_space on the way
+    out, image_seq_len divided by stack_factor^2 (src/model_fns.py:68); fp32 mode, loss / logits / tokens / gradients."""
+    from dalle_mtf_b200.vae_engine import VaeEngine
+    from oracle import vae as OV
+    cb, K, size, B, sf = [[2, 32], [2, 64]], 64, 32, 3, 2
+    g = torch.Generator().manual_seed(5)
+    p = OV.init_params(cb, K, stack_factor=sf, seed=9)
+    for k in p:
+        if k.endswith("/bias"):
+            p[k] = torch.randn(p[k].shape, generator=g) * 0.05
+    img = torch.rand(B, size, size, 3, generator=g) * 2 - 1
+    hw = size // sf // 4
+    u = torch.rand(B * hw * hw, K, generator=g).clamp_(1e-9, 1.0)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    loss, out, logits = OV.forward(leaves, img, u.view(B, hw, hw, K), cb, 1.0, True, stack_factor=sf)
+    loss.backward()
+    eng = VaeEngine(K, size, cb, stack_factor=sf)
+    assert eng.image_seq_len == OV.image_seq_len(size, cb, sf) == hw * hw
+    eng.load_params(p)
+    eng.zero_grads()
+    acc = torch.zeros(1, device=DEV)
+    recon = eng.forward(img.to(DEV), u.to(DEV), 1.0, True, loss_accum=acc)
+    eng.backward()
+    torch.cuda.synchronize()
+    assert tuple(recon.shape) == (B, size, size, 3)
+    assert relfro(eng._b["logits"], logits.reshape(-1, K)) < 1e-4
+    assert relfro(recon, out) < 1e-4 and relfro(acc, loss.reshape(1)) < 1e-4
+    assert torch.equal(eng.encode_tokens(img.to(DEV)).cpu().long(), OV.encode_tokens(p, img, cb, stack_factor=sf))
+    eg = eng.export_params(eng.grads)
+    for k in p:
+        assert relfro(eg[k], leaves[k].grad) < 5e-3, k

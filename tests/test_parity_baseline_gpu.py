@@ -284,3 +284,9 @@ def test_optimizer_options_weight_decay_exclusions_and_null_clipping(hp_extra):
         k = "layer_0/attn/q"
         assert relfro(nodecay[k] - params[k], newp[k] - params[k]) > 1e-3
         assert torch.equal(nodecay["layer_0/norm_1/g"], newp["layer_0/norm_1/g"])
+
+
+def test_dalle_12b_width_single_layer_matches_oracle():
+    """X1 geometry (BASELINE.json configs[4]: n_embd 4096, 32 heads of 128): one layer at tiny B / S — exercises the
+    d = 4096 LayerNorm kernels, K = 4096 / N = 16384 GEMM shapes and the 32-head attention against the oracle."""
+    _dalle_parity("12B-width d4096 L1 H32 S320 V3571 B1", 4096, 1, 32, 3000, 570, 64, 256, 1, True, seed=13)
