@@ -41,8 +41,46 @@ static encode_tiled_fn get_encode_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs a microsecond or two of host time per call and every GEMM / conv / attention launch
+// needs two to four maps.  A map depends only on (base pointer, geometry), and the engines launch the same kernels on
+// the same pre-allocated buffers every step, so encoded maps are cached (per thread; dropped wholesale when full).
+struct TmapKey {
+  uint64_t v[16];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapEntry {
+  TmapKey key;
+  CUtensorMap map;
+  bool used = false;
+};
+static constexpr int TMAP_CACHE = 2048;  // power of two
+
+static int make_tmap_bf16_uncached(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                   const uint64_t* strides_bytes, const uint32_t* box);
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
+  static thread_local TmapEntry* cache = new TmapEntry[TMAP_CACHE];
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.v[0] = reinterpret_cast<uint64_t>(base);
+  k.v[1] = (uint64_t)rank;
+  for (int i = 0; i < rank && i < 5; ++i) { k.v[2 + i] = dims[i]; k.v[11 + i] = box[i]; }
+  for (int i = 0; i + 1 < rank && i < 4; ++i) k.v[7 + i] = strides_bytes[i];
+  uint64_t h = 1469598103934665603ull;
+  for (int i = 0; i < 16; ++i) { h ^= k.v[i]; h *= 1099511628211ull; }
+  TmapEntry& e = cache[(h ^ (h >> 29)) & (TMAP_CACHE - 1)];
+  if (e.used && e.key == k) {
+    *out = e.map;
+    return DB200_OK;
+  }
+  const int rc = make_tmap_bf16_uncached(out, base, rank, dims, strides_bytes, box);
+  if (rc == DB200_OK) { e.key = k; e.map = *out; e.used = true; }
+  return rc;
+}
+
+static int make_tmap_bf16_uncached(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                   const uint64_t* strides_bytes, const uint32_t* box) {
   encode_tiled_fn fn = get_encode_fn();
   if (!fn) return set_error(DB200_E_CUDA, "cuTensorMapEncodeTiled driver entry point not available");
   if (!aligned16(base)) return set_error(DB200_E_ALIGN, "TMA base pointer %p is not 16-byte aligned", base);

@@ -681,6 +681,10 @@ extern "C" int db200_rowmatmul_tn_f32(db200_stream_t stream_, const float* a, co
   return launch_wgrad(stream, p, true);
 }
 
+namespace db200 {
+int conv_first_tc_launch(cudaStream_t stream, const float* x, const float* w, const float* bias, void* y_bf16, int N,
+                         int H, int W, int Cout);
+}
 // y (bf16 NHWC) = conv4x4/s2/SAME(x fp32 NHWC [N][H][W][3], w f32 [4][4][3][Cout]) + bias.   Cout % 64 == 0.
 extern "C" int db200_conv2d_first_fwd(db200_stream_t stream_, const float* x, const float* w, const float* bias,
                                       void* y_bf16, int N, int H, int W, int Cout) {
@@ -689,15 +693,21 @@ extern "C" int db200_conv2d_first_fwd(db200_stream_t stream_, const float* x, co
   DB200_REQUIRE(H % 2 == 0 && W % 2 == 0 && Cout % 64 == 0 && Cout <= 256, DB200_E_UNSUPPORTED,
                 "conv2d_first_fwd: needs even H, W and Cout in {64,128,192,256}");
   DB200_REQUIRE(aligned16(w) && aligned16(y_bf16), DB200_E_ALIGN, "conv2d_first_fwd: unaligned pointer");
+  return conv_first_tc_launch(stream, x, w, bias, y_bf16, N, H, W, Cout);  // tcgen05 (conv_first_tc.cu)
+}
+
+// CUDA-core version of the first layer (fp32 FMA; kept for A/B measurements: FMA-bound at ~5x the tensor-core kernel)
+extern "C" int db200_conv2d_first_fwd_fma(db200_stream_t stream_, const float* x, const float* w, const float* bias,
+                                          void* y_bf16, int N, int H, int W, int Cout) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(x && w && y_bf16 && N > 0 && H % 2 == 0 && W % 2 == 0 && Cout % 64 == 0 && Cout <= 256,
+                DB200_E_INVALID, "conv2d_first_fwd_fma: bad arguments");
   const int Ho = H / 2, Wo = W / 2;
   const int tiles = ((Wo + CF_TW - 1) / CF_TW) * ((Ho + CF_TH - 1) / CF_TH) * N;
   const size_t smem = (size_t)(48 * Cout + (2 * CF_TH + 2) * (2 * CF_TW + 2) * 3) * sizeof(float);
   if (smem > 48 * 1024) {
-    static bool attr = false;
-    if (!attr) {
-      DB200_CUDA(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      attr = true;
-    }
+    static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);  // once, thread-safe
+    DB200_CUDA(attr_rc);
   }
   conv_first_kernel<<<tiles, 128, smem, stream>>>(x, w, bias, reinterpret_cast<bf16*>(y_bf16), N, H, W, Cout);
   return check_launch("conv_first_kernel");

@@ -270,12 +270,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 template <int BN>
 static int conv_tc_launch(cudaStream_t stream, const CUtensorMap* tmA, const CUtensorMap& tmB, const ConvTcParams& p) {
   using Cfg = ConvTcCfg<BN>;
-  static bool attr = false;
-  if (!attr) {
-    DB200_CUDA(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)Cfg::SMEM_BYTES));
-    attr = true;
-  }
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);  // once, thread-safe
+  DB200_CUDA(attr_rc);
   const int total = p.tiles_n * p.tiles_h * p.tiles_w * p.tiles_c;
   const int grid = total < sm_count() ? total : sm_count();
   conv_tc_kernel<BN><<<grid, CT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA[0], tmA[1], tmA[2], tmA[3], tmB, p);
@@ -514,12 +510,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_cons
 template <int BN>
 static int wgrad_tc_launch(cudaStream_t stream, const CUtensorMap* tmP, const CUtensorMap* tmQ, const WgradTcParams& p) {
   using Cfg = WgradCfg<BN>;
-  static bool attr = false;
-  if (!attr) {
-    DB200_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)Cfg::SMEM_BYTES));
-    attr = true;
-  }
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(conv_wgrad_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);  // once, thread-safe
+  DB200_CUDA(attr_rc);
   const int grid = p.b_tiles * p.a_tiles * p.ntaps * p.splits;
   conv_wgrad_tc_kernel<BN><<<grid, CT_THREADS, Cfg::SMEM_BYTES, stream>>>(tmP[0], tmP[1], tmP[2], tmP[3], tmQ[0],
                                                                           tmQ[1], tmQ[2], tmQ[3], p);

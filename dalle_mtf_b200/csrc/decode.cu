@@ -13,10 +13,14 @@
 
 namespace db200 {
 
+// pos_dev != NULL: the position is read from device memory (CUDA-graph replay: one captured step serves every position)
+// and the token of row b is ids[b * ld_ids + pos] (the [B][S] token matrix itself); else ids[b * ld_ids] at `pos`.
 __global__ void embed_at_kernel(const int* __restrict__ ids, const bf16* __restrict__ wte, const bf16* __restrict__ wpe,
-                                bf16* __restrict__ out, int d, int V, int pos) {
+                                bf16* __restrict__ out, int d, int V, int pos, const int* __restrict__ pos_dev,
+                                long long ld_ids) {
   const int b = blockIdx.x;
-  int id = ids[b];
+  if (pos_dev) pos = *pos_dev;
+  int id = ids[b * ld_ids + (pos_dev ? pos : 0)];
   id = id < 0 ? 0 : (id >= V ? V - 1 : id);
   const bf16* w = wte + (long long)id * d;
   const bf16* p = wpe + (long long)pos * d;
@@ -28,8 +32,9 @@ __global__ void embed_at_kernel(const int* __restrict__ ids, const bf16* __restr
 template <int DH>
 __global__ void __launch_bounds__(128)
 attn_decode_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc, bf16* __restrict__ out,
-                   int S, int H, int pos, float scale) {
+                   int S, int H, int pos, float scale, const int* __restrict__ pos_dev) {
   extern __shared__ float sc[];
+  if (pos_dev) pos = *pos_dev;
   __shared__ float red[4];
   __shared__ float qs[DH];
   const int h = blockIdx.x, b = blockIdx.y;
@@ -80,7 +85,7 @@ attn_decode_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __
 
 __global__ void __launch_bounds__(256)
 sample_rows_kernel(const float* __restrict__ logits, const float* __restrict__ u, int* __restrict__ idx, long long ld,
-                   int lo, int hi, float inv_temp) {
+                   int lo, int hi, float inv_temp, const int* __restrict__ pos_dev, long long ld_idx) {
   __shared__ float bv[8];
   __shared__ int bi[8];
   const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,9 +109,13 @@ sample_rows_kernel(const float* __restrict__ logits, const float* __restrict__ u
   if (tid == 0) {
     for (int w = 1; w < 8; ++w)
       if (bv[w] > best || (bv[w] == best && bi[w] < arg)) { best = bv[w]; arg = bi[w]; }
-    idx[r] = lo + (arg == 0x7fffffff ? 0 : arg);  // all -inf / NaN row: first allowed id
+    // pos_dev != NULL (graph replay): the sample is the token of position *pos_dev + 1 of the [rows][ld_idx] matrix
+    int* dst = pos_dev ? idx + r * ld_idx + (*pos_dev + 1) : idx + r;
+    *dst = lo + (arg == 0x7fffffff ? 0 : arg);  // all -inf / NaN row: first allowed id
   }
 }
+
+__global__ void incr_i32_kernel(int* p, int delta) { *p += delta; }
 
 __global__ void onehot_rows_kernel(const int* __restrict__ idx, float* __restrict__ y, int K, int offset) {
   const int r = blockIdx.x;
@@ -125,35 +134,69 @@ extern "C" int db200_embed_fwd_at(db200_stream_t stream_, const int32_t* ids, co
   DB200_REQUIRE(B > 0 && d > 0 && V > 0 && pos >= 0 && pos < n_pos, DB200_E_INVALID,
                 "embed_fwd_at: B %d d %d V %d pos %d of %d", B, d, V, pos, n_pos);
   embed_at_kernel<<<B, 256, 0, stream>>>(ids, static_cast<const bf16*>(wte), static_cast<const bf16*>(wpe),
-                                         static_cast<bf16*>(out), d, V, pos);
+                                         static_cast<bf16*>(out), d, V, pos, nullptr, 1);
   return check_launch("embed_at_kernel");
 }
 
-extern "C" int db200_attn_decode(db200_stream_t stream_, const void* qkv_step, void* k_cache, void* v_cache, void* out,
-                                 int B, int S, int H, int dh, int pos, float scale) {
+// ---- device-side position variants (CUDA-graph replay of the per-position step): `pos_dev` points at one int32 in
+// device memory that the caller advances with db200_incr_i32 between replays; `tokens` is the [B][ld] token matrix.
+extern "C" int db200_embed_fwd_at_dev(db200_stream_t stream_, const int32_t* tokens, long long ld, const void* wte,
+                                      const void* wpe, void* out, int B, int d, int V, const int32_t* pos_dev) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(tokens && wte && wpe && out && pos_dev && B > 0 && d > 0 && V > 0 && ld > 0, DB200_E_INVALID,
+                "embed_fwd_at_dev: bad argument");
+  embed_at_kernel<<<B, 256, 0, stream>>>(tokens, static_cast<const bf16*>(wte), static_cast<const bf16*>(wpe),
+                                         static_cast<bf16*>(out), d, V, 0, pos_dev, ld);
+  return check_launch("embed_at_kernel");
+}
+
+extern "C" int db200_incr_i32(db200_stream_t stream_, int32_t* p, int delta) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(p, DB200_E_INVALID, "incr_i32: null pointer");
+  incr_i32_kernel<<<1, 1, 0, stream>>>(p, delta);
+  return check_launch("incr_i32_kernel");
+}
+
+// pos_dev == NULL: position `pos` (scores need pos + 1 floats of shared memory); else the position is read on the
+// device and shared memory is sized for all S keys.
+static int attn_decode_launch(cudaStream_t stream, const void* qkv_step, void* k_cache, void* v_cache, void* out, int B,
+                              int S, int H, int dh, int pos, float scale, const int32_t* pos_dev) {
   DB200_REQUIRE(qkv_step && k_cache && v_cache && out, DB200_E_INVALID, "attn_decode: null pointer");
   DB200_REQUIRE(B > 0 && H > 0 && S > 0 && pos >= 0 && pos < S, DB200_E_INVALID, "attn_decode: B %d H %d pos %d of %d",
                 B, H, pos, S);
   DB200_REQUIRE(dh == 64 || dh == 128, DB200_E_UNSUPPORTED, "attn_decode: head_dim %d not in {64,128}", dh);
-  DB200_REQUIRE((size_t)(pos + 1) * 4 <= 200 * 1024, DB200_E_UNSUPPORTED, "attn_decode: %d keys exceed shared memory",
-                pos + 1);
-  const size_t smem = (size_t)(pos + 1) * sizeof(float);
+  const size_t keys = pos_dev ? (size_t)S : (size_t)(pos + 1);
+  DB200_REQUIRE(keys * 4 <= 200 * 1024, DB200_E_UNSUPPORTED, "attn_decode: %zu keys exceed shared memory", keys);
+  const size_t smem = keys * sizeof(float);
   dim3 grid(H, B);
-  if (dh == 128) {
-    if (smem > 48 * 1024)
-      DB200_CUDA(cudaFuncSetAttribute(attn_decode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  static const cudaError_t a128 = cudaFuncSetAttribute(attn_decode_kernel<128>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  static const cudaError_t a64 = cudaFuncSetAttribute(attn_decode_kernel<64>,
+                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  DB200_CUDA(a128);
+  DB200_CUDA(a64);
+  if (dh == 128)
     attn_decode_kernel<128><<<grid, 128, smem, stream>>>(static_cast<const bf16*>(qkv_step),
                                                          static_cast<bf16*>(k_cache), static_cast<bf16*>(v_cache),
-                                                         static_cast<bf16*>(out), S, H, pos, scale);
-  } else {
-    if (smem > 48 * 1024)
-      DB200_CUDA(cudaFuncSetAttribute(attn_decode_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                                                         static_cast<bf16*>(out), S, H, pos, scale, pos_dev);
+  else
     attn_decode_kernel<64><<<grid, 128, smem, stream>>>(static_cast<const bf16*>(qkv_step), static_cast<bf16*>(k_cache),
                                                         static_cast<bf16*>(v_cache), static_cast<bf16*>(out), S, H, pos,
-                                                        scale);
-  }
+                                                        scale, pos_dev);
   return check_launch("attn_decode_kernel");
+}
+
+extern "C" int db200_attn_decode(db200_stream_t stream_, const void* qkv_step, void* k_cache, void* v_cache, void* out,
+                                 int B, int S, int H, int dh, int pos, float scale) {
+  return attn_decode_launch(static_cast<cudaStream_t>(stream_), qkv_step, k_cache, v_cache, out, B, S, H, dh, pos, scale,
+                            nullptr);
+}
+
+extern "C" int db200_attn_decode_dev(db200_stream_t stream_, const void* qkv_step, void* k_cache, void* v_cache,
+                                     void* out, int B, int S, int H, int dh, const int32_t* pos_dev, float scale) {
+  DB200_REQUIRE(pos_dev, DB200_E_INVALID, "attn_decode_dev: null position pointer");
+  return attn_decode_launch(static_cast<cudaStream_t>(stream_), qkv_step, k_cache, v_cache, out, B, S, H, dh, 0, scale,
+                            pos_dev);
 }
 
 extern "C" int db200_sample_rows(db200_stream_t stream_, const float* logits, const float* u_or_null, int32_t* idx,
@@ -163,7 +206,19 @@ extern "C" int db200_sample_rows(db200_stream_t stream_, const float* logits, co
   DB200_REQUIRE(rows > 0 && lo >= 0 && hi > lo && hi <= ld, DB200_E_INVALID, "sample_rows: rows %d range [%d,%d) ld %lld",
                 rows, lo, hi, ld);
   DB200_REQUIRE(inv_temp > 0.f, DB200_E_INVALID, "sample_rows: inv_temp must be positive");
-  sample_rows_kernel<<<rows, 256, 0, stream>>>(logits, u_or_null, idx, ld, lo, hi, inv_temp);
+  sample_rows_kernel<<<rows, 256, 0, stream>>>(logits, u_or_null, idx, ld, lo, hi, inv_temp, nullptr, 1);
+  return check_launch("sample_rows_kernel");
+}
+
+// graph-replay variant: the sample of row r becomes tokens[r * ld_tokens + *pos_dev + 1]
+extern "C" int db200_sample_rows_at(db200_stream_t stream_, const float* logits, const float* u_or_null,
+                                    int32_t* tokens, long long ld_tokens, int rows, long long ld, int lo, int hi,
+                                    float inv_temp, const int32_t* pos_dev) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  DB200_REQUIRE(logits && tokens && pos_dev, DB200_E_INVALID, "sample_rows_at: null pointer");
+  DB200_REQUIRE(rows > 0 && lo >= 0 && hi > lo && hi <= ld && inv_temp > 0.f, DB200_E_INVALID,
+                "sample_rows_at: rows %d range [%d,%d) ld %lld", rows, lo, hi, ld);
+  sample_rows_kernel<<<rows, 256, 0, stream>>>(logits, u_or_null, tokens, ld, lo, hi, inv_temp, pos_dev, ld_tokens);
   return check_launch("sample_rows_kernel");
 }
 

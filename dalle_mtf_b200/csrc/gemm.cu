@@ -206,12 +206,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN>
 static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DB200_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)Cfg::SMEM_BYTES);  // once, thread-safe (magic static)
+  DB200_CUDA(attr_rc);
   const int total = p.m_tiles * p.n_tiles * p.splits;
   const int grid = total < sm_count() ? total : sm_count();
   gemm_tc_kernel<BN><<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
@@ -220,14 +217,13 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& tmA, const CUtens
 
 int launch_gemm_2cta(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p);
 
-// 2-CTA pairs (gemm2.cu) when there are enough 256x256 tiles to fill the 74 SM pairs; DB200_GEMM_2CTA=0 disables.
+// 2-CTA pairs (gemm2.cu) when there are enough 256x256 tiles to fill the 74 SM pairs.
 static bool use_2cta(const GemmParams& p, int bn) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("DB200_GEMM_2CTA");
-    enabled = (e == nullptr) ? 1 : (atoi(e) != 0);
-  }
-  if (!enabled || bn != 256) return false;
+#ifdef DB200_DEV_KNOBS  // development builds only: DB200_GEMM_2CTA=0 disables the pair kernel for A/B timing
+  static const int enabled = [] { const char* e = getenv("DB200_GEMM_2CTA"); return (e == nullptr) ? 1 : (atoi(e) != 0); }();
+  if (!enabled) return false;
+#endif
+  if (bn != 256) return false;
   const int pair_tiles = ((p.M + 255) / 256) * p.n_tiles * p.splits;
   return pair_tiles >= sm_count() / 2;
 }
@@ -302,10 +298,12 @@ extern "C" int db200_gemm_bf16(db200_stream_t stream_, const void* A, int a_mn_m
   p.splits = splits;
   p.kb_total = kb_total;
   p.mode = mode;
-  {  // timing experiments only: skip the epilogue work (results are garbage) to expose the TMA + MMA ceiling
+#ifdef DB200_DEV_KNOBS  // development builds only (make DEV=1): never compiled into the shipped library
+  {  // timing experiments: skip the epilogue work (results are garbage) to expose the TMA + MMA ceiling
     static const bool noepi = [] { const char* e = getenv("DB200_GEMM_NOEPI"); return e && e[0] == '1'; }();
     if (noepi) p.mode = -1;
   }
+#endif
   p.out_f32 = epi->out_f32;
   p.relu = epi->relu;
   p.alpha = epi->alpha;
@@ -329,10 +327,12 @@ extern "C" int db200_gemm_bf16(db200_stream_t stream_, const void* A, int a_mn_m
   if (mode != DB200_EPI_CE_STATS && mode != DB200_EPI_CE_GRAD) {
     const int tiles256 = p.m_tiles * ((N + 255) / 256) * splits;
     if (N <= 128 || tiles256 * 2 <= sm_count()) bn = 128;
+#ifdef DB200_DEV_KNOBS
     if (const char* e = getenv("DB200_GEMM_BN")) {  // tuning knob (experiments only)
       const int v = atoi(e);
       if (v == 128 || v == 256) bn = v;
     }
+#endif
   }
   p.n_tiles = (N + bn - 1) / bn;
   p.n_parts = 2 * p.n_tiles;

@@ -273,11 +273,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 int launch_gemm_2cta(cudaStream_t stream, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    DB200_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
-    attr_set = true;
-  }
+  static const cudaError_t attr_rc = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);  // once, thread-safe (magic static)
+  DB200_CUDA(attr_rc);
   const int m_tiles2 = (p.M + 255) / 256;
   const int total = m_tiles2 * p.n_tiles * p.splits;
   int clusters = sm_count() / 2;

@@ -41,24 +41,49 @@ __global__ void embed_fwd_kernel(const int* __restrict__ ids, const bf16* __rest
   }
 }
 
-__global__ void embed_bwd_wte_kernel(const int* __restrict__ ids, const bf16* __restrict__ dx,
-                                     float* __restrict__ dwte, int T, int d, int V) {
+// dwte[ids[t]] += dx[t].  A thread owns 8 columns of a strip of EMB_STRIP consecutive tokens and merges RUNS of equal
+// ids in registers before touching memory: captions are right-padded with one id (src/input_fns.py:32-38), so the
+// ~220 consecutive padding positions of every sequence collapse into one red.add per strip instead of 220 serialised
+// reductions on the same 2 KiB row of dwte (same-address reductions serialise in L2; that run was most of this
+// kernel's time).  Different ids still go through red.global.add.v4.f32.
+constexpr int EMB_STRIP = 32;
+__global__ void __launch_bounds__(256)
+embed_bwd_wte_kernel(const int* __restrict__ ids, const bf16* __restrict__ dx, float* __restrict__ dwte, int T, int d,
+                     int V) {
   const int vec_per_row = d >> 3;
-  const long long total = (long long)T * vec_per_row;
+  const long long total = (long long)((T + EMB_STRIP - 1) / EMB_STRIP) * vec_per_row;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int t = (int)(i / vec_per_row);
-    const int c = (int)(i - (long long)t * vec_per_row) << 3;
-    int id = ids[t];
-    if (id < 0 || id >= V) continue;
-    float g[8];
-    unpack8(*reinterpret_cast<const uint4*>(dx + (long long)t * d + c), g);
-    float* dst = dwte + (long long)id * d + c;  // 32-byte aligned: two REDG.E.ADD.F32x4
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(g[0]), "f"(g[1]), "f"(g[2]), "f"(g[3])
-                 : "memory");
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(g[4]), "f"(g[5]), "f"(g[6]),
-                 "f"(g[7])
-                 : "memory");
+    const int strip = (int)(i / vec_per_row);
+    const int c = (int)(i - (long long)strip * vec_per_row) << 3;
+    const int t0 = strip * EMB_STRIP, t1 = min(T, t0 + EMB_STRIP);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int cur = -1;
+    auto flush = [&]() {
+      if (cur >= 0 && cur < V) {
+        float* dst = dwte + (long long)cur * d + c;  // 32-byte aligned: two REDG.E.ADD.F32x4
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(acc[0]), "f"(acc[1]), "f"(acc[2]),
+                     "f"(acc[3])
+                     : "memory");
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(acc[4]), "f"(acc[5]),
+                     "f"(acc[6]), "f"(acc[7])
+                     : "memory");
+      }
+    };
+    for (int t = t0; t < t1; ++t) {
+      const int id = ids[t];
+      if (id != cur) {
+        flush();
+        cur = id;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      }
+      float g[8];
+      unpack8(*reinterpret_cast<const uint4*>(dx + (long long)t * d + c), g);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += g[j];
+    }
+    flush();
   }
 }
 
@@ -531,7 +556,7 @@ extern "C" int db200_embed_bwd(db200_stream_t stream_, const int32_t* ids, const
   DB200_REQUIRE(B > 0 && S > 0 && d > 0 && V > 0 && d % 8 == 0, DB200_E_INVALID,
                 "embed_bwd: need B,S,V > 0 and d %% 8 == 0");
   DB200_REQUIRE(ids && aligned16(dx) && dwte && dwpe, DB200_E_ALIGN, "embed_bwd: NULL or unaligned pointer");
-  const long long total = (long long)B * S * (d / 8);
+  const long long total = (long long)(((long long)B * S + EMB_STRIP - 1) / EMB_STRIP) * (d / 8);
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   embed_bwd_wte_kernel<<<blocks, 256, 0, stream>>>(ids, (const bf16*)dx, dwte, B * S, d, V);
   int rc = check_launch("embed_bwd_wte_kernel");

@@ -141,6 +141,7 @@ class DalleEngine:
             self.vec32 = torch.zeros(off, dtype=F32, device=dev)
             self._vec_table = torch.tensor(table, dtype=torch.int64, device=dev)
         self.gnorm_sq = torch.zeros(1, dtype=F32, device=dev)
+        self._grads_clean = False
         self._bufs = None
         self._buf_key = None
 
@@ -478,7 +479,14 @@ class DalleEngine:
 
     # ------------------------------------------------------------------------------------------ optimiser
     def zero_grads(self):
-        self.grads.zero_()
+        """Gradients accumulate (red.add), so every step starts from zeros.  The Adam kernel writes those zeros while it
+        streams the gradient it consumes, so after an optimiser step only the 64 aux scalars (loss) need clearing; the
+        full 4 B/param memset runs only when backward ran without an optimiser step in between (tests, first step)."""
+        if self._grads_clean:
+            self.grads[self.aux_off:].zero_()
+        else:
+            self.grads.zero_()
+        self._grads_clean = False
 
     def _decay_segments(self):
         """Contiguous [start, end, decays) runs of the flat buffer: mtf's AdamWeightDecayOptimizer is built with
@@ -520,7 +528,8 @@ class DalleEngine:
             return
         if not weight_decay:
             ops.adam_step(self.master[:n], self.adam_m[:n], self.adam_v[:n], self.grads[:n], self.shadow[:n], lr,
-                          beta1, beta2, eps, 0.0, gn, clip, 1.0, False, 0)
+                          beta1, beta2, eps, 0.0, gn, clip, 1.0, False, 0, zero_grad=True)
+            self._grads_clean = True
             return
         for s, e, d in self._decay_segments():     # `update += weight_decay * param` only on the kernels / embeddings
             ops.adam_step(self.master[s:e], self.adam_m[s:e], self.adam_v[s:e], self.grads[s:e], self.shadow[s:e], lr,

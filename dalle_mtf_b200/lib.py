@@ -58,6 +58,10 @@ _SIGNATURES = {
     "db200_attn_decode": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32],
     "db200_sample_rows": [c_vp, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_f32],
     "db200_onehot_rows_f32": [c_vp, c_vp, c_vp, c_int, c_int, c_int],
+    "db200_embed_fwd_at_dev": [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp],
+    "db200_attn_decode_dev": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_f32],
+    "db200_sample_rows_at": [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_f32, c_vp],
+    "db200_incr_i32": [c_vp, c_vp, c_int],
     "db200_crc32c": [c_vp, c_u64, c_vp],
     "db200_tfrecord_masked_crc": [c_vp, c_u64, c_vp],
     "db200_tfrecord_frame": [c_vp, c_u64, c_vp],
@@ -72,12 +76,13 @@ _SIGNATURES = {
     "db200_split_f32_to_bf16x2": [c_vp, c_vp, c_vp, c_vp, c_sz],
     "db200_sqnorm_f32": [c_vp, c_vp, c_sz, c_vp],
     "db200_adam_step": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_f32, c_f32, c_f32, c_f32, c_f32, c_vp, c_f32,
-                        c_f32, c_int, c_int],
+                        c_f32, c_int, c_int, c_int],
     "db200_conv2d_fwd": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp],
     "db200_conv2d_fwd_tc": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp],
     "db200_conv2d_dgrad_tc": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp],
     "db200_conv2d_wgrad_tc": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp],
     "db200_conv2d_first_fwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int],
+    "db200_conv2d_first_fwd_fma": [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int],
     "db200_conv2d_dgrad": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp, c_vp],
     "db200_conv2d_wgrad": [c_vp, ctypes.POINTER(ConvDesc), c_vp, c_vp, c_vp, c_vp],
     "db200_rowmatmul_f32": [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int],

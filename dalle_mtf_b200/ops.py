@@ -247,14 +247,14 @@ def sqnorm(g, out_accum):
 
 
 def adam_step(p, m, v, g, p_bf16, lr, beta1=0.9, beta2=0.999, eps=1e-6, weight_decay=0.0, gnorm_sq=None,
-              clip=0.0, grad_scale=1.0, bias_correction=False, step=0):
+              clip=0.0, grad_scale=1.0, bias_correction=False, step=0, zero_grad=False):
     L.require_device()
     for t, n in ((p, "p"), (m, "m"), (v, "v"), (g, "g")):
         _chk(t, F32, n)
     _chk(p_bf16, BF16, "p_bf16")
     check(L.load().db200_adam_step(stream_ptr(), ptr(p), ptr(m), ptr(v), ptr(g), ptr(p_bf16), p.numel(), lr, beta1,
                                    beta2, eps, weight_decay, ptr(gnorm_sq), clip, grad_scale, int(bias_correction),
-                                   int(step)), "adam_step")
+                                   int(step), int(zero_grad)), "adam_step")
 
 
 # ----------------------------------------------------------------------------------------------- VAE ops
@@ -444,6 +444,39 @@ def sample_rows(logits, u, idx, lo, hi, inv_temp=1.0):
     check(L.load().db200_sample_rows(stream_ptr(), ptr(logits), ptr(u), ptr(idx), rows, logits.stride(0), int(lo),
                                      int(hi), float(inv_temp)), "db200_sample_rows")
     return idx
+
+
+def embed_fwd_at_dev(tokens, wte, wpe, out, pos_dev):
+    """embed_fwd_at with the position (and the token column) taken from the device scalar pos_dev (graph replay)."""
+    L.require_device()
+    _chk(tokens, I32, "tokens"); _chk(wte, BF16, "wte"); _chk(wpe, BF16, "wpe"); _chk(out, BF16, "out")
+    B, d = out.shape
+    check(L.load().db200_embed_fwd_at_dev(stream_ptr(), ptr(tokens), tokens.stride(0), ptr(wte), ptr(wpe), ptr(out), B,
+                                          d, wte.shape[0], ptr(pos_dev)), "db200_embed_fwd_at_dev")
+    return out
+
+
+def attn_decode_dev(qkv_step, k_cache, v_cache, out, pos_dev, scale):
+    L.require_device()
+    B, S, H, dh = k_cache.shape
+    check(L.load().db200_attn_decode_dev(stream_ptr(), ptr(qkv_step), ptr(k_cache), ptr(v_cache), ptr(out), B, S, H, dh,
+                                         ptr(pos_dev), float(scale)), "db200_attn_decode_dev")
+    return out
+
+
+def sample_rows_at(logits, u, tokens, lo, hi, inv_temp, pos_dev):
+    """tokens[r, pos + 1] = lo + argmax over [lo, hi) of logits * inv_temp + Gumbel(u)   (pos read on the device)."""
+    L.require_device()
+    _chk(logits, F32, "logits"); _chk(u, F32, "u"); _chk(tokens, I32, "tokens")
+    check(L.load().db200_sample_rows_at(stream_ptr(), ptr(logits), ptr(u), ptr(tokens), tokens.stride(0),
+                                        logits.shape[0], logits.stride(0), int(lo), int(hi), float(inv_temp),
+                                        ptr(pos_dev)), "db200_sample_rows_at")
+    return tokens
+
+
+def incr_i32(p, delta=1):
+    L.require_device()
+    check(L.load().db200_incr_i32(stream_ptr(), ptr(p), int(delta)), "db200_incr_i32")
 
 
 def onehot_rows(idx, y, offset=0):

@@ -66,6 +66,77 @@ class DalleSampler:
         ops.gemm(self.ln, e.W("wout"), self.logit, B, e.Vpad, e.d, a_mn=False, b_mn=True, bias=e.P("bout"))
         return self.logit
 
+    # -------------------------------------------------------------------------------------------- CUDA-graph path
+    def _step_dev(self, tokens):
+        """self.step with the position (and the input token column) read on the device from self.pos_dev."""
+        e = self.e
+        ops.embed_fwd_at_dev(tokens, e.W("wte"), e.W("wpe"), self.x[0], self.pos_dev)
+        x_in, x_out = self.x
+        for i in range(e.L):
+            p = f"l{i}."
+            ops.layernorm_fwd(x_in, e.P(p + "ln1_g"), e.P(p + "ln1_b"), self.ln, self.mean, self.rstd, e.ln_eps)
+            ops.linear_fwd(self.ln, e.W(p + "wqkv"), self.qkv)
+            ops.attn_decode_dev(self.qkv, self.kc[i], self.vc[i], self.att, self.pos_dev, e.attn_scale)
+            ops.linear_fwd(self.att, e.W(p + "wo"), self.xmid, bias=e.P(p + "o_b"), residual=x_in)
+            ops.layernorm_fwd(self.xmid, e.P(p + "ln2_g"), e.P(p + "ln2_b"), self.ln, self.mean, self.rstd, e.ln_eps)
+            ops.linear_fwd(self.ln, e.W(p + "w1"), self.h1, bias=e.P(p + "b1"), relu=True)
+            ops.linear_fwd(self.h1, e.W(p + "w2"), x_out, bias=e.P(p + "b2"), residual=self.xmid)
+            x_in, x_out = x_out, x_in
+        ops.layernorm_fwd(x_in, e.P("lnf_g"), e.P("lnf_b"), self.ln, self.mean, self.rstd, e.ln_eps)
+        ops.gemm(self.ln, e.W("wout"), self.logit, tokens.shape[0], e.Vpad, e.d, a_mn=False, b_mn=True, bias=e.P("bout"))
+        return self.logit
+
+    def _capture(self, B, greedy, inv_t):
+        """Two graphs over static buffers: the prompt step (teacher forcing: the next token is already in the token
+        matrix) and the sampling step (step -> noise -> Gumbel-max into column pos + 1); both end by advancing pos_dev."""
+        e = self.e
+        key = (B, greedy, inv_t)
+        if getattr(self, "_graph_key", None) == key:
+            return
+        dev = e.device
+        self.tokens = torch.zeros(B, e.S, dtype=I32, device=dev)
+        self.pos_dev = torch.zeros(1, dtype=I32, device=dev)
+        lo, hi = e.text_vocab_size, e.text_vocab_size + e.image_vocab_size
+        self.u = None if greedy else torch.empty(B, hi - lo, dtype=F32, device=dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):     # eager warm-up: function attributes, tensor maps, lazy allocations
+            self._step_dev(self.tokens)
+            if self.u is not None:
+                self.u.uniform_(1e-9, 1.0)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.g_prompt, self.g_sample = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_prompt):
+            self._step_dev(self.tokens)
+            ops.incr_i32(self.pos_dev, 1)
+        with torch.cuda.graph(self.g_sample):
+            logits = self._step_dev(self.tokens)
+            if self.u is not None:
+                self.u.uniform_(1e-9, 1.0)          # default CUDA generator: graph-safe Philox offsets
+            ops.sample_rows_at(logits, self.u, self.tokens, lo, hi, inv_t, self.pos_dev)
+            ops.incr_i32(self.pos_dev, 1)
+        self._graph_key = key
+
+    @torch.no_grad()
+    def generate_graphed(self, text_ids, temperature=1.0):
+        """generate() with the per-position step replayed from CUDA graphs (position kept on the device): removes the
+        ~45 us of Python / ctypes / launch overhead per kernel that bounds eager generation.  Noise comes from torch's
+        default CUDA generator (seed it with torch.manual_seed)."""
+        e = self.e
+        B, TL = text_ids.shape
+        assert TL == e.text_seq_len, f"expected {e.text_seq_len} text positions, got {TL}"
+        self._alloc(B)
+        greedy = temperature is None or temperature <= 0
+        inv_t = 1.0 if greedy else 1.0 / float(temperature)
+        self._capture(B, greedy, inv_t)
+        self.tokens.zero_()
+        self.tokens[:, :TL] = text_ids
+        self.pos_dev.zero_()
+        for pos in range(e.S - 1):
+            (self.g_prompt if pos + 1 < TL else self.g_sample).replay()
+        return self.tokens.clone()
+
     @torch.no_grad()
     def generate(self, text_ids, temperature=1.0, generator=None, return_logits=False):
         """text_ids int32 [B, text_seq_len] (device) -> int32 [B, text_seq_len + image_seq_len]: the prompt followed by

@@ -99,6 +99,7 @@ class VaeEngine:
             self.cb_hi = torch.zeros(self.n_hid, self.K, dtype=BF16, device=dev)
             self.cb_lo = torch.zeros(self.n_hid, self.K, dtype=BF16, device=dev)
         self._B = None
+        self._grads_clean = False
 
     # ------------------------------------------------------------------------------------------ parameters
     def P(self, name):
@@ -456,7 +457,12 @@ class VaeEngine:
 
     # ------------------------------------------------------------------------------------------ optimiser
     def zero_grads(self):
-        self.grads.zero_()
+        """See DalleEngine.zero_grads: the Adam kernel leaves the gradient buffer zeroed behind itself."""
+        if self._grads_clean:
+            self.grads[self.aux_off:].zero_()
+        else:
+            self.grads.zero_()
+        self._grads_clean = False
 
     def optimizer_step(self, lr, step, grad_scale=1.0, beta1=0.9, beta2=0.999, eps=1e-8):
         """tf.train.AdamOptimizer (bias-corrected, no clipping), src/model_fns_tf.py:58-66.  `step` = t >= 1.
@@ -464,6 +470,7 @@ class VaeEngine:
         n = self.n_params_padded
         ops.adam_step(self.master[:n], self.adam_m[:n], self.adam_v[:n], self.grads[:n],
                       None if self.shadow is None else self.shadow[:n], lr, beta1, beta2, eps, 0.0, None, 0.0,
-                      grad_scale, True, step)
+                      grad_scale, True, step, zero_grad=True)
+        self._grads_clean = True
         if self._cb_tc:
             ops.split_f32(self.P("codebook/codebook"), self.cb_hi, self.cb_lo)

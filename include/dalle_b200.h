@@ -156,11 +156,14 @@ int db200_split_f32_to_bf16x2(db200_stream_t stream, const float* src, void* hi_
  *            bias_correction == 0:  p -= lr * (m / (sqrt(v) + eps) + wd*p)
  *            bias_correction == 1:  p -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)      (t = step, >= 1)
  *            p_bf16 (optional) receives the rounded updated parameter (compute copy).
+ *            zero_grad != 0: g is overwritten with 0 once consumed (the gradient buffer accumulates with red.add, so it
+ *            must start every step at zero: this folds that memset into the pass that already streams g).
  * ------------------------------------------------------------------------------------------------------------------ */
 int db200_sqnorm_f32(db200_stream_t stream, const float* g, size_t n, float* out_accum);
-int db200_adam_step(db200_stream_t stream, float* p, float* m, float* v, const float* g, void* p_bf16_or_null,
+int db200_adam_step(db200_stream_t stream, float* p, float* m, float* v, float* g, void* p_bf16_or_null,
                     size_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                    const float* gnorm_sq_or_null, float clip, float grad_scale, int bias_correction, int step);
+                    const float* gnorm_sq_or_null, float clip, float grad_scale, int bias_correction, int step,
+                    int zero_grad);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * K11  discrete-VAE convolutions, NHWC activations / HWIO kernels like tf.layers.conv2d
@@ -199,6 +202,9 @@ int db200_conv2d_wgrad_tc(db200_stream_t stream, const db200_conv_desc* c, const
 /* First encoder layer (Cin = 3, 4x4, stride 2, SAME) straight from the fp32 image to bf16 activations:
  * dedicated CUDA-core kernel (K = 48 is too small for the tensor pipe).  x: f32 [N][H][W][3], w: f32 [4][4][3][Cout]. */
 int db200_conv2d_first_fwd(db200_stream_t stream, const float* x, const float* w, const float* bias_or_null,
+                           void* y_bf16, int N, int H, int W, int Cout);
+/* the same layer on the CUDA cores (fp32 FMA): kept for A/B measurements only */
+int db200_conv2d_first_fwd_fma(db200_stream_t stream, const float* x, const float* w, const float* bias_or_null,
                            void* y_bf16, int N, int H, int W, int Cout);
 int db200_conv2d_dgrad(db200_stream_t stream, const db200_conv_desc* c, const void* dy, const float* w,
                        const void* x_for_relu_mask_or_null, const void* dres_or_null, void* dx);
@@ -267,6 +273,18 @@ int db200_attn_decode(db200_stream_t stream, const void* qkv_step_bf16, void* k_
 int db200_sample_rows(db200_stream_t stream, const float* logits, const float* u_or_null, int32_t* idx, int rows,
                       long long ld, int lo, int hi, float inv_temp);
 int db200_onehot_rows_f32(db200_stream_t stream, const int32_t* idx, float* y, int rows, int K, int offset);
+/* Device-side-position variants: the position lives in ONE int32 in device memory (`pos_dev`, advanced with
+ * db200_incr_i32), so a single captured CUDA graph of the per-position step is replayed for every position (generation
+ * is launch-bound: ~46 kernels per position).  `tokens` is the [B][ld] token matrix: the step reads column *pos_dev and
+ * the sampler writes column *pos_dev + 1. */
+int db200_embed_fwd_at_dev(db200_stream_t stream, const int32_t* tokens, long long ld, const void* wte_bf16,
+                           const void* wpe_bf16, void* out_bf16, int B, int d, int V, const int32_t* pos_dev);
+int db200_attn_decode_dev(db200_stream_t stream, const void* qkv_step_bf16, void* k_cache_bf16, void* v_cache_bf16,
+                          void* out_bf16, int B, int S, int H, int dh, const int32_t* pos_dev, float scale);
+int db200_sample_rows_at(db200_stream_t stream, const float* logits, const float* u_or_null, int32_t* tokens,
+                         long long ld_tokens, int rows, long long ld, int lo, int hi, float inv_temp,
+                         const int32_t* pos_dev);
+int db200_incr_i32(db200_stream_t stream, int32_t* p, int delta);
 
 /* Segmented bf16 -> f32 gather (one launch): segment i copies table[3i+2] elements from src + table[3i] to
  * dst + table[3i+1]; `table_dev` is an int64 array in device memory.  ZeRO-1 mode: rebuilds the compact fp32 copy of the

@@ -38,6 +38,7 @@ def _worker(rank, world, port, out):
     eng.forward(global_tokens[start:start + per].to(dev))
     eng.backward(1.0 / T, on_bucket_ready=dp.make_bucket_hook(eng.grads))
     dp.wait()
+    g_dp = eng.grads[:eng.n_params_padded].clone()     # the optimiser step zeroes the buffer behind itself
     eng.optimizer_step(1e-3)
     torch.cuda.synchronize()
     loss_dp = eng.grads[eng.aux_off].item() / T
@@ -47,11 +48,12 @@ def _worker(rank, world, port, out):
     ref.zero_grads()
     ref.forward(global_tokens.to(dev))
     ref.backward(1.0 / T)
+    g_ref = ref.grads[:ref.n_params_padded].clone()
     ref.optimizer_step(1e-3)
     torch.cuda.synchronize()
     loss_ref = ref.grads[ref.aux_off].item() / T
     n = eng.n_params_padded
-    gerr = ((eng.grads[:n] - ref.grads[:n]).norm() / ref.grads[:n].norm()).item()
+    gerr = ((g_dp - g_ref).norm() / g_ref.norm()).item()
     perr = ((eng.master[:n] - ref.master[:n]).norm() / ref.master[:n].norm()).item()
     dp.barrier()
     out.put((rank, loss_dp, loss_ref, gerr, perr))

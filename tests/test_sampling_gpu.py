@@ -148,3 +148,22 @@ def test_model_classes_expose_sampling_and_predict_still_raises():
     from dalle_mtf_b200 import model_fns
     with pytest.raises(NotImplementedError):
         model_fns.dalle_model_fn(None, None, "predict", {"mode": "predict"})
+
+
+def test_graph_replayed_generation_equals_eager_generation_when_greedy():
+    """CUDA-graph replay of the per-position step (device-side position, db200_*_dev entry points) must produce exactly
+    the tokens of the eager loop under greedy decoding (same kernels, same order)."""
+    from dalle_mtf_b200.dalle_engine import DalleEngine
+    from dalle_mtf_b200.sampling import DalleSampler
+    eng = DalleEngine(256, 2, 2, 300, 40, 10, 14)
+    eng.init_params(3)
+    smp = DalleSampler(eng)
+    g = torch.Generator().manual_seed(2)
+    text = torch.randint(0, 299, (3, 10), generator=g).to(torch.int32).cuda()
+    eager = smp.generate(text, temperature=0.0)
+    graphed = smp.generate_graphed(text, temperature=0.0)
+    assert torch.equal(eager, graphed)
+    again = smp.generate_graphed(text.flip(0).contiguous(), temperature=0.0)      # graphs are reused for new prompts
+    assert torch.equal(again, smp.generate(text.flip(0).contiguous(), temperature=0.0))
+    sampled = smp.generate_graphed(text, temperature=1.0)
+    assert ((sampled[:, 10:] >= 300) & (sampled[:, 10:] < 340)).all() and torch.equal(sampled[:, :10], text)
