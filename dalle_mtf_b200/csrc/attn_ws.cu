@@ -154,14 +154,21 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     if (lane == 0) {
       mbar_expect_tx(q_full, C::TILE);
       ws_load_tile<DH>(sQ, &tmQKV, q_full, 0 * H + h, qt * 128, b);
-      for (int j = 0; j < n_kv; ++j) {
-        const int sk = j % NK, sv = j % NV;
-        mbar_wait(k_empty + 8 * sk, ((uint32_t)(j / NK) & 1u) ^ 1u);
-        mbar_expect_tx(k_full + 8 * sk, C::TILE);
-        ws_load_tile<DH>(sK + sk * C::TILE, &tmQKV, k_full + 8 * sk, 1 * H + h, j * 128, b);
-        mbar_wait(v_empty + 8 * sv, ((uint32_t)(j / NV) & 1u) ^ 1u);
-        mbar_expect_tx(v_full + 8 * sv, C::TILE);
-        ws_load_tile<DH>(sV + sv * C::TILE, &tmQKV, v_full + 8 * sv, 2 * H + h, j * 128, b);
+      // the two rings advance independently (K is consumed two blocks ahead of V): poll both, never block on one
+      int jk = 0, jv = 0;
+      while (jk < n_kv || jv < n_kv) {
+        if (jk < n_kv && mbar_try_wait(k_empty + 8 * (jk % NK), ((uint32_t)(jk / NK) & 1u) ^ 1u)) {
+          const int sk = jk % NK;
+          mbar_expect_tx(k_full + 8 * sk, C::TILE);
+          ws_load_tile<DH>(sK + sk * C::TILE, &tmQKV, k_full + 8 * sk, 1 * H + h, jk * 128, b);
+          ++jk;
+        }
+        if (jv < n_kv && mbar_try_wait(v_empty + 8 * (jv % NV), ((uint32_t)(jv / NV) & 1u) ^ 1u)) {
+          const int sv = jv % NV;
+          mbar_expect_tx(v_full + 8 * sv, C::TILE);
+          ws_load_tile<DH>(sV + sv * C::TILE, &tmQKV, v_full + 8 * sv, 2 * H + h, jv * 128, b);
+          ++jv;
+        }
       }
     }
   } else if (warp == 9) {
@@ -310,11 +317,14 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
 namespace {
 template <int DH>
 struct BwdWs {
-  static constexpr int NS = 2;                     // ring depth of the streamed [128][DH] tile pairs
+  // two streamed [128][DH] tiles per block live in separate rings: the one that is needed until the LAST product of its
+  // block (Q_i for dK, K_j for dQ) three deep, the one that is released early (dO_i after dV, V_j after dP) two deep
+  static constexpr int NA = 3, NB = 2;
   static constexpr uint32_t TILE = 128 * DH * 2;
-  static constexpr uint32_t STAT_BYTES = NS * 256 * 4;
+  static constexpr uint32_t STAT_BYTES = 2 * 256 * 4;
   static constexpr uint32_t BAR_BYTES = 256;
-  static constexpr size_t SMEM = 1024 + 2 * TILE + NS * 2 * TILE + STAT_BYTES + BAR_BYTES;
+  // dynamic shared memory is declared 1024-byte aligned (the 128-byte swizzle needs it): no alignment slack
+  static constexpr size_t SMEM = 2 * TILE + (NA + NB) * TILE + STAT_BYTES + BAR_BYTES;
   static constexpr int THREADS = 384;
 };
 }  // namespace
@@ -327,18 +337,22 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
                         int S, int H, float scale) {
   using C = BwdWs<DH>;
-  constexpr int NS = C::NS;
-  extern __shared__ uint8_t smem_raw[];
+  constexpr int NA = C::NA, NB = C::NB;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sK = base, sV = sK + C::TILE, sR = sV + C::TILE;  // ring stage st: Q_i at sR + st*2*TILE, dO_i behind it
-  const uint32_t sStat = sR + NS * 2 * C::TILE;
+  const uint32_t base = raw;                    // 1024-byte aligned (checked below)
+  const uint32_t sK = base, sV = sK + C::TILE;
+  const uint32_t sQr = sV + C::TILE;            // Q_i ring (NA deep): needed until dK of its block
+  const uint32_t sOr = sQr + NA * C::TILE;      // dO_i ring (NB deep): released after dV of its block
+  const uint32_t sStat = sOr + NB * C::TILE;    // [2][lse2 128 | delta 128]
   const uint32_t bars = sStat + C::STAT_BYTES;
   const uint32_t x_full = bars;
-  const uint32_t r_full = bars + 8;             // [NS]
-  const uint32_t r_empty = r_full + 8 * NS;     // [NS]
-  const uint32_t stat_full = r_empty + 8 * NS;  // [NS]
-  const uint32_t sa_ready = stat_full + 8 * NS; // S^T of block it in TMEM
+  const uint32_t a_full = bars + 8;             // [NA]
+  const uint32_t a_empty = a_full + 8 * NA;     // [NA]
+  const uint32_t b_full = a_empty + 8 * NA;     // [NB]
+  const uint32_t b_empty = b_full + 8 * NB;     // [NB]
+  const uint32_t stat_full = b_empty + 8 * NB;  // [2]
+  const uint32_t sa_ready = stat_full + 16;     // S^T of block it in TMEM
   const uint32_t sb_ready = sa_ready + 8;       // dP^T
   const uint32_t pa_ready = sb_ready + 8;       // P^T written (8 warps)
   const uint32_t pb_ready = pa_ready + 8;       // dS^T written
@@ -360,10 +374,11 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
+    if (raw & 1023u) __trap();  // the 128-byte swizzle needs 1024-byte aligned tiles
     mbar_init(x_full, 1);
-    for (int i = 0; i < NS; ++i) {
-      mbar_init(r_full + 8 * i, 1); mbar_init(r_empty + 8 * i, 1); mbar_init(stat_full + 8 * i, 1);
-    }
+    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) mbar_init(stat_full + 8 * i, 1);
     mbar_init(sa_ready, 1); mbar_init(sb_ready, 1);
     mbar_init(pa_ready, 8); mbar_init(pb_ready, 8);
     mbar_init(acc_done, 1);
@@ -382,13 +397,20 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       mbar_expect_tx(x_full, 2 * C::TILE);
       ws_load_tile<DH>(sK, &tmQKV, x_full, 1 * H + h, r0, b);
       ws_load_tile<DH>(sV, &tmQKV, x_full, 2 * H + h, r0, b);
-      for (int it = 0; it < n_it; ++it) {
-        const int st = it % NS;
-        mbar_wait(r_empty + 8 * st, ((uint32_t)(it / NS) & 1u) ^ 1u);
-        const uint32_t fb = r_full + 8 * st, dq = sR + st * 2 * C::TILE;
-        mbar_expect_tx(fb, 2 * C::TILE);
-        ws_load_tile<DH>(dq, &tmQKV, fb, 0 * H + h, (jb + it) * 128, b);          // Q_i
-        ws_load_tile<DH>(dq + C::TILE, &tmDO, fb, h, (jb + it) * 128, b);         // dO_i
+      int ia = 0, ib = 0;  // the rings advance independently: poll both, never block on one
+      while (ia < n_it || ib < n_it) {
+        if (ia < n_it && mbar_try_wait(a_empty + 8 * (ia % NA), ((uint32_t)(ia / NA) & 1u) ^ 1u)) {
+          const int st = ia % NA;
+          mbar_expect_tx(a_full + 8 * st, C::TILE);
+          ws_load_tile<DH>(sQr + st * C::TILE, &tmQKV, a_full + 8 * st, 0 * H + h, (jb + ia) * 128, b);   // Q_i
+          ++ia;
+        }
+        if (ib < n_it && mbar_try_wait(b_empty + 8 * (ib % NB), ((uint32_t)(ib / NB) & 1u) ^ 1u)) {
+          const int st = ib % NB;
+          mbar_expect_tx(b_full + 8 * st, C::TILE);
+          ws_load_tile<DH>(sOr + st * C::TILE, &tmDO, b_full + 8 * st, h, (jb + ib) * 128, b);            // dO_i
+          ++ib;
+        }
       }
     }
   } else if (warp == 9) {
@@ -397,19 +419,19 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);  // logits: both operands K-major (K = dh)
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // gradients: A from TMEM, B MN-major (K = queries)
       auto issue_s = [&](int it) {   // S^T = K Q_i^T
-        const int st = it % NS;
-        mbar_wait(r_full + 8 * st, (uint32_t)(it / NS) & 1u);
+        const int st = it % NA;
+        mbar_wait(a_full + 8 * st, (uint32_t)(it / NA) & 1u);
         tc_fence_after();
-        const uint32_t q = sR + st * 2 * C::TILE;
+        const uint32_t q = sQr + st * C::TILE;
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tST, desc_kmajor(sK, kk), desc_kmajor(q, kk), idesc_l, kk > 0);
         umma_commit(sa_ready);
       };
       auto issue_dp = [&](int it) {  // dP^T = V dO_i^T
-        const int st = it % NS;
-        mbar_wait(r_full + 8 * st, (uint32_t)(it / NS) & 1u);
+        const int st = it % NB;
+        mbar_wait(b_full + 8 * st, (uint32_t)(it / NB) & 1u);
         tc_fence_after();
-        const uint32_t o = sR + st * 2 * C::TILE + C::TILE;
+        const uint32_t o = sOr + st * C::TILE;
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tdPT, desc_kmajor(sV, kk), desc_kmajor(o, kk), idesc_l, kk > 0);
         umma_commit(sb_ready);
@@ -418,21 +440,21 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       issue_s(0);
       issue_dp(0);
       for (int it = 0; it < n_it; ++it) {
-        const int st = it % NS;
-        const uint32_t q = sR + st * 2 * C::TILE, o = q + C::TILE;
+        const uint32_t q = sQr + (it % NA) * C::TILE, o = sOr + (it % NB) * C::TILE;
         const uint32_t acc = it > 0 ? 1u : 0u;
         mbar_wait(pa_ready, (uint32_t)it & 1u);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i
           umma_bf16_ts(tmem, tST + ts_split_col(kk), desc_mnmajor(o, kk), idesc_g, acc | (kk > 0));
+        umma_commit(b_empty + 8 * (it % NB));  // dO_i is free
         if (it + 1 < n_it) issue_s(it + 1);    // runs under phase B of this block
         mbar_wait(pb_ready, (uint32_t)it & 1u);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
           umma_bf16_ts(tmem + DH, tdPT + ts_split_col(kk), desc_mnmajor(q, kk), idesc_g, acc | (kk > 0));
-        umma_commit(r_empty + 8 * st);
+        umma_commit(a_empty + 8 * (it % NA));  // Q_i is free
         if (it + 1 < n_it) issue_dp(it + 1);   // runs under phase A of the next block
       }
       umma_commit(acc_done);
@@ -441,8 +463,9 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     // ------------------------------------------------------------------------------------------- lse / delta stager
     float* stat_w = reinterpret_cast<float*>(smem_raw + (sStat - raw));
     for (int it = 0; it < n_it; ++it) {
-      const int st = it % NS;
-      mbar_wait(r_empty + 8 * st, ((uint32_t)(it / NS) & 1u) ^ 1u);
+      const int st = it & 1;
+      // slot `st` was last read by phase B of block it-2, which precedes the dK product that frees Q_{it-2}
+      if (it >= 2) mbar_wait(a_empty + 8 * ((it - 2) % NA), (uint32_t)((it - 2) / NA) & 1u);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int c = lane + 32 * u, q = (jb + it) * 128 + c;
@@ -466,11 +489,11 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     const uint32_t tS = tST + 64 * g + lane_off, tdP = tdPT + 64 * g + lane_off;
     const float c1 = scale * LOG2E_F;
     for (int it = 0; it < n_it; ++it) {
-      const int st = it % NS;
+      const int st = it & 1;
       const float4* sl = reinterpret_cast<const float4*>(stat + st * 256 + 64 * g);
       const float4* sd = reinterpret_cast<const float4*>(stat + st * 256 + 128 + 64 * g);
       // ---- phase A: P^T = 2^(c1 s - lse2[query]); pair dropped where key > query (only the first block is diagonal)
-      mbar_wait(stat_full + 8 * st, (uint32_t)(it / NS) & 1u);
+      mbar_wait(stat_full + 8 * st, (uint32_t)(it >> 1) & 1u);
       mbar_wait(sa_ready, (uint32_t)it & 1u);
       tc_fence_after();
       uint32_t pk[32];
@@ -549,16 +572,20 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
                       const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S,
                       int H, float scale) {
   using C = BwdWs<DH>;
-  constexpr int NS = C::NS;
-  extern __shared__ uint8_t smem_raw[];
+  constexpr int NA = C::NA, NB = C::NB;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sQ = base, sdO = sQ + C::TILE, sR = sdO + C::TILE;  // ring stage st: K_j at sR + st*2*TILE, V_j behind
-  const uint32_t bars = sR + NS * 2 * C::TILE + C::STAT_BYTES;
+  const uint32_t base = raw;                     // 1024-byte aligned (checked below)
+  const uint32_t sQ = base, sdO = sQ + C::TILE;
+  const uint32_t sKr = sdO + C::TILE;            // K_j ring (NA deep): needed until dQ of its block
+  const uint32_t sVr = sKr + NA * C::TILE;       // V_j ring (NB deep): released right after dP of its block
+  const uint32_t bars = sVr + NB * C::TILE + C::STAT_BYTES;
   const uint32_t x_full = bars;
-  const uint32_t r_full = bars + 8;              // [NS]
-  const uint32_t r_empty = r_full + 8 * NS;      // [NS]
-  const uint32_t sd_ready = r_empty + 8 * NS;    // S, dP of block j in TMEM
+  const uint32_t a_full = bars + 8;              // [NA]
+  const uint32_t a_empty = a_full + 8 * NA;      // [NA]
+  const uint32_t b_full = a_empty + 8 * NA;      // [NB]
+  const uint32_t b_empty = b_full + 8 * NB;      // [NB]
+  const uint32_t sd_ready = b_empty + 8 * NB;    // S, dP of block j in TMEM
   const uint32_t sd_loaded = sd_ready + 8;       // both groups hold them in registers (8 warps)
   const uint32_t ds_ready = sd_loaded + 8;       // [2] dS of block j written (8 warps)
   const uint32_t ds_free = ds_ready + 16;        // [2] the dQ product has consumed that dS slot
@@ -579,8 +606,10 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
+    if (raw & 1023u) __trap();  // the 128-byte swizzle needs 1024-byte aligned tiles
     mbar_init(x_full, 1);
-    for (int i = 0; i < NS; ++i) { mbar_init(r_full + 8 * i, 1); mbar_init(r_empty + 8 * i, 1); }
+    for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
+    for (int i = 0; i < NB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
     mbar_init(sd_ready, 1);
     mbar_init(sd_loaded, 8);
     for (int i = 0; i < 2; ++i) { mbar_init(ds_ready + 8 * i, 8); mbar_init(ds_free + 8 * i, 1); }
@@ -600,13 +629,20 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       mbar_expect_tx(x_full, 2 * C::TILE);
       ws_load_tile<DH>(sQ, &tmQKV, x_full, 0 * H + h, r0, b);
       ws_load_tile<DH>(sdO, &tmDO, x_full, h, r0, b);
-      for (int j = 0; j < n_it; ++j) {
-        const int st = j % NS;
-        mbar_wait(r_empty + 8 * st, ((uint32_t)(j / NS) & 1u) ^ 1u);
-        const uint32_t fb = r_full + 8 * st, dk = sR + st * 2 * C::TILE;
-        mbar_expect_tx(fb, 2 * C::TILE);
-        ws_load_tile<DH>(dk, &tmQKV, fb, 1 * H + h, j * 128, b);                  // K_j
-        ws_load_tile<DH>(dk + C::TILE, &tmQKV, fb, 2 * H + h, j * 128, b);        // V_j
+      int ia = 0, ib = 0;  // the rings advance independently: poll both, never block on one
+      while (ia < n_it || ib < n_it) {
+        if (ia < n_it && mbar_try_wait(a_empty + 8 * (ia % NA), ((uint32_t)(ia / NA) & 1u) ^ 1u)) {
+          const int st = ia % NA;
+          mbar_expect_tx(a_full + 8 * st, C::TILE);
+          ws_load_tile<DH>(sKr + st * C::TILE, &tmQKV, a_full + 8 * st, 1 * H + h, ia * 128, b);   // K_j
+          ++ia;
+        }
+        if (ib < n_it && mbar_try_wait(b_empty + 8 * (ib % NB), ((uint32_t)(ib / NB) & 1u) ^ 1u)) {
+          const int st = ib % NB;
+          mbar_expect_tx(b_full + 8 * st, C::TILE);
+          ws_load_tile<DH>(sVr + st * C::TILE, &tmQKV, b_full + 8 * st, 2 * H + h, ib * 128, b);   // V_j
+          ++ib;
+        }
       }
     }
   } else if (warp == 9) {
@@ -615,31 +651,31 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dQ = dS K : A from TMEM, B MN-major (K = keys)
       auto issue_l = [&](int j) {  // S = Q K_j^T, dP = dO V_j^T
-        const int st = j % NS;
-        mbar_wait(r_full + 8 * st, (uint32_t)(j / NS) & 1u);
+        mbar_wait(a_full + 8 * (j % NA), (uint32_t)(j / NA) & 1u);
+        mbar_wait(b_full + 8 * (j % NB), (uint32_t)(j / NB) & 1u);
         tc_fence_after();
-        const uint32_t k = sR + st * 2 * C::TILE, v = k + C::TILE;
+        const uint32_t k = sKr + (j % NA) * C::TILE, v = sVr + (j % NB) * C::TILE;
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tSb, desc_kmajor(sQ, kk), desc_kmajor(k, kk), idesc_l, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tdPb, desc_kmajor(sdO, kk), desc_kmajor(v, kk), idesc_l, kk > 0);
         umma_commit(sd_ready);
+        umma_commit(b_empty + 8 * (j % NB));  // V_j is free as soon as dP has consumed it
       };
       mbar_wait(x_full, 0);
       issue_l(0);
       for (int j = 0; j < n_it; ++j) {
-        const int st = j % NS;
         if (j + 1 < n_it) {  // the groups hold block j in registers: the next logits run under their arithmetic
           mbar_wait(sd_loaded, (uint32_t)j & 1u);
           issue_l(j + 1);
         }
         mbar_wait(ds_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
         tc_fence_after();
-        const uint32_t k = sR + st * 2 * C::TILE, tdS = tdSb + 64 * (j & 1);
+        const uint32_t k = sKr + (j % NA) * C::TILE, tdS = tdSb + 64 * (j & 1);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
           umma_bf16_ts(tmem, tdS + kk * 8, desc_mnmajor(k, kk), idesc_g, (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(r_empty + 8 * st);
+        umma_commit(a_empty + 8 * (j % NA));  // K_j is free
         umma_commit(ds_free + 8 * (j & 1));
       }
       umma_commit(acc_done);

@@ -309,3 +309,20 @@ def test_optimizer_config_distinguishes_missing_from_null_clipping():
     import pytest
     with pytest.raises(ValueError):
         OptimizerConfig(defaultdict(lambda: None, dict(base, weight_decay=-1)))
+
+
+def test_tokenizer_loads_bpe_files_from_a_local_directory(tmp_path):
+    """src/data/tokenizer_utils.py:4-16 offline: vocab.json + merges.txt from a directory, `<|padding|>` appended as
+    the last id (the real GPT-2 files give len 50258 / pad id 50257; a toy vocabulary is used here)."""
+    import json
+    from dalle_mtf_b200.tokenizer import get_tokenizer
+    vocab = {c: i for i, c in enumerate(["a", "b", "c", "ab", "abc", "Ġ", "Ġa", "<|endoftext|>"])}
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    (tmp_path / "merges.txt").write_text("#version: 0.2\na b\nab c\nĠ a\n")
+    for kind in (None, "hf_gp2tokenizer"):
+        tok = get_tokenizer(kind, vocab_dir=str(tmp_path))
+        assert len(tok) == len(vocab) + 1 and tok.pad_token_id == len(vocab)
+        assert tok.encode("abc") == [vocab["abc"]] and tok.encode("ab a") == [vocab["ab"], vocab["Ġa"]]
+    import pytest
+    with pytest.raises(FileNotFoundError):
+        get_tokenizer(None, vocab_dir=str(tmp_path / "missing"))
