@@ -60,6 +60,9 @@ def per_gpu_batch_for(workload, n_gpus, scaling):
     return per_gpu
 
 
+N_LAYERS_OVERRIDE = None   # --n-layers: smoke runs of a big workload with fewer layers (shown in config.workload)
+
+
 def load_params(n_gpus, workload="dalle_example", scaling="weak"):
     from dalle_mtf_b200.utils import fetch_model_params
     cfg = WORKLOADS[workload][0]
@@ -71,6 +74,8 @@ def load_params(n_gpus, workload="dalle_example", scaling="weak"):
     p["vae_random_init"] = True        # no pretrained VAE checkpoint in a throughput run (random-init weights)
     p["padding_id"] = 50257
     p["model_path"] = None
+    if N_LAYERS_OVERRIDE:
+        p["n_layers"] = int(N_LAYERS_OVERRIDE)
     return p
 
 
@@ -320,6 +325,7 @@ def measure_dalle(args, dp, device, workload, steps, warmup, full):
     params = load_params(args.gpus, workload, args.scaling)
     params["_dp"] = dp
     cfg_file, _, d_model, n_layers, vocab = WORKLOADS[workload]
+    n_layers = params["n_layers"]
     per_gpu_batch = per_gpu_batch_for(workload, args.gpus, args.scaling)
     it = iter(dalle_input_fn(params))
     host_batches = [next(it) for _ in range(4)]                 # pinned host memory
@@ -463,10 +469,15 @@ def main():
                          "dalle_coco = configs[3] shape (n_embd 1024, 24 layers, 16 heads, 16 sequences per GPU)")
     ap.add_argument("--scaling", type=str, default="weak", choices=["weak", "strong"],
                     help="weak: 32 sequences per GPU (global batch 32 N); strong: global batch fixed at 32 (32 / N per GPU)")
+    ap.add_argument("--n-layers", type=int, default=0,
+                    help="override the workload's layer count (smoke runs only; the line's config names the override)")
     ap.add_argument("--no-extra", action="store_true", help="skip the bounded dalle_coco / vae_coco side measurements")
     ap.add_argument("--vae-coco", action="store_true",
                     help="measure configs/vae_coco_b200.json (256x256, K=8192, bf16, 16 images per GPU) instead")
     args = ap.parse_args()
+    if args.n_layers:
+        global N_LAYERS_OVERRIDE
+        N_LAYERS_OVERRIDE = args.n_layers
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)

@@ -28,6 +28,8 @@
 //             under the next block's S^T product:   S0 dP0 | [A0] dV0 S1 | [B0] dK0 dP1 | [A1] dV1 S2 | ...
 //   dQ      : lanes = queries; the groups release S / dP as soon as they are in registers, so the next block's two logit
 //             products run under the dS arithmetic; dS goes to its own double-buffered TMEM slot:  dQ += dS K_j.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -45,8 +47,9 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-// the 256 threads of the two math warpgroups (named barrier 1; barrier 0 is __syncthreads)
-__device__ __forceinline__ void math_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// all threads of the NG math warpgroups (named barrier 1; barrier 0 is __syncthreads)
+template <int NG>
+__device__ __forceinline__ void math_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(128 * NG) : "memory"); }
 
 template <int DH>
 __device__ __forceinline__ void ws_load_tile(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int chan, int row0,
@@ -63,8 +66,35 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kk) {
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) {
   return umma_smem_desc_sw128(tile + kk * 2048, T128B, 1024);
 }
-// column of K-step kk (16 bf16 = 8 packed columns) of a TMEM A operand stored as two 32-column halves, one per group slice
-__device__ __forceinline__ uint32_t ts_split_col(int kk) { return (kk < 4) ? kk * 8 : 64 + (kk - 4) * 8; }
+// column of K-step kk (16 bf16 = 8 packed columns) of a TMEM A operand whose 128 K-elements are stored group by group:
+// group g's 128/NG elements sit packed at the start of its own 128/NG-column slice
+template <int NG>
+__device__ __forceinline__ uint32_t ts_split_col(int kk) {
+  constexpr int CG = 128 / NG;            // elements (= fp32 columns) per group slice
+  const int e = kk * 16;                  // first K element of this step
+  return (e / CG) * CG + (e % CG) / 2;
+}
+// 32-bit TMEM loads / stores of N consecutive columns (N = 16 or 32)
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t* r) {
+  if constexpr (N == 32) tmem_ld_x32(taddr, r); else tmem_ld_x16(taddr, r);
+}
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r) {
+  if constexpr (N == 32) tmem_st_x32(taddr, r); else tmem_st_x16(taddr, r);
+}
+template <int N>
+__device__ __forceinline__ void store_cols_bf16(bf16* dst, const uint32_t* r, float mul) {
+#pragma unroll
+  for (int e = 0; e < N; e += 8) {
+    uint4 q;
+    q.x = pack_bf16x2(__uint_as_float(r[e]) * mul, __uint_as_float(r[e + 1]) * mul);
+    q.y = pack_bf16x2(__uint_as_float(r[e + 2]) * mul, __uint_as_float(r[e + 3]) * mul);
+    q.z = pack_bf16x2(__uint_as_float(r[e + 4]) * mul, __uint_as_float(r[e + 5]) * mul);
+    q.w = pack_bf16x2(__uint_as_float(r[e + 6]) * mul, __uint_as_float(r[e + 7]) * mul);
+    *reinterpret_cast<uint4*>(dst + e) = q;
+  }
+}
 
 __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
   tc_fence_before();
@@ -87,30 +117,36 @@ __device__ __forceinline__ void store_row_bf16(bf16* dst, const uint32_t* r, flo
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
-template <int DH>
+template <int DH, int NG>
 struct FwdWs {
   static constexpr int NK = (DH == 128) ? 3 : 4;   // K ring depth (128-key blocks): logits run two blocks ahead
   static constexpr int NV = (DH == 128) ? 2 : 4;   // V ring depth
   static constexpr uint32_t TILE = 128 * DH * 2;   // one [128][DH] bf16 operand tile
-  static constexpr uint32_t XCH_BYTES = 2 * 2 * 128 * 4;
+  static constexpr uint32_t XCH_BYTES = 2 * NG * 128 * 4;
   static constexpr uint32_t BAR_BYTES = 256;
   static constexpr size_t SMEM = 1024 + TILE + (NK + NV) * TILE + XCH_BYTES + BAR_BYTES;
-  static constexpr int THREADS = 320;
+  static constexpr int THREADS = (4 * NG + 2) * 32;  // NG math warpgroups + TMA warp + MMA warp
 };
 
 }  // namespace
 
-template <int DH>
-__global__ void __launch_bounds__(320, 1)
+// NG = number of softmax warpgroups = column groups of every 128-key block (2: 64 columns per thread, 4: 32).  More
+// groups = more resident warps per scheduler: the per-warp instruction stream is a chain of dependent fp32 / MUFU ops,
+// and with two math warps per scheduler it issues once every ~6 cycles (ncu, profiles/ncu_attn_r02.md).
+template <int DH, int NG>
+__global__ void __launch_bounds__((4 * NG + 2) * 32, 1)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out,
                    int S, int H, float scale) {
-  using C = FwdWs<DH>;
+  using C = FwdWs<DH, NG>;
   constexpr int NK = C::NK, NV = C::NV;
+  constexpr int CG = 128 / NG;       // key columns of a block per group (= per thread)
+  constexpr int OG = DH / NG;        // output columns per group
+  constexpr int TMA_WARP = 4 * NG, MMA_WARP = 4 * NG + 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sQ = base, sK = sQ + C::TILE, sV = sK + NK * C::TILE;
-  const uint32_t sX = sV + NV * C::TILE;                 // [2 parities][2 groups][128 rows] f32 maxima / sums
+  const uint32_t sX = sV + NV * C::TILE;                 // [2 parities][NG groups][128 rows] f32 maxima / sums
   const uint32_t bars = sX + C::XCH_BYTES;
   const uint32_t q_full = bars;
   const uint32_t k_full = bars + 8;                // [NK]
@@ -138,18 +174,18 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     mbar_init(q_full, 1);
     for (int i = 0; i < NK; ++i) { mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1); }
     for (int i = 0; i < NV; ++i) { mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(s_ready + 8 * i, 1); mbar_init(p_ready + 8 * i, 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(s_ready + 8 * i, 1); mbar_init(p_ready + 8 * i, 4 * NG); }
     mbar_init(o_done, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == TMA_WARP) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tO = tmem + 256;
 
-  if (warp == 8) {
+  if (warp == TMA_WARP) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
       mbar_expect_tx(q_full, C::TILE);
@@ -171,7 +207,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T : both K-major (K = dh)
@@ -197,7 +233,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         const uint32_t vb = sV + sv * C::TILE, tP = tmem + (j & 1) * 128;
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_bf16_ts(tO, tP + ts_split_col(kk), desc_mnmajor(vb, kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_bf16_ts(tO, tP + ts_split_col<NG>(kk), desc_mnmajor(vb, kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(o_done);
         umma_commit(v_empty + 8 * sv);
         if (j + 2 < n_kv) issue_s(j + 2);  // into the buffer whose P the product above has just been queued to consume
@@ -205,57 +241,59 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     }
   } else {
     // ------------------------------------------------------------------------------------------- softmax warpgroups
-    const int g = warp >> 2;                       // column half of every key block / of the output
+    const int g = warp >> 2;                       // column group of every key block / of the output
     const int row = tid & 127;                     // query row inside the tile = TMEM lane
     const int qi = qt * 128 + row;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const float c1 = scale * LOG2E_F;
-    float m_used = -INFINITY;  // the maximum the accumulated P / O / l are scaled by (identical in both groups)
+    float m_used = -INFINITY;  // the maximum the accumulated P / O / l are scaled by (identical in all groups)
     float l_run = 0.f;         // partial row sum over this group's key columns
     for (int j = 0; j < n_kv; ++j) {
-      const uint32_t tS = tmem + (j & 1) * 128 + 64 * g + lane_off;
+      const uint32_t tS = tmem + (j & 1) * 128 + CG * g + lane_off;
       mbar_wait(s_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
-      uint32_t sv[64];
-      tmem_ld_x32(tS, sv);
-      tmem_ld_x32(tS + 32, sv + 32);
+      uint32_t sv[CG];
+#pragma unroll
+      for (int c = 0; c < CG / 32; ++c) tmem_ld_x32(tS + c * 32, sv + c * 32);
       tmem_ld_wait();
       if (j == qt) {  // diagonal block: keys after the query are masked (src/dalle_mtf/models.py:221-227)
-        const int lim = row - 64 * g;  // columns c > lim of this slice are in the future
+        const int lim = row - CG * g;  // columns c > lim of this slice are in the future
 #pragma unroll
-        for (int c = 0; c < 64; ++c)
+        for (int c = 0; c < CG; ++c)
           if (c > lim) sv[c] = 0xff800000u;  // -inf
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < 64; c += 4) {
+      for (int c = 0; c < CG; c += 4) {
         mx0 = fmaxf(mx0, __uint_as_float(sv[c]));
         mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
         mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
       }
       float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      float* xp = xch + (j & 1) * 256;
+      float* xp = xch + (j & 1) * (NG * 128);
       xp[g * 128 + row] = mx;
-      math_bar_sync();  // both halves' maxima visible; both groups hold their S values in registers
-      mx = fmaxf(mx, xp[(g ^ 1) * 128 + row]);  // finite: key 0 is visible to every query
+      math_bar_sync<NG>();  // all groups' maxima visible; every group holds its S values in registers
+#pragma unroll
+      for (int o = 1; o < NG; ++o) mx = fmaxf(mx, xp[((g + o) % NG) * 128 + row]);  // finite: key 0 is always visible
       if (j == 0) {
         m_used = mx;
       } else {
-        const bool need = (mx - m_used) * c1 > 8.f;  // same decision in both threads of a row
+        const bool need = (mx - m_used) * c1 > 8.f;  // same decision in every thread of a row
         if (__any_sync(0xffffffffu, need)) {         // tcgen05.ld / st are warp-collective
           mbar_wait(o_done, (uint32_t)(j - 1) & 1u);  // the previous P.V has landed in O
           tc_fence_after();
           const float alpha = need ? ex2f((m_used - mx) * c1) : 1.f;
+          constexpr int W = OG >= 32 ? 32 : 16;  // this group's share of the output columns
 #pragma unroll
-          for (int c = 0; c < DH / 64; ++c) {  // this group's half of the output columns
-            uint32_t r[32];
-            const uint32_t ta = tO + lane_off + g * (DH / 2) + c * 32;
-            tmem_ld_x32(ta, r);
+          for (int c = 0; c < OG / W; ++c) {
+            uint32_t r[W];
+            const uint32_t ta = tO + lane_off + g * OG + c * W;
+            tmem_ld_n<W>(ta, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_x32(ta, r);
+            for (int i = 0; i < W; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+            tmem_st_n<W>(ta, r);
           }
           if (need) {
             l_run *= alpha;
@@ -263,11 +301,11 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
           }
         }
       }
-      // P_j = 2^(c1 (s - m_used)) -> bf16 pairs -> the first 32 columns of this group's slice of the S buffer
+      // P_j = 2^(c1 (s - m_used)) -> bf16 pairs -> the first CG/2 columns of this group's slice of the S buffer
       const float mc = m_used * c1;
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < CG / 32; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -283,27 +321,30 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       tmem_st_wait();
       warp_arrive(p_ready + 8 * (j & 1), lane);
     }
-    // ---- epilogue: O / l -> bf16 (this group's half of the columns), lse
-    float* xp = xch + (n_kv & 1) * 256;  // the parity the last block did not use
+    // ---- epilogue: O / l -> bf16 (this group's share of the columns), lse
+    float* xp = xch + (n_kv & 1) * (NG * 128);  // the parity the last block did not use
     xp[g * 128 + row] = l_run;
     mbar_wait(o_done, (uint32_t)(n_kv - 1) & 1u);
     tc_fence_after();
-    math_bar_sync();
-    const float l_tot = l_run + xp[(g ^ 1) * 128 + row];
-    const float inv = 1.f / l_tot;
-    bf16* op = out + (((long long)b * S + qi) * H + h) * DH + g * (DH / 2);
+    math_bar_sync<NG>();
+    float l_tot = 0.f;
 #pragma unroll
-    for (int c = 0; c < DH / 64; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(tO + lane_off + g * (DH / 2) + c * 32, r);
+    for (int o = 0; o < NG; ++o) l_tot += xp[o * 128 + row];  // same order in every group: identical 1 / l
+    const float inv = 1.f / l_tot;
+    bf16* op = out + (((long long)b * S + qi) * H + h) * DH + g * OG;
+    constexpr int W = OG >= 32 ? 32 : 16;
+#pragma unroll
+    for (int c = 0; c < OG / W; ++c) {
+      uint32_t r[W];
+      tmem_ld_n<W>(tO + lane_off + g * OG + c * W, r);
       tmem_ld_wait();
-      if (qi < S) store_row_bf16(op + c * 32, r, inv);
+      if (qi < S) store_cols_bf16<W>(op + c * W, r, inv);
     }
     if (qi < S && g == 0) lse_out[((long long)b * H + h) * S + qi] = m_used * scale + logf(l_tot);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == TMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -315,7 +356,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
 //   ds = p * (dp - delta) * scale
 // ------------------------------------------------------------------------------------------------------------------
 namespace {
-template <int DH>
+template <int DH, int NG>
 struct BwdWs {
   // two streamed [128][DH] tiles per block live in separate rings: the one that is needed until the LAST product of its
   // block (Q_i for dK, K_j for dQ) three deep, the one that is released early (dO_i after dV, V_j after dP) two deep
@@ -325,19 +366,21 @@ struct BwdWs {
   static constexpr uint32_t BAR_BYTES = 256;
   // dynamic shared memory is declared 1024-byte aligned (the 128-byte swizzle needs it): no alignment slack
   static constexpr size_t SMEM = 2 * TILE + (NA + NB) * TILE + STAT_BYTES + BAR_BYTES;
-  static constexpr int THREADS = 384;
+  static constexpr int THREADS = (4 * NG + 4) * 32;  // NG math warpgroups + TMA, MMA, stager (+ one idle) warps
 };
 }  // namespace
 
 // dK / dV: CTA = 128 keys (TMEM lanes), loop over the 128-query blocks i >= its own.  TMEM: dV [0,dh) dK [dh,2dh)
 // S^T [256,384) dP^T [384,512).
-template <int DH>
-__global__ void __launch_bounds__(384, 1)
+template <int DH, int NG>
+__global__ void __launch_bounds__((4 * NG + 4) * 32, 1)
 attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
                         int S, int H, float scale) {
-  using C = BwdWs<DH>;
+  using C = BwdWs<DH, NG>;
   constexpr int NA = C::NA, NB = C::NB;
+  constexpr int CG = 128 / NG;       // query columns of a block per group (= per thread)
+  constexpr int TMA_WARP = 4 * NG, MMA_WARP = 4 * NG + 1, STAT_WARP = 4 * NG + 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = raw;                    // 1024-byte aligned (checked below)
@@ -354,7 +397,7 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   const uint32_t stat_full = b_empty + 8 * NB;  // [2]
   const uint32_t sa_ready = stat_full + 16;     // S^T of block it in TMEM
   const uint32_t sb_ready = sa_ready + 8;       // dP^T
-  const uint32_t pa_ready = sb_ready + 8;       // P^T written (8 warps)
+  const uint32_t pa_ready = sb_ready + 8;       // P^T written (all math warps)
   const uint32_t pb_ready = pa_ready + 8;       // dS^T written
   const uint32_t acc_done = pb_ready + 8;
   const uint32_t tmem_slot = acc_done + 8;
@@ -380,18 +423,18 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     for (int i = 0; i < NB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) mbar_init(stat_full + 8 * i, 1);
     mbar_init(sa_ready, 1); mbar_init(sb_ready, 1);
-    mbar_init(pa_ready, 8); mbar_init(pb_ready, 8);
+    mbar_init(pa_ready, 4 * NG); mbar_init(pb_ready, 4 * NG);
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == TMA_WARP) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tST = tmem + 256, tdPT = tmem + 384;
 
-  if (warp == 8) {
+  if (warp == TMA_WARP) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
       mbar_expect_tx(x_full, 2 * C::TILE);
@@ -413,7 +456,7 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);  // logits: both operands K-major (K = dh)
@@ -446,20 +489,20 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i
-          umma_bf16_ts(tmem, tST + ts_split_col(kk), desc_mnmajor(o, kk), idesc_g, acc | (kk > 0));
+          umma_bf16_ts(tmem, tST + ts_split_col<NG>(kk), desc_mnmajor(o, kk), idesc_g, acc | (kk > 0));
         umma_commit(b_empty + 8 * (it % NB));  // dO_i is free
         if (it + 1 < n_it) issue_s(it + 1);    // runs under phase B of this block
         mbar_wait(pb_ready, (uint32_t)it & 1u);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
-          umma_bf16_ts(tmem + DH, tdPT + ts_split_col(kk), desc_mnmajor(q, kk), idesc_g, acc | (kk > 0));
+          umma_bf16_ts(tmem + DH, tdPT + ts_split_col<NG>(kk), desc_mnmajor(q, kk), idesc_g, acc | (kk > 0));
         umma_commit(a_empty + 8 * (it % NA));  // Q_i is free
         if (it + 1 < n_it) issue_dp(it + 1);   // runs under phase A of the next block
       }
       umma_commit(acc_done);
     }
-  } else if (warp == 10) {
+  } else if (warp == STAT_WARP) {
     // ------------------------------------------------------------------------------------------- lse / delta stager
     float* stat_w = reinterpret_cast<float*>(smem_raw + (sStat - raw));
     for (int it = 0; it < n_it; ++it) {
@@ -480,26 +523,26 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(stat_full + 8 * st);
     }
-  } else if (warp < 8) {
+  } else if (warp < 4 * NG) {
     // ------------------------------------------------------------------------------------------- gradient warpgroups
-    const int g = warp >> 2;            // query columns [64g, 64g+64) of every block
+    const int g = warp >> 2;            // query columns [CG g, CG g + CG) of every block
     const int row = tid & 127;          // key row = TMEM lane
     const int ki = r0 + row;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
-    const uint32_t tS = tST + 64 * g + lane_off, tdP = tdPT + 64 * g + lane_off;
+    const uint32_t tS = tST + CG * g + lane_off, tdP = tdPT + CG * g + lane_off;
     const float c1 = scale * LOG2E_F;
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
-      const float4* sl = reinterpret_cast<const float4*>(stat + st * 256 + 64 * g);
-      const float4* sd = reinterpret_cast<const float4*>(stat + st * 256 + 128 + 64 * g);
+      const float4* sl = reinterpret_cast<const float4*>(stat + st * 256 + CG * g);
+      const float4* sd = reinterpret_cast<const float4*>(stat + st * 256 + 128 + CG * g);
       // ---- phase A: P^T = 2^(c1 s - lse2[query]); pair dropped where key > query (only the first block is diagonal)
       mbar_wait(stat_full + 8 * st, (uint32_t)(it >> 1) & 1u);
       mbar_wait(sa_ready, (uint32_t)it & 1u);
       tc_fence_after();
-      uint32_t pk[32];
-      const int lim = (it == 0) ? row - 64 * g : -1;  // columns c < lim are queries before this key
+      uint32_t pk[CG / 2];
+      const int lim = (it == 0) ? row - CG * g : -1;  // columns c < lim are queries before this key
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < CG / 32; ++c) {
         uint32_t rs[32];
         tmem_ld_x32(tS + c * 32, rs);
         tmem_ld_wait();
@@ -517,15 +560,15 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           pk[(cc >> 1) + 1] = pack_bf16x2(p2, p3);
         }
       }
-      tmem_st_x32(tS, pk);
+      tmem_st_n<CG / 2>(tS, pk);
       tmem_st_wait();
       warp_arrive(pa_ready, lane);
       // ---- phase B: dS^T = (P^T * scale) (dP^T - delta[query])
       mbar_wait(sb_ready, (uint32_t)it & 1u);
       tc_fence_after();
-      uint32_t dk[32];
+      uint32_t dk[CG / 2];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < CG / 32; ++c) {
         uint32_t rd[32];
         tmem_ld_x32(tdP + c * 32, rd);
         tmem_ld_wait();
@@ -540,25 +583,28 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
                                           (pb.y * scale) * (__uint_as_float(rd[i + 3]) - d4.w));
         }
       }
-      tmem_st_x32(tdP, dk);
+      tmem_st_n<CG / 2>(tdP, dk);
       tmem_st_wait();
       warp_arrive(pb_ready, lane);
     }
-    // ---- epilogue: group 0 writes dV, group 1 dK (bf16 rows of dqkv)
+    // ---- epilogue: the 2 dh accumulator columns (dV | dK) are split evenly over the groups
     mbar_wait(acc_done, 0);
     tc_fence_after();
-    bf16* dst = dqkv + ((((long long)b * S + ki) * 3 + (g == 0 ? 2 : 1)) * H + h) * DH;
+    constexpr int EG = 2 * DH / NG;                 // columns per group
+    const int acc_i = (g * EG) / DH;                // 0: dV, 1: dK
+    const int col0 = (g * EG) % DH;
+    bf16* dst = dqkv + ((((long long)b * S + ki) * 3 + (acc_i == 0 ? 2 : 1)) * H + h) * DH + col0;
 #pragma unroll 1
-    for (int c = 0; c < DH / 32; ++c) {
+    for (int c = 0; c < EG / 32; ++c) {
       uint32_t r[32];
-      tmem_ld_x32(tmem + lane_off + g * DH + c * 32, r);
+      tmem_ld_x32(tmem + lane_off + g * EG + c * 32, r);
       tmem_ld_wait();
-      if (ki < S) store_row_bf16(dst + c * 32, r, 1.f);
+      if (ki < S) store_cols_bf16<32>(dst + c * 32, r, 1.f);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == TMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -566,13 +612,15 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
 // dQ: CTA = 128 queries (TMEM lanes), loop over the 128-key blocks j <= its own.  TMEM: dQ [0,dh) S [128,256)
 // dP [256,384) dS [384,448) [448,512).
-template <int DH>
-__global__ void __launch_bounds__(384, 1)
+template <int DH, int NG>
+__global__ void __launch_bounds__((4 * NG + 4) * 32, 1)
 attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S,
                       int H, float scale) {
-  using C = BwdWs<DH>;
+  using C = BwdWs<DH, NG>;
   constexpr int NA = C::NA, NB = C::NB;
+  constexpr int CG = 128 / NG;       // key columns of a block per group (= per thread)
+  constexpr int TMA_WARP = 4 * NG, MMA_WARP = 4 * NG + 1;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = raw;                     // 1024-byte aligned (checked below)
@@ -586,8 +634,8 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   const uint32_t b_full = a_empty + 8 * NA;      // [NB]
   const uint32_t b_empty = b_full + 8 * NB;      // [NB]
   const uint32_t sd_ready = b_empty + 8 * NB;    // S, dP of block j in TMEM
-  const uint32_t sd_loaded = sd_ready + 8;       // both groups hold them in registers (8 warps)
-  const uint32_t ds_ready = sd_loaded + 8;       // [2] dS of block j written (8 warps)
+  const uint32_t sd_loaded = sd_ready + 8;       // every group holds them in registers (all math warps)
+  const uint32_t ds_ready = sd_loaded + 8;       // [2] dS of block j written (all math warps)
   const uint32_t ds_free = ds_ready + 16;        // [2] the dQ product has consumed that dS slot
   const uint32_t acc_done = ds_free + 16;
   const uint32_t tmem_slot = acc_done + 8;
@@ -611,41 +659,41 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
     mbar_init(sd_ready, 1);
-    mbar_init(sd_loaded, 8);
-    for (int i = 0; i < 2; ++i) { mbar_init(ds_ready + 8 * i, 8); mbar_init(ds_free + 8 * i, 1); }
+    mbar_init(sd_loaded, 4 * NG);
+    for (int i = 0; i < 2; ++i) { mbar_init(ds_ready + 8 * i, 4 * NG); mbar_init(ds_free + 8 * i, 1); }
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 512);
+  if (warp == TMA_WARP) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tSb = tmem + 128, tdPb = tmem + 256, tdSb = tmem + 384;
 
-  if (warp == 8) {
+  if (warp == TMA_WARP) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
       mbar_expect_tx(x_full, 2 * C::TILE);
       ws_load_tile<DH>(sQ, &tmQKV, x_full, 0 * H + h, r0, b);
       ws_load_tile<DH>(sdO, &tmDO, x_full, h, r0, b);
-      int ia = 0, ib = 0;  // the rings advance independently: poll both, never block on one
-      while (ia < n_it || ib < n_it) {
+      int ia = 0, ib2 = 0;  // the rings advance independently: poll both, never block on one
+      while (ia < n_it || ib2 < n_it) {
         if (ia < n_it && mbar_try_wait(a_empty + 8 * (ia % NA), ((uint32_t)(ia / NA) & 1u) ^ 1u)) {
           const int st = ia % NA;
           mbar_expect_tx(a_full + 8 * st, C::TILE);
           ws_load_tile<DH>(sKr + st * C::TILE, &tmQKV, a_full + 8 * st, 1 * H + h, ia * 128, b);   // K_j
           ++ia;
         }
-        if (ib < n_it && mbar_try_wait(b_empty + 8 * (ib % NB), ((uint32_t)(ib / NB) & 1u) ^ 1u)) {
-          const int st = ib % NB;
+        if (ib2 < n_it && mbar_try_wait(b_empty + 8 * (ib2 % NB), ((uint32_t)(ib2 / NB) & 1u) ^ 1u)) {
+          const int st = ib2 % NB;
           mbar_expect_tx(b_full + 8 * st, C::TILE);
-          ws_load_tile<DH>(sVr + st * C::TILE, &tmQKV, b_full + 8 * st, 2 * H + h, ib * 128, b);   // V_j
-          ++ib;
+          ws_load_tile<DH>(sVr + st * C::TILE, &tmQKV, b_full + 8 * st, 2 * H + h, ib2 * 128, b);  // V_j
+          ++ib2;
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);
@@ -680,13 +728,13 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       }
       umma_commit(acc_done);
     }
-  } else if (warp < 8) {
+  } else if (warp < 4 * NG) {
     // ------------------------------------------------------------------------------------------- gradient warpgroups
-    const int g = warp >> 2;            // key columns [64g, 64g+64) of every block
+    const int g = warp >> 2;            // key columns [CG g, CG g + CG) of every block
     const int row = tid & 127;          // query row = TMEM lane
     const int qi = r0 + row;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
-    const uint32_t tS = tSb + 64 * g + lane_off, tdP = tdPb + 64 * g + lane_off;
+    const uint32_t tS = tSb + CG * g + lane_off, tdP = tdPb + CG * g + lane_off;
     const float c1 = scale * LOG2E_F;
     float lse2 = INFINITY, dl = 0.f;    // out-of-range query row: p = 0
     if (qi < S) {
@@ -696,21 +744,22 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     for (int j = 0; j < n_it; ++j) {
       mbar_wait(sd_ready, (uint32_t)j & 1u);
       tc_fence_after();
-      uint32_t rs[64], rd[64];
-      tmem_ld_x32(tS, rs);
-      tmem_ld_x32(tS + 32, rs + 32);
-      tmem_ld_x32(tdP, rd);
-      tmem_ld_x32(tdP + 32, rd + 32);
+      uint32_t rs[CG], rd[CG];
+#pragma unroll
+      for (int c = 0; c < CG / 32; ++c) {
+        tmem_ld_x32(tS + c * 32, rs + c * 32);
+        tmem_ld_x32(tdP + c * 32, rd + c * 32);
+      }
       tmem_ld_wait();
       warp_arrive(sd_loaded, lane);      // S / dP may be overwritten by the next block's logits
-      const int lim = (j == ib) ? row - 64 * g : 64;  // columns c > lim are keys after this query (diagonal block)
+      const int lim = (j == ib) ? row - CG * g : CG;  // columns c > lim are keys after this query (diagonal block)
       if (j >= 2) {                      // the dQ product of block j-2 has consumed this dS slot
         mbar_wait(ds_free + 8 * (j & 1), (uint32_t)((j - 2) >> 1) & 1u);
         tc_fence_after();
       }
-      const uint32_t tdS = tdSb + 64 * (j & 1) + 32 * g + lane_off;
+      const uint32_t tdS = tdSb + 64 * (j & 1) + (CG / 2) * g + lane_off;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < CG / 32; ++c) {
         uint32_t dk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
@@ -726,21 +775,22 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
       tmem_st_wait();
       warp_arrive(ds_ready + 8 * (j & 1), lane);
     }
-    // ---- epilogue: each group writes half of the dQ columns
+    // ---- epilogue: each group writes its share of the dQ columns
     mbar_wait(acc_done, 0);
     tc_fence_after();
-    bf16* dst = dqkv + ((((long long)b * S + qi) * 3 + 0) * H + h) * DH + g * (DH / 2);
+    constexpr int EG = DH / NG, W = EG >= 32 ? 32 : 16;
+    bf16* dst = dqkv + ((((long long)b * S + qi) * 3 + 0) * H + h) * DH + g * EG;
 #pragma unroll 1
-    for (int c = 0; c < DH / 64; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(tmem + lane_off + g * (DH / 2) + c * 32, r);
+    for (int c = 0; c < EG / W; ++c) {
+      uint32_t r[W];
+      tmem_ld_n<W>(tmem + lane_off + g * EG + c * W, r);
       tmem_ld_wait();
-      if (qi < S) store_row_bf16(dst + c * 32, r, 1.f);
+      if (qi < S) store_cols_bf16<W>(dst + c * W, r, 1.f);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == TMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -762,53 +812,67 @@ static int ws_o_map(CUtensorMap* tm, const void* o, int B, int S, int H, int dh)
   return make_tmap_bf16(tm, o, 4, dims, strides, box);
 }
 
-template <int DH>
+// DB200_ATTN_NG (development A/B switch, read once): number of math warpgroups per CTA, 2 or 4 (default 4)
+static int attn_ng() {
+  static const int ng = [] { const char* e = getenv("DB200_ATTN_NG"); return (e && atoi(e) == 2) ? 2 : 4; }();
+  return ng;
+}
+
+template <int DH, int NG>
 static int fwd_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H,
                            float scale) {
-  using C = FwdWs<DH>;
+  using C = FwdWs<DH, NG>;
   CUtensorMap tm;
   int rc = ws_qkv_map(&tm, qkv, B, S, H, DH);
   if (rc != DB200_OK) return rc;
-  static const cudaError_t attr = cudaFuncSetAttribute(attn_fwd_ws_kernel<DH>,
+  static const cudaError_t attr = cudaFuncSetAttribute(attn_fwd_ws_kernel<DH, NG>,
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   DB200_CUDA(attr);
   dim3 grid(((S + 127) / 128) * H * B);
-  attn_fwd_ws_kernel<DH><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, scale);
+  attn_fwd_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, scale);
   return check_launch("attn_fwd_ws_kernel");
 }
 
 int attn_fwd_ws_launch(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H, int dh,
                        float scale) {
-  if (dh == 128) return fwd_ws_launch_t<128>(stream, qkv, out, lse, B, S, H, scale);
-  return fwd_ws_launch_t<64>(stream, qkv, out, lse, B, S, H, scale);
+  if (attn_ng() == 2) {
+    if (dh == 128) return fwd_ws_launch_t<128, 2>(stream, qkv, out, lse, B, S, H, scale);
+    return fwd_ws_launch_t<64, 2>(stream, qkv, out, lse, B, S, H, scale);
+  }
+  if (dh == 128) return fwd_ws_launch_t<128, 4>(stream, qkv, out, lse, B, S, H, scale);
+  return fwd_ws_launch_t<64, 4>(stream, qkv, out, lse, B, S, H, scale);
 }
 
-template <int DH>
+template <int DH, int NG>
 static int bwd_ws_launch_t(cudaStream_t stream, const void* qkv, const void* dout, const float* lse,
                            const float* delta, void* dqkv, int B, int S, int H, float scale) {
-  using C = BwdWs<DH>;
+  using C = BwdWs<DH, NG>;
   CUtensorMap tq, to;
   int rc = ws_qkv_map(&tq, qkv, B, S, H, DH);
   if (rc == DB200_OK) rc = ws_o_map(&to, dout, B, S, H, DH);
   if (rc != DB200_OK) return rc;
-  static const cudaError_t a0 = cudaFuncSetAttribute(attn_bwd_dkdv_ws_kernel<DH>,
+  static const cudaError_t a0 = cudaFuncSetAttribute(attn_bwd_dkdv_ws_kernel<DH, NG>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-  static const cudaError_t a1 = cudaFuncSetAttribute(attn_bwd_dq_ws_kernel<DH>,
+  static const cudaError_t a1 = cudaFuncSetAttribute(attn_bwd_dq_ws_kernel<DH, NG>,
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   DB200_CUDA(a0);
   DB200_CUDA(a1);
   dim3 grid(((S + 127) / 128) * H * B);
-  attn_bwd_dkdv_ws_kernel<DH><<<grid, C::THREADS, C::SMEM, stream>>>(tq, to, lse, delta, (bf16*)dqkv, S, H, scale);
+  attn_bwd_dkdv_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tq, to, lse, delta, (bf16*)dqkv, S, H, scale);
   rc = check_launch("attn_bwd_dkdv_ws_kernel");
   if (rc != DB200_OK) return rc;
-  attn_bwd_dq_ws_kernel<DH><<<grid, C::THREADS, C::SMEM, stream>>>(tq, to, lse, delta, (bf16*)dqkv, S, H, scale);
+  attn_bwd_dq_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tq, to, lse, delta, (bf16*)dqkv, S, H, scale);
   return check_launch("attn_bwd_dq_ws_kernel");
 }
 
 int attn_bwd_ws_launch(cudaStream_t stream, const void* qkv, const void* dout, const float* lse, const float* delta,
                        void* dqkv, int B, int S, int H, int dh, float scale) {
-  if (dh == 128) return bwd_ws_launch_t<128>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
-  return bwd_ws_launch_t<64>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
+  if (attn_ng() == 2) {
+    if (dh == 128) return bwd_ws_launch_t<128, 2>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
+    return bwd_ws_launch_t<64, 2>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
+  }
+  if (dh == 128) return bwd_ws_launch_t<128, 4>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
+  return bwd_ws_launch_t<64, 4>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
 }
 
 }  // namespace db200

@@ -28,15 +28,19 @@ __global__ void embed_at_kernel(const int* __restrict__ ids, const bf16* __restr
     out[(long long)b * d + i] = __float2bfloat16(__bfloat162float(w[i]) + __bfloat162float(p[i]));
 }
 
-// one CTA per (head, batch); 128 threads.  scores live in dynamic shared memory (pos + 1 floats).
+// one CTA per (head, batch); 8 warps.  Keys are split over the warps in BOTH passes (scores, then P.V), a warp reads a
+// whole cached row per instruction (dh * 2 contiguous bytes) and keeps four rows in flight: the per-thread serial walk
+// over `pos` keys of the first version made generation latency-bound (~100 us per call at pos ~ 1000).
+// Scores live in dynamic shared memory (pos + 1 floats, or S when the position is read on the device).
 template <int DH>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 attn_decode_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc, bf16* __restrict__ out,
                    int S, int H, int pos, float scale, const int* __restrict__ pos_dev) {
   extern __shared__ float sc[];
+  __shared__ float red[8];
+  __shared__ float part[8][DH];
   if (pos_dev) pos = *pos_dev;
-  __shared__ float red[4];
-  __shared__ float qs[DH];
+  constexpr int EPL = DH / 32;  // elements per lane (4 or 2): lane l owns [l * EPL, (l + 1) * EPL) of a row
   const int h = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bf16* q = qkv + ((long long)b * 3 + 0) * H * DH + (long long)h * DH;
@@ -44,29 +48,58 @@ attn_decode_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __
   const bf16* v = qkv + ((long long)b * 3 + 2) * H * DH + (long long)h * DH;
   bf16* kcb = kc + ((long long)b * S * H + h) * DH;  // + j * H * DH
   bf16* vcb = vc + ((long long)b * S * H + h) * DH;
-  for (int t = tid; t < DH; t += 128) {
-    kcb[(long long)pos * H * DH + t] = k[t];
-    vcb[(long long)pos * H * DH + t] = v[t];
-    qs[t] = __bfloat162float(q[t]);
+  const long long rs = (long long)H * DH;            // row stride of the caches
+  for (int t = tid; t < DH; t += 256) {
+    kcb[(long long)pos * rs + t] = k[t];
+    vcb[(long long)pos * rs + t] = v[t];
   }
+  float qr[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) qr[e] = __bfloat162float(q[lane * EPL + e]);
   __syncthreads();  // this block's own global writes are visible to it after the barrier
   const int n = pos + 1;
+  auto load_row = [&](const bf16* base, int j, float* o) {
+    if (EPL == 4) {
+      const uint2 u = *reinterpret_cast<const uint2*>(base + (long long)j * rs + lane * 4);
+      const float2 a = unpack_bf16x2(u.x), c = unpack_bf16x2(u.y);
+      o[0] = a.x; o[1] = a.y; o[2] = c.x; o[3] = c.y;
+    } else {
+      const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(base + (long long)j * rs + lane * 2));
+      o[0] = a.x; o[1] = a.y;
+    }
+  };
+  // ---- scores: warp w takes keys w, w + 8, ... four at a time
   float mx = -INFINITY;
-  for (int j = warp; j < n; j += 4) {
-    const bf16* kj = kcb + (long long)j * H * DH;
-    float s = 0.f;
+  for (int j0 = warp; j0 < n; j0 += 32) {
+    float kr[4][EPL], s[4];
 #pragma unroll
-    for (int e = lane; e < DH; e += 32) s += qs[e] * __bfloat162float(kj[e]);
-    s = warp_sum(s) * scale;
-    if (lane == 0) sc[j] = s;
-    mx = fmaxf(mx, s);
+    for (int u = 0; u < 4; ++u)
+      if (j0 + 8 * u < n) load_row(kcb, j0 + 8 * u, kr[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[u] = 0.f;
+      if (j0 + 8 * u < n) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) s[u] += qr[e] * kr[u][e];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = warp_sum(s[u]) * scale;
+      if (j0 + 8 * u < n) {
+        if (lane == 0) sc[j0 + 8 * u] = t;
+        mx = fmaxf(mx, t);
+      }
+    }
   }
   if (lane == 0) red[warp] = mx;
   __syncthreads();
-  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  mx = red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
   __syncthreads();
   float sum = 0.f;
-  for (int j = tid; j < n; j += 128) {
+  for (int j = tid; j < n; j += 256) {
     const float p = __expf(sc[j] - mx);
     sum += p;
     sc[j] = __bfloat162float(__float2bfloat16(p));  // P goes through bf16 for the PV product, the sum does not
@@ -74,12 +107,35 @@ attn_decode_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __
   sum = warp_sum(sum);
   if (lane == 0) red[warp] = sum;
   __syncthreads();
-  sum = red[0] + red[1] + red[2] + red[3];
+  sum = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  // ---- P.V: warp w accumulates its keys' contributions to all dh outputs, then the 8 partials are summed
+  float acc[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) acc[e] = 0.f;
+  for (int j0 = warp; j0 < n; j0 += 32) {
+    float vr[4][EPL];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (j0 + 8 * u < n) load_row(vcb, j0 + 8 * u, vr[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (j0 + 8 * u < n) {
+        const float p = sc[j0 + 8 * u];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) acc[e] += p * vr[u][e];
+      }
+  }
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) part[warp][lane * EPL + e] = acc[e];
+  __syncthreads();
   const float inv = 1.f / sum;
-  for (int t = tid; t < DH; t += 128) {
-    float acc = 0.f;
-    for (int j = 0; j < n; ++j) acc += sc[j] * __bfloat162float(vcb[(long long)j * H * DH + t]);
-    out[((long long)b * H + h) * DH + t] = __float2bfloat16(acc * inv);
+  for (int t = tid; t < DH; t += 256) {
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) o += part[w][t];
+    out[((long long)b * H + h) * DH + t] = __float2bfloat16(o * inv);
   }
 }
 
@@ -176,11 +232,11 @@ static int attn_decode_launch(cudaStream_t stream, const void* qkv_step, void* k
   DB200_CUDA(a128);
   DB200_CUDA(a64);
   if (dh == 128)
-    attn_decode_kernel<128><<<grid, 128, smem, stream>>>(static_cast<const bf16*>(qkv_step),
+    attn_decode_kernel<128><<<grid, 256, smem, stream>>>(static_cast<const bf16*>(qkv_step),
                                                          static_cast<bf16*>(k_cache), static_cast<bf16*>(v_cache),
                                                          static_cast<bf16*>(out), S, H, pos, scale, pos_dev);
   else
-    attn_decode_kernel<64><<<grid, 128, smem, stream>>>(static_cast<const bf16*>(qkv_step), static_cast<bf16*>(k_cache),
+    attn_decode_kernel<64><<<grid, 256, smem, stream>>>(static_cast<const bf16*>(qkv_step), static_cast<bf16*>(k_cache),
                                                         static_cast<bf16*>(v_cache), static_cast<bf16*>(out), S, H, pos,
                                                         scale, pos_dev);
   return check_launch("attn_decode_kernel");

@@ -326,3 +326,17 @@ def test_tokenizer_loads_bpe_files_from_a_local_directory(tmp_path):
     import pytest
     with pytest.raises(FileNotFoundError):
         get_tokenizer(None, vocab_dir=str(tmp_path / "missing"))
+
+
+def test_bench_helpers_flop_counts_and_scaling_modes():
+    """SURVEY.md §8d figures: vae_example 4.03 GFLOP / image, vae_coco (K = 8192) 1 221.6; strong scaling keeps the
+    config's global batch (32 -> 4 per GPU at N = 8), weak scaling the per-GPU batch."""
+    import bench
+    assert abs(bench.vae_train_flops_per_image([[3, 64], [3, 128], [3, 256]], 32, 512) / 1e9 - 4.032) < 0.01
+    assert abs(bench.vae_train_flops_per_image([[2, 128], [3, 256], [5, 512]], 256, 8192) / 1e9 - 1221.6) < 0.1
+    assert bench.per_gpu_batch_for("dalle_example", 8, "weak") == 32
+    assert bench.per_gpu_batch_for("dalle_example", 8, "strong") == 4
+    p = bench.load_params(8, "dalle_example", "strong")
+    assert p["train_batch_size"] == 32 and p["mesh_shape"] == "data:8"
+    assert bench.load_params(8, "dalle_12b")["optimizer_state_sharding"] is True
+    assert len(bench.csrc_hash()) == 16

@@ -316,7 +316,11 @@ def test_causal_attention_fwd_bwd(ops, B, S, H, dh, scale, mag):
     dqkv = torch.zeros_like(qd)
     ops.attn_bwd(qd, out, dd, lse, torch.zeros(1, device=DEV), torch.zeros(B, H, S, device=DEV), dqkv, B, S, H, dh, scale)
     for i in range(3):   # P and dS are rounded to bf16 before the second products -> 2e-2
-        assert relmax(dqkv[:, :, i], qf.grad[:, :, i]) < 2e-2
+        ref = qf.grad[:, :, i]
+        if ref.abs().max() == 0:   # S = 1: one key, P = 1, dq = dk = 0 exactly; the kernels give dP - delta with O rounded
+            assert dqkv[:, :, i].float().abs().max().item() < 1e-4     # to bf16 inside delta: ~1e-6, not 0
+        else:
+            assert relmax(dqkv[:, :, i], ref) < 2e-2
 
 
 def test_attention_is_causal_at_full_size(ops):
