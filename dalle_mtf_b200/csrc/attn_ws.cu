@@ -58,14 +58,14 @@ __device__ __forceinline__ void ws_load_tile(uint32_t dst, const CUtensorMap* tm
   for (int t = 0; t < DH / 64; ++t) tma_load_4d(dst + t * T128B, tm, bar, 64 * t, chan, row0, b);
 }
 
-// K-major [128][DH] tile, K-step kk (16 elements of dh)
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile, int kk) {
-  return umma_smem_desc_sw128(tile + (kk / 4) * T128B + (kk % 4) * 32, 0, 1024);
-}
-// the same tile read as an MN-major operand (K = its 128 rows, N = dh), K-step kk (16 rows)
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile, int kk) {
-  return umma_smem_desc_sw128(tile + kk * 2048, T128B, 1024);
-}
+// UMMA shared-memory descriptors of a [128][DH] tile: built ONCE per tile, K-steps are `base + constant` (the start
+// address field holds address >> 4 and cannot overflow: shared memory ends below 256 KiB).
+//   K-major  (K = dh):                  K-step kk = 16 elements  -> (kk / 4) sub-tiles of 16 KiB + (kk % 4) * 32 bytes
+//   MN-major (K = the 128 rows, N = dh): K-step kk = 16 rows      -> kk * 2048 bytes; 64-wide N atoms are T128B apart (LBO)
+__device__ __forceinline__ uint64_t desc_k_base(uint32_t tile) { return umma_smem_desc_sw128(tile, 0, 1024); }
+__device__ __forceinline__ uint64_t desc_mn_base(uint32_t tile) { return umma_smem_desc_sw128(tile, T128B, 1024); }
+__device__ __forceinline__ constexpr uint64_t kstep_k(int kk) { return (uint64_t)((kk / 4) * (T128B >> 4) + (kk % 4) * 2); }
+__device__ __forceinline__ constexpr uint64_t kstep_mn(int kk) { return (uint64_t)(kk * 128); }
 // column of K-step kk (16 bf16 = 8 packed columns) of a TMEM A operand whose 128 K-elements are stored group by group:
 // group g's 128/NG elements sit packed at the start of its own 128/NG-column slice
 template <int NG>
@@ -136,7 +136,10 @@ struct FwdWs {
 template <int DH, int NG>
 __global__ void __launch_bounds__((4 * NG + 2) * 32, 1)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out,
-                   int S, int H, float scale) {
+                   int S, int H, float scale, int xflags) {
+#ifndef DB200_DEV_KNOBS
+  xflags = 0;  // timing experiments exist in development builds only (make DEV=1); results are wrong under them
+#endif
   using C = FwdWs<DH, NG>;
   constexpr int NK = C::NK, NV = C::NV;
   constexpr int CG = 128 / NG;       // key columns of a block per group (= per thread)
@@ -209,18 +212,26 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     }
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // The whole warp runs this loop convergently (waits, descriptor arithmetic in uniform registers); only the tensor
+    // instructions are predicated on the leader lane.
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T : both K-major (K = dh)
       constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);   // O = P V   : A from TMEM, B MN-major (K = keys)
+      const uint64_t dq = desc_k_base(sQ);
       auto issue_s = [&](int j) {
         const int sk = j % NK;
         mbar_wait(k_full + 8 * sk, (uint32_t)(j / NK) & 1u);
         tc_fence_after();
-        const uint32_t kb = sK + sk * C::TILE, tS = tmem + (j & 1) * 128;
+        const uint64_t dk = desc_k_base(sK + sk * C::TILE);
+        const uint32_t tS = tmem + (j & 1) * 128;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tS, desc_kmajor(sQ, kk), desc_kmajor(kb, kk), idesc_s, kk > 0);
-        umma_commit(s_ready + 8 * (j & 1));
-        umma_commit(k_empty + 8 * sk);
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16_ss(tS, dq + kstep_k(kk), dk + kstep_k(kk), idesc_s, kk > 0 ? 1u : 0u);
+          umma_commit(s_ready + 8 * (j & 1));
+          umma_commit(k_empty + 8 * sk);
+        }
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -230,12 +241,16 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         mbar_wait(v_full + 8 * sv, (uint32_t)(j / NV) & 1u);
         mbar_wait(p_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
         tc_fence_after();
-        const uint32_t vb = sV + sv * C::TILE, tP = tmem + (j & 1) * 128;
+        const uint64_t dv = desc_mn_base(sV + sv * C::TILE);
+        const uint32_t tP = tmem + (j & 1) * 128;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16_ts(tO, tP + ts_split_col<NG>(kk), desc_mnmajor(vb, kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(o_done);
-        umma_commit(v_empty + 8 * sv);
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ts(tO, tP + ts_split_col<NG>(kk), dv + kstep_mn(kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(o_done);
+          umma_commit(v_empty + 8 * sv);
+        }
+        __syncwarp();
         if (j + 2 < n_kv) issue_s(j + 2);  // into the buffer whose P the product above has just been queued to consume
       }
     }
@@ -252,6 +267,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       const uint32_t tS = tmem + (j & 1) * 128 + CG * g + lane_off;
       mbar_wait(s_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
+      if (xflags & 2) {  // experiment: pure hand-off chain, no softmax work at all
+        warp_arrive(p_ready + 8 * (j & 1), lane);
+        continue;
+      }
       uint32_t sv[CG];
 #pragma unroll
       for (int c = 0; c < CG / 32; ++c) tmem_ld_x32(tS + c * 32, sv + c * 32);
@@ -272,10 +291,12 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       }
       float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       float* xp = xch + (j & 1) * (NG * 128);
+      if (!(xflags & 4)) {  // (experiment bit 2: no cross-group exchange)
       xp[g * 128 + row] = mx;
       math_bar_sync<NG>();  // all groups' maxima visible; every group holds its S values in registers
 #pragma unroll
       for (int o = 1; o < NG; ++o) mx = fmaxf(mx, xp[((g + o) % NG) * 128 + row]);  // finite: key 0 is always visible
+      }
       if (j == 0) {
         m_used = mx;
       } else {
@@ -309,8 +330,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2f(fmaf(__uint_as_float(sv[c * 32 + i]), c1, -mc));
-          const float p1 = ex2f(fmaf(__uint_as_float(sv[c * 32 + i + 1]), c1, -mc));
+          float p0 = fmaf(__uint_as_float(sv[c * 32 + i]), c1, -mc);
+          float p1 = fmaf(__uint_as_float(sv[c * 32 + i + 1]), c1, -mc);
+          if (!(xflags & 1)) { p0 = ex2f(p0); p1 = ex2f(p1); }  // (experiment bit 0: no MUFU)
           l0 += p0;
           l1 += p1;
           pk[i >> 1] = pack_bf16x2(p0, p1);
@@ -323,6 +345,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     }
     // ---- epilogue: O / l -> bf16 (this group's share of the columns), lse
     float* xp = xch + (n_kv & 1) * (NG * 128);  // the parity the last block did not use
+    if (xflags & 2) m_used = 0.f;
     xp[g * 128 + row] = l_run;
     mbar_wait(o_done, (uint32_t)(n_kv - 1) & 1u);
     tc_fence_after();
@@ -458,49 +481,65 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     }
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // convergent warp: waits and descriptor arithmetic by all lanes (uniform registers), tensor instructions predicated
+    {
       constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);  // logits: both operands K-major (K = dh)
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // gradients: A from TMEM, B MN-major (K = queries)
+      const uint64_t dkk = desc_k_base(sK), dvk = desc_k_base(sV);
       auto issue_s = [&](int it) {   // S^T = K Q_i^T
         const int st = it % NA;
         mbar_wait(a_full + 8 * st, (uint32_t)(it / NA) & 1u);
         tc_fence_after();
-        const uint32_t q = sQr + st * C::TILE;
+        const uint64_t q = desc_k_base(sQr + st * C::TILE);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tST, desc_kmajor(sK, kk), desc_kmajor(q, kk), idesc_l, kk > 0);
-        umma_commit(sa_ready);
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16_ss(tST, dkk + kstep_k(kk), q + kstep_k(kk), idesc_l, kk > 0 ? 1u : 0u);
+          umma_commit(sa_ready);
+        }
+        __syncwarp();
       };
       auto issue_dp = [&](int it) {  // dP^T = V dO_i^T
         const int st = it % NB;
         mbar_wait(b_full + 8 * st, (uint32_t)(it / NB) & 1u);
         tc_fence_after();
-        const uint32_t o = sOr + st * C::TILE;
+        const uint64_t o = desc_k_base(sOr + st * C::TILE);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tdPT, desc_kmajor(sV, kk), desc_kmajor(o, kk), idesc_l, kk > 0);
-        umma_commit(sb_ready);
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16_ss(tdPT, dvk + kstep_k(kk), o + kstep_k(kk), idesc_l, kk > 0 ? 1u : 0u);
+          umma_commit(sb_ready);
+        }
+        __syncwarp();
       };
       mbar_wait(x_full, 0);
       issue_s(0);
       issue_dp(0);
       for (int it = 0; it < n_it; ++it) {
-        const uint32_t q = sQr + (it % NA) * C::TILE, o = sOr + (it % NB) * C::TILE;
+        const uint64_t q = desc_mn_base(sQr + (it % NA) * C::TILE), o = desc_mn_base(sOr + (it % NB) * C::TILE);
         const uint32_t acc = it > 0 ? 1u : 0u;
         mbar_wait(pa_ready, (uint32_t)it & 1u);
         tc_fence_after();
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i
-          umma_bf16_ts(tmem, tST + ts_split_col<NG>(kk), desc_mnmajor(o, kk), idesc_g, acc | (kk > 0));
-        umma_commit(b_empty + 8 * (it % NB));  // dO_i is free
-        if (it + 1 < n_it) issue_s(it + 1);    // runs under phase B of this block
+          for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i
+            umma_bf16_ts(tmem, tST + ts_split_col<NG>(kk), o + kstep_mn(kk), idesc_g, kk > 0 ? 1u : acc);
+          umma_commit(b_empty + 8 * (it % NB));  // dO_i is free
+        }
+        __syncwarp();
+        if (it + 1 < n_it) issue_s(it + 1);      // runs under phase B of this block
         mbar_wait(pb_ready, (uint32_t)it & 1u);
         tc_fence_after();
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
-          umma_bf16_ts(tmem + DH, tdPT + ts_split_col<NG>(kk), desc_mnmajor(q, kk), idesc_g, acc | (kk > 0));
-        umma_commit(a_empty + 8 * (it % NA));  // Q_i is free
-        if (it + 1 < n_it) issue_dp(it + 1);   // runs under phase A of the next block
+          for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
+            umma_bf16_ts(tmem + DH, tdPT + ts_split_col<NG>(kk), q + kstep_mn(kk), idesc_g, kk > 0 ? 1u : acc);
+          umma_commit(a_empty + 8 * (it % NA));  // Q_i is free
+          if (it == n_it - 1) umma_commit(acc_done);
+        }
+        __syncwarp();
+        if (it + 1 < n_it) issue_dp(it + 1);     // runs under phase A of the next block
       }
-      umma_commit(acc_done);
     }
   } else if (warp == STAT_WARP) {
     // ------------------------------------------------------------------------------------------- lse / delta stager
@@ -695,20 +734,27 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     }
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // convergent warp: waits and descriptor arithmetic by all lanes (uniform registers), tensor instructions predicated
+    {
       constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dQ = dS K : A from TMEM, B MN-major (K = keys)
+      const uint64_t dqk = desc_k_base(sQ), dok = desc_k_base(sdO);
       auto issue_l = [&](int j) {  // S = Q K_j^T, dP = dO V_j^T
         mbar_wait(a_full + 8 * (j % NA), (uint32_t)(j / NA) & 1u);
         mbar_wait(b_full + 8 * (j % NB), (uint32_t)(j / NB) & 1u);
         tc_fence_after();
-        const uint32_t k = sKr + (j % NA) * C::TILE, v = sVr + (j % NB) * C::TILE;
+        const uint64_t k = desc_k_base(sKr + (j % NA) * C::TILE), v = desc_k_base(sVr + (j % NB) * C::TILE);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tSb, desc_kmajor(sQ, kk), desc_kmajor(k, kk), idesc_l, kk > 0);
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16_ss(tSb, dqk + kstep_k(kk), k + kstep_k(kk), idesc_l, kk > 0 ? 1u : 0u);
 #pragma unroll
-        for (int kk = 0; kk < DH / 16; ++kk) umma_bf16_ss(tdPb, desc_kmajor(sdO, kk), desc_kmajor(v, kk), idesc_l, kk > 0);
-        umma_commit(sd_ready);
-        umma_commit(b_empty + 8 * (j % NB));  // V_j is free as soon as dP has consumed it
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16_ss(tdPb, dok + kstep_k(kk), v + kstep_k(kk), idesc_l, kk > 0 ? 1u : 0u);
+          umma_commit(sd_ready);
+          umma_commit(b_empty + 8 * (j % NB));  // V_j is free as soon as dP has consumed it
+        }
+        __syncwarp();
       };
       mbar_wait(x_full, 0);
       issue_l(0);
@@ -719,14 +765,18 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
         }
         mbar_wait(ds_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
         tc_fence_after();
-        const uint32_t k = sKr + (j % NA) * C::TILE, tdS = tdSb + 64 * (j & 1);
+        const uint64_t k = desc_mn_base(sKr + (j % NA) * C::TILE);
+        const uint32_t tdS = tdSb + 64 * (j & 1);
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_bf16_ts(tmem, tdS + kk * 8, desc_mnmajor(k, kk), idesc_g, (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(a_empty + 8 * (j % NA));  // K_j is free
-        umma_commit(ds_free + 8 * (j & 1));
+          for (int kk = 0; kk < 8; ++kk)
+            umma_bf16_ts(tmem, tdS + kk * 8, k + kstep_mn(kk), idesc_g, (j > 0 || kk > 0) ? 1u : 0u);
+          umma_commit(a_empty + 8 * (j % NA));  // K_j is free
+          umma_commit(ds_free + 8 * (j & 1));
+          if (j == n_it - 1) umma_commit(acc_done);
+        }
+        __syncwarp();
       }
-      umma_commit(acc_done);
     }
   } else if (warp < 4 * NG) {
     // ------------------------------------------------------------------------------------------- gradient warpgroups
@@ -829,7 +879,8 @@ static int fwd_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, floa
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   DB200_CUDA(attr);
   dim3 grid(((S + 127) / 128) * H * B);
-  attn_fwd_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, scale);
+  static const int xflags = [] { const char* e = getenv("DB200_ATTN_EXP"); return e ? atoi(e) : 0; }();  // DEV builds only
+  attn_fwd_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, scale, xflags);
   return check_launch("attn_fwd_ws_kernel");
 }
 

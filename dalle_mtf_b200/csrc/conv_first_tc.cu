@@ -118,17 +118,18 @@ conv_first_tc_kernel(const float* __restrict__ x, const float* __restrict__ w, c
     fence_proxy_async_smem();  // generic-proxy stores -> visible to tcgen05.mma (async proxy)
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
+      const uint64_t dh = umma_smem_desc_sw128(sAh, 0, 1024), dl = umma_smem_desc_sw128(sAl, 0, 1024);
+      const uint64_t db = umma_smem_desc_sw128(sB, 0, 1024);
+      if (elect_one_sync()) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16_ss(tmem, umma_smem_desc_sw128(sAh + kk * 32, 0, 1024), umma_smem_desc_sw128(sB + kk * 32, 0, 1024),
-                     idesc, kk > 0);
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem, dh + 2u * kk, db + 2u * kk, idesc, kk > 0);
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk)
-        umma_bf16_ss(tmem, umma_smem_desc_sw128(sAl + kk * 32, 0, 1024), umma_smem_desc_sw128(sB + kk * 32, 0, 1024),
-                     idesc, 1u);
-      umma_commit(bar);
+        for (int kk = 0; kk < 4; ++kk) umma_bf16_ss(tmem, dl + 2u * kk, db + 2u * kk, idesc, 1u);
+        umma_commit(bar);
+      }
+      __syncwarp();
     }
     mbar_wait(bar, phase);
     phase ^= 1u;

@@ -110,7 +110,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int nkb = p.ntaps * p.kchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    // converged producer warp; elect.sync picks the lane that issues the TMA instructions (uniform-datapath code, no
+    // per-lane waterfall around each UTMALDG)
+    {
       const CUtensorMap* maps[4] = {&tmA0, &tmA1, &tmA2, &tmA3};
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -120,6 +122,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(empty_bar + 8 * stage, phase ^ 1);
             const uint32_t fb = full_bar + 8 * stage;
+            if (elect_one_sync()) {
             mbar_expect_tx(fb, Cfg::STAGE_BYTES);
             tma_load_4d(sA + stage * CT_A_BYTES, maps[tp.map], fb, kc * 64, t.ox0 + tp.dx, t.oy0 + tp.dy, t.n0);
             const uint32_t b_dst = sB + stage * Cfg::B_BYTES;
@@ -132,6 +135,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               for (int s = 0; s < BN / 64; ++s)
                 tma_load_2d(b_dst + s * CT_SLAB, &tmB, fb, t.c_blk * BN + 64 * s, tp.wrow + kc * 64);
             }
+            }  // elect
+            __syncwarp();
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -147,15 +152,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(full_bar + 8 * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_base = sA + stage * CT_A_BYTES, b_base = sB + stage * Cfg::B_BYTES;
+        const uint32_t a_base = sA + stage * CT_A_BYTES, b_base = sB + stage * Cfg::B_BYTES;
+        const uint64_t ad0 = umma_smem_desc_sw128(a_base, 0, 1024);
+        const uint64_t bd0 = p.b_kmajor ? umma_smem_desc_sw128(b_base, 0, 1024) : umma_smem_desc_sw128(b_base, CT_SLAB, 1024);
+        const uint64_t bstep = p.b_kmajor ? 2u : 128u;      // (32 B | 2 KiB) >> 4 per 16-deep K-step
+        if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t bdesc = p.b_kmajor ? umma_smem_desc_sw128(b_base + k * 32, 0, 1024)
-                                              : umma_smem_desc_sw128(b_base + k * 2048, CT_SLAB, 1024);
-            umma_bf16_ss(d_tmem, umma_smem_desc_sw128(a_base + k * 32, 0, 1024), bdesc, idesc,
-                         (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(d_tmem, ad0 + 2u * k, bd0 + bstep * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar + 8 * stage);
           if (kb == nkb - 1) umma_commit(tfull_bar + 8 * acc);
         }
@@ -431,7 +435,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_cons
 
   if (pt1 > pt0) {
     if (warp == 0) {
-      if (lane == 0) {
+      {
         const CUtensorMap* pm[4] = {&tmP0, &tmP1, &tmP2, &tmP3};
         const CUtensorMap* qm[4] = {&tmQ0, &tmQ1, &tmQ2, &tmQ3};
         uint32_t stage = 0, phase = 0;
@@ -442,11 +446,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_cons
           const int n0 = t * p.TN;
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
-          mbar_expect_tx(fb, Cfg::STAGE_BYTES);
           const uint32_t a_dst = sA + stage * Cfg::A_BYTES, b_dst = sB + stage * Cfg::B_BYTES;
-          // rank-5 maps {64 ch, W, H, N, C/64}: all 64-channel slabs of the operand in one TMA op
-          tma_load_5d(a_dst, pm[tp.pmap], fb, 0, ox0 + tp.pdx, oy0 + tp.pdy, n0, a_blk * 2);
-          tma_load_5d(b_dst, qm[tp.qmap], fb, 0, ox0 + tp.qdx, oy0 + tp.qdy, n0, b_blk * (BN / 64));
+          if (elect_one_sync()) {
+            mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+            // rank-5 maps {64 ch, W, H, N, C/64}: all 64-channel slabs of the operand in one TMA op
+            tma_load_5d(a_dst, pm[tp.pmap], fb, 0, ox0 + tp.pdx, oy0 + tp.pdy, n0, a_blk * 2);
+            tma_load_5d(b_dst, qm[tp.qmap], fb, 0, ox0 + tp.qdx, oy0 + tp.qdy, n0, b_blk * (BN / 64));
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -456,12 +463,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmP0, const __grid_cons
       for (int pt = pt0; pt < pt1; ++pt) {
         mbar_wait(full_bar + 8 * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_base = sA + stage * Cfg::A_BYTES, b_base = sB + stage * Cfg::B_BYTES;
+        const uint32_t a_base = sA + stage * Cfg::A_BYTES, b_base = sB + stage * Cfg::B_BYTES;
+        const uint64_t ad0 = umma_smem_desc_sw128(a_base, 128 * 128, 1024), bd0 = umma_smem_desc_sw128(b_base, 128 * 128, 1024);
+        if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)  // 16 pixels per MMA; 64-channel atoms are 16 KiB apart
-            umma_bf16_ss(tmem_base, umma_smem_desc_sw128(a_base + k * 2048, 128 * 128, 1024),
-                         umma_smem_desc_sw128(b_base + k * 2048, 128 * 128, 1024), idesc, (pt > pt0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)  // 16 pixels (2 KiB) per MMA; 64-channel atoms are 16 KiB apart
+            umma_bf16_ss(tmem_base, ad0 + 128u * k, bd0 + 128u * k, idesc, (pt > pt0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar + 8 * stage);
           if (pt == pt1 - 1) umma_commit(done_bar);
         }

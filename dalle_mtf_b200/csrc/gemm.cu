@@ -78,7 +78,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // converged warp, issuer picked by elect.sync (see gemm2.cu): TMA instructions compile to plain uniform-datapath code
+    {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile);
@@ -86,6 +87,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb = full_bar + 8 * stage;
+          if (elect_one_sync()) {
           mbar_expect_tx(fb, Cfg::STAGE_BYTES);
           const int k0 = kb * BK;
           const uint32_t a_dst = sA + stage * A_BYTES;
@@ -106,6 +108,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_2d(b_dst, &tmB, fb, k0, n0);
           }
+          }  // elect
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -122,19 +126,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = t.kb0; kb < t.kb1; ++kb) {
         mbar_wait(full_bar + 8 * stage, phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_base = sA + stage * A_BYTES;
-          const uint32_t b_base = sB + stage * Cfg::B_BYTES;
+        // K-major: a K-step advances 16 elements (32 B) inside the 128 B swizzle row; MN-major: 16 k-rows (2 KiB), 64-wide
+        // MN atoms are SLAB_BYTES apart (LBO).  One descriptor base per operand tile + a constant per K-step, all in
+        // uniform registers; the issuing lane is picked by elect.sync.
+        const uint32_t a_base = sA + stage * A_BYTES;
+        const uint32_t b_base = sB + stage * Cfg::B_BYTES;
+        const uint64_t ad0 = p.a_mn ? umma_smem_desc_sw128(a_base, SLAB_BYTES, 1024) : umma_smem_desc_sw128(a_base, 0, 1024);
+        const uint64_t bd0 = p.b_mn ? umma_smem_desc_sw128(b_base, SLAB_BYTES, 1024) : umma_smem_desc_sw128(b_base, 0, 1024);
+        const uint64_t astep = p.a_mn ? 128u : 2u, bstep = p.b_mn ? 128u : 2u;
+        if (elect_one_sync()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major: advance 16 elements (32 B) inside the 128 B swizzle row.
-            // MN-major: advance 16 k-rows (2 KiB); 64-wide MN atoms are SLAB_BYTES apart (LBO).
-            const uint64_t adesc = p.a_mn ? umma_smem_desc_sw128(a_base + k * 2048, SLAB_BYTES, 1024)
-                                          : umma_smem_desc_sw128(a_base + k * 32, 0, 1024);
-            const uint64_t bdesc = p.b_mn ? umma_smem_desc_sw128(b_base + k * 2048, SLAB_BYTES, 1024)
-                                          : umma_smem_desc_sw128(b_base + k * 32, 0, 1024);
-            umma_bf16_ss(d_tmem, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16_ss(d_tmem, ad0 + k * astep, bd0 + k * bstep, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar + 8 * stage);                  // frees the smem slot when these MMAs retire
           if (kb == t.kb1 - 1) umma_commit(tfull_bar + 8 * acc);  // accumulator complete -> epilogue
         }

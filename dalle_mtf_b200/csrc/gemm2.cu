@@ -147,7 +147,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    // The warp stays converged (every lane waits on the barrier); the TMA instructions are issued by the lane
+    // elect.sync picks — ptxas then emits them as plain uniform-datapath instructions instead of a lane-by-lane
+    // "waterfall" loop around each one (what `if (lane == 0)` around the whole loop compiled to).
+    {
       uint32_t stage = 0, phase = 0;
       for (int tile = cid; tile < total_tiles; tile += n_clusters) {
         const Tile2 t = decode_tile2(p, m_tiles2, tile);
@@ -155,10 +158,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t fb_leader = (full_bar + 8 * stage) & PEER_MASK;
-          if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * G2_STAGE);  // bytes of both CTAs land on this barrier
           const int k0 = kb * BK;
           const uint32_t a_dst = sA + stage * G2_A_BYTES;
           const uint32_t b_dst = sB + stage * G2_B_BYTES;
+          if (elect_one_sync()) {
+          if (leader) mbar_expect_tx(full_bar + 8 * stage, 2 * G2_STAGE);  // bytes of both CTAs land on this barrier
           if (p.a_3d) {
             tma_load_3d_2sm(a_dst, &tmA, fb_leader, 0, k0, m0 >> 6);
           } else if (p.a_mn) {
@@ -175,6 +179,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           } else {
             tma_load_2d_2sm(b_dst, &tmB, fb_leader, k0, n0);
           }
+          }  // elect
+          __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -192,17 +198,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = t.kb0; kb < t.kb1; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_base = sA + stage * G2_A_BYTES;
-            const uint32_t b_base = sB + stage * G2_B_BYTES;
+          // descriptors = one base per operand tile + a constant per K-step (16 elements: 32 bytes inside the swizzle
+          // row for K-major, 16 k-rows = 2 KiB for MN-major), all in uniform registers; elect.sync picks the issuer
+          const uint32_t a_base = sA + stage * G2_A_BYTES;
+          const uint32_t b_base = sB + stage * G2_B_BYTES;
+          const uint64_t ad0 = p.a_mn ? umma_smem_desc_sw128(a_base, SLAB_BYTES, 1024) : umma_smem_desc_sw128(a_base, 0, 1024);
+          const uint64_t bd0 = p.b_mn ? umma_smem_desc_sw128(b_base, SLAB_BYTES, 1024) : umma_smem_desc_sw128(b_base, 0, 1024);
+          const uint64_t astep = p.a_mn ? 128u : 2u, bstep = p.b_mn ? 128u : 2u;
+          if (elect_one_sync()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-              const uint64_t adesc = p.a_mn ? umma_smem_desc_sw128(a_base + k * 2048, SLAB_BYTES, 1024)
-                                            : umma_smem_desc_sw128(a_base + k * 32, 0, 1024);
-              const uint64_t bdesc = p.b_mn ? umma_smem_desc_sw128(b_base + k * 2048, SLAB_BYTES, 1024)
-                                            : umma_smem_desc_sw128(b_base + k * 32, 0, 1024);
-              umma_bf16_ss_2sm(d_tmem, adesc, bdesc, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
-            }
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ss_2sm(d_tmem, ad0 + k * astep, bd0 + k * bstep, idesc, (kb > t.kb0 || k > 0) ? 1u : 0u);
             umma_commit_2sm_mc(empty_bar + 8 * stage);
             if (kb == t.kb1 - 1) umma_commit_2sm_mc(tfull_bar + 8 * acc);
           }

@@ -150,6 +150,21 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// elect.sync: true in exactly one (the lowest active) lane of a converged warp.  ptxas recognises the pattern and emits a
+// single ELECT + predicated / uniformly-branched code for the guarded block — unlike `lane == 0`, which it must treat as
+// an arbitrary per-thread predicate (a lane-by-lane "waterfall" loop around every uniform-datapath instruction).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred)
+      :
+      : "memory");
+  return pred != 0;
+}
+
 // Arrive (once) on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 // Implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

@@ -10,7 +10,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdalle_b200.so")
+# DB200_LIB: load another build of the library (development: `make DEV=1 LIB=../libdalle_b200_dev.so`)
+LIB_PATH = os.environ.get("DB200_LIB") or os.path.join(_HERE, "libdalle_b200.so")
 
 c_int = ctypes.c_int
 c_i64 = ctypes.c_int64
