@@ -10,33 +10,9 @@
 // padding SAME); codebook matmuls src/vae_tf/models.py:118,127 reuse the same kernels with a 1x1 geometry.
 #include "common.cuh"
 #include "ptx.cuh"
+#include "conv_params.cuh"
 
 namespace db200 {
-
-constexpr int MAX_TAPS = 16;
-
-struct Tap {
-  int dy, dx;       // source pixel = (oy*in_stride + dy, ox*in_stride + dx)
-  long long w_off;  // element offset of this tap's [K][N] slab in the weight tensor
-};
-
-struct ConvGemmParams {
-  int NB, OH, OW;          // enumeration grid of output pixels (M = NB*OH*OW)
-  int out_H, out_W;        // spatial dims of the output tensor
-  int out_stride, oa, ob;  // output pixel = (oy*out_stride + oa, ox*out_stride + ob)
-  int in_H, in_W, in_stride;
-  int K, Nn;               // channels contracted / produced
-  int ntaps;
-  Tap taps[MAX_TAPS];
-  long long w_k_stride, w_n_stride;
-  const void* x;
-  const float* w;
-  const float* bias;
-  const void* residual;  // same layout/dtype as y
-  const void* mask;      // same layout/dtype as y: y *= (mask > 0)
-  void* y;
-  int relu;
-};
 
 template <typename T> __device__ __forceinline__ float ldf(const T* p);
 template <> __device__ __forceinline__ float ldf<float>(const float* p) { return *p; }
@@ -145,22 +121,6 @@ conv_gemm_kernel(const ConvGemmParams p) {
     }
   }
 }
-
-struct WgradTap {
-  int pdy, pdx, qdy, qdx;
-  long long w_off;
-};
-struct ConvWgradParams {
-  int NB, OH, OW;  // enumeration grid (contracted)
-  int pH, pW, pC, p_stride;
-  int qH, qW, qC, q_stride;
-  int ntaps, splits;
-  WgradTap taps[MAX_TAPS];
-  long long a_stride, b_stride;
-  const void* P;
-  const void* Q;
-  float* dw;
-};
 
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -325,8 +285,18 @@ conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
   }
 }
 
+#ifdef DB200_DEV_KNOBS
+static bool f32_fma_only() {   // development A/B switch: keep fp32 convolutions on the CUDA-core kernels
+  static const bool v = [] { const char* e = getenv("DB200_CONV_F32_FMA"); return e && atoi(e) != 0; }();
+  return v;
+}
+#else
+static bool f32_fma_only() { return false; }
+#endif
+
 static int launch_gemm(cudaStream_t stream, const ConvGemmParams& p, bool act_f32) {
   const long long M = (long long)p.NB * p.OH * p.OW;
+  if (act_f32 && !f32_fma_only() && conv_gemm_f32_tc_ok(p)) return conv_gemm_f32_tc_launch(stream, p);
   dim3 grid((unsigned)((M + 63) / 64), (unsigned)((p.Nn + 63) / 64));
   if (act_f32) conv_gemm_kernel<float><<<grid, 256, 0, stream>>>(p);
   else         conv_gemm_kernel<bf16><<<grid, 256, 0, stream>>>(p);
@@ -431,7 +401,7 @@ static int launch_wgrad(cudaStream_t stream, ConvWgradParams& p, bool act_f32) {
     DB200_REQUIRE(M < (1ll << 31), DB200_E_UNSUPPORTED, "conv2d_wgrad: more than 2^31 pixels");
     const int cblocks = (q.wC + 63) / 64;
     int splits = (sm_count() * 8 + cblocks - 1) / cblocks;
-    const long long max_splits = (M + 1023) / 1024;
+    const long long max_splits = (M + 127) / 128;   // >= 32 pixels per lane group
     if (splits > max_splits) splits = (int)max_splits;
     if (splits < 1) splits = 1;
     q.splits = splits;
@@ -440,6 +410,7 @@ static int launch_wgrad(cudaStream_t stream, ConvWgradParams& p, bool act_f32) {
     else         conv_wgrad_skinny_kernel<bf16><<<grid, 256, 0, stream>>>(q);
     return check_launch("conv_wgrad_skinny_kernel");
   }
+  if (act_f32 && !f32_fma_only() && conv_wgrad_f32_tc_ok(p)) return conv_wgrad_f32_tc_launch(stream, p);
   const long long M = (long long)p.NB * p.OH * p.OW;
   const int tiles = ((p.pC + 63) / 64) * ((p.qC + 63) / 64) * p.ntaps;
   int splits = (sm_count() * 4 + tiles - 1) / tiles;

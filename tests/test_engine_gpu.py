@@ -123,7 +123,11 @@ def test_dalle_class_mirrors_reference_forward_signature():
 # ------------------------------------------------------------------------------------------------------- VAE
 @pytest.mark.parametrize("N,H,Cin,Cout,k,stride,transposed", [
     (2, 8, 16, 24, 3, 1, False), (2, 9, 5, 70, 3, 1, False), (2, 8, 3, 32, 4, 2, False), (3, 12, 20, 36, 4, 2, False),
-    (2, 6, 24, 16, 4, 2, True), (1, 5, 70, 9, 4, 2, True), (2, 8, 16, 3, 1, 1, False)])
+    (2, 6, 24, 16, 4, 2, True), (1, 5, 70, 9, 4, 2, True), (2, 8, 16, 3, 1, 1, False),
+    # channel counts that are multiples of 64 run on tcgen05 through the three-way bf16 split (conv_f32_tc.cu)
+    (2, 8, 64, 64, 3, 1, False), (3, 9, 128, 64, 3, 1, False), (2, 8, 64, 128, 4, 2, False),
+    (2, 6, 128, 64, 4, 2, True), (1, 4, 256, 256, 3, 1, False), (2, 8, 64, 512, 1, 1, False),
+    (5, 16, 64, 64, 3, 1, False)])
 def test_direct_conv_fwd_dgrad_wgrad_fp32(N, H, Cin, Cout, k, stride, transposed):
     from dalle_mtf_b200 import ops
     from oracle import vae as OV
