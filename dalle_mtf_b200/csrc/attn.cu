@@ -1,4 +1,4 @@
-// K4 — causal flash attention, forward and backward, on tcgen05 / TMEM for sm_100a.
+// K4 — causal flash attention, forward and backward: the C-ABI entry points and the row-wise delta pre-pass.
 //
 // Replaces mtf_transformer.attention.attention + the [S,S] additive -1e10 mask the reference materialises
 // (src/dalle_mtf/models.py:221-227, 287-299).  Logits are fp32 (TMEM accumulators), softmax is fp32, P is rounded to
@@ -8,254 +8,17 @@
 // Layout: qkv bf16 [B][S][3][H][dh] (the fused q|k|v projection output), out / dout bf16 [B][S][H][dh],
 //         lse f32 [B][H][S] (natural log of sum exp(scale*s)), dqkv like qkv.
 //
-// Design (all three kernels): 256 threads; threads t and t+128 share TMEM lane t (= one query row of the 128-row tile,
-// or one key row of the dK/dV accumulators) and each handle half of its columns.  Operand tiles are brought by TMA as [rows][64] bf16 sub-tiles with the
-// 128-byte swizzle, which serves both as a K-major UMMA operand (K = head dim) and as an MN-major one (K = rows), so
-// Q, K, V, dO are each loaded once and used for every product they appear in.  P / dS are written by the softmax
-// threads straight into the same swizzled layout and consumed by the next tcgen05.mma.
-//   fwd      : CTA per (q block, head, batch), loop over kv blocks; S and P.V products in TMEM, running max/sum
-//              and the output accumulator in registers.  2 CTAs/SM overlap one CTA's softmax with the other's MMAs.
-//   bwd dK/dV: CTA per (kv block, head, batch), loop over q blocks >= kv block; dV += P^T dO, dK += dS^T Q in TMEM.
-//   bwd dQ   : CTA per (q block, head, batch), loop over kv blocks <= q block; dQ += dS K in TMEM (no atomics).
-#include <cstdlib>
-
+// The kernels are the warp-specialised ones of attn_ws.cu (TMA warp, MMA-issuer warp, softmax warpgroups, P / dS handed
+// over through TMEM); this file validates the arguments, runs delta = rowsum(dO * O) and launches them.
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace db200 {
 
-constexpr float LOG2E = 1.4426950408889634f;
-
-// MUFU.EX2 directly (exp2f() adds range handling the softmax does not need: arguments are <= 0 or the result is
-// masked / multiplied by 0).  ex2.approx(-inf) = +0.
-__device__ __forceinline__ float ex2(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-// Load a [ROWS][DH] tile (DH/64 swizzled sub-tiles of ROWS*128 bytes) from a rank-4 map {dh, chan, seq, batch}.
-template <int DH>
-__device__ __forceinline__ void tma_prefetch_tile(const CUtensorMap* tm, int chan, int row0, int b) {
-#pragma unroll
-  for (int t = 0; t < DH / 64; ++t) tma_prefetch_4d(tm, 64 * t, chan, row0, b);
-}
-
-template <int DH>
-__device__ __forceinline__ void tma_load_tile(uint32_t dst, uint32_t rows_bytes, const CUtensorMap* tm, uint32_t bar,
-                                              int chan, int row0, int b) {
-#pragma unroll
-  for (int t = 0; t < DH / 64; ++t) tma_load_4d(dst + t * rows_bytes, tm, bar, 64 * t, chan, row0, b);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// forward
-// ------------------------------------------------------------------------------------------------------------------
-template <int DH>
-struct FwdCfg {
-  static constexpr int BNK = (DH == 128) ? 64 : 128;  // keys per inner block (keeps smem <= ~80 KiB -> 2 CTAs/SM)
-  static constexpr uint32_t Q_BYTES = 128 * DH * 2;
-  static constexpr uint32_t KV_BYTES = BNK * DH * 2;
-  static constexpr uint32_t P_BYTES = 128 * BNK * 2;
-  static constexpr size_t SMEM = 1024 + Q_BYTES + 2 * KV_BYTES + P_BYTES + 64 + 2 * 128 * 4 + 64;
-};
-
-template <int DH>
-__global__ void __launch_bounds__(256, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                bf16* __restrict__ out, float* __restrict__ lse_out, int S, int H, float scale) {
-  using C = FwdCfg<DH>;
-  constexpr int BNK = C::BNK;
-  constexpr int HC = BNK / 2;  // key columns of S handled by one thread (two threads share a query row)
-  constexpr int HD = DH / 2;   // output columns accumulated by one thread
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sQ = base, sK = sQ + C::Q_BYTES, sV = sK + C::KV_BYTES, sP = sV + C::KV_BYTES;
-  const uint32_t bars = sP + C::P_BYTES;
-  const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16, bar_s = bars + 24, bar_o = bars + 32;
-  const uint32_t tmem_slot = bars + 40;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-  float* xch = reinterpret_cast<float*>(smem_raw + (bars + 64 - raw));  // [2][128] row-max exchange
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int rowi = tid & 127, half = tid >> 7;  // TMEM lane (query row in the tile), column half
-  const int qb = gridDim.x - 1 - blockIdx.x;    // heavy (late) query blocks first
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qb * 128;
-  const int kv_len = min(S, q0 + 128);
-  const int n_kv = (kv_len + BNK - 1) / BNK;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmKV);
-    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_s, 1); mbar_init(bar_o, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot_ptr;
-  const uint32_t tS = tmem, tO = tmem + 128;
-  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
-
-  if (tid == 0) {
-    mbar_expect_tx(bar_q, C::Q_BYTES);
-    tma_load_tile<DH>(sQ, 128 * 128, &tmQ, bar_q, /*chan=*/0 * H + h, q0, b);
-    mbar_expect_tx(bar_k, C::KV_BYTES);
-    tma_load_tile<DH>(sK, BNK * 128, &tmKV, bar_k, 1 * H + h, 0, b);
-    mbar_expect_tx(bar_v, C::KV_BYTES);
-    tma_load_tile<DH>(sV, BNK * 128, &tmKV, bar_v, 2 * H + h, 0, b);
-  }
-
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, BNK, 0, 0);  // S = Q K^T : both K-major (K = dh)
-  constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);   // O = P V   : A K-major (K = keys), B MN-major
-
-  const int qi = q0 + rowi;  // this thread's query index
-  const float c1 = scale * LOG2E;
-  float m_run = -INFINITY, l_run = 0.f;  // l_run: partial sum over this thread's key columns
-  float o_acc[HD];
-#pragma unroll
-  for (int e = 0; e < HD; ++e) o_acc[e] = 0.f;
-
-  mbar_wait(bar_q, 0);
-
-  for (int j = 0; j < n_kv; ++j) {
-    const uint32_t ph = j & 1;
-    if (tid == 0) {
-      mbar_wait(bar_k, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk) {
-        const uint64_t ad = umma_smem_desc_sw128(sQ + (kk / 4) * (128 * 128) + (kk % 4) * 32, 0, 1024);
-        const uint64_t bd = umma_smem_desc_sw128(sK + (kk / 4) * (BNK * 128) + (kk % 4) * 32, 0, 1024);
-        umma_bf16_ss(tS, ad, bd, idesc_s, kk > 0);
-      }
-      umma_commit(bar_s);
-    }
-    mbar_wait(bar_s, ph);
-    tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {  // K buffer is free: prefetch the next key block under the softmax
-      mbar_expect_tx(bar_k, C::KV_BYTES);
-      tma_load_tile<DH>(sK, BNK * 128, &tmKV, bar_k, 1 * H + h, (j + 1) * BNK, b);
-    }
-    // ---- softmax: this thread's half of the row, kept in registers
-    const int k0 = j * BNK + half * HC;
-    const bool need_mask = (j * BNK + BNK - 1) > q0;
-    float sv[HC];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int c = 0; c < HC / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(tS + lane_off + half * HC + c * 32, r);
-      tmem_ld_wait();
-      if (need_mask && (k0 + c * 32 + 31) > qi) {  // chunk crosses the diagonal
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[i]);
-          if ((k0 + c * 32 + i) > qi) s = -INFINITY;
-          sv[c * 32 + i] = s;
-          mx = fmaxf(mx, s);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(r[i]);
-          sv[c * 32 + i] = s;
-          mx = fmaxf(mx, s);
-        }
-      }
-    }
-    xch[half * 128 + rowi] = mx;
-    tc_fence_before();
-    __syncthreads();  // (1) both halves' maxima visible; every thread has finished reading S from TMEM
-    const float m_new = fmaxf(m_run, fmaxf(mx, xch[(half ^ 1) * 128 + rowi]));  // finite: key 0 is always visible
-    const float alpha = ex2((m_run - m_new) * c1);
-    const float mc = m_new * c1;
-    float lsum = 0.f;
-#pragma unroll
-    for (int c = 0; c < HC / 32; ++c) {
-      uint32_t pk[16];
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2(fmaf(sv[c * 32 + i], c1, -mc)), p1 = ex2(fmaf(sv[c * 32 + i + 1], c1, -mc));  // ex2(-inf) = 0
-        lsum += p0 + p1;
-        pk[i >> 1] = pack_bf16x2(p0, p1);
-      }
-      const int col = half * HC + c * 32;  // column inside the [128][BNK] P tile
-      const uint32_t sub = sP + (col / 64) * (128 * 128);
-      const int cc = col % 64;
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        st_shared_v4(sub + sw128_offset(rowi, cc + g * 8), pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-    }
-    l_run = l_run * alpha + lsum;
-    m_run = m_new;
-    fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to tcgen05.mma (async proxy)
-    __syncthreads();           // (2) P complete
-    // ---- O_j = P V_j  (fresh accumulator; the running output lives in registers)
-    if (tid == 0) {
-      mbar_wait(bar_v, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < BNK / 16; ++kk) {
-        const uint64_t ad = umma_smem_desc_sw128(sP + (kk / 4) * (128 * 128) + (kk % 4) * 32, 0, 1024);
-        const uint64_t bd = umma_smem_desc_sw128(sV + kk * 2048, BNK * 128, 1024);
-        umma_bf16_ss(tO, ad, bd, idesc_o, kk > 0);
-      }
-      umma_commit(bar_o);
-    }
-#pragma unroll
-    for (int e = 0; e < HD; ++e) o_acc[e] *= alpha;
-    mbar_wait(bar_o, ph);
-    tc_fence_after();
-    if (tid == 0 && j + 1 < n_kv) {
-      mbar_expect_tx(bar_v, C::KV_BYTES);
-      tma_load_tile<DH>(sV, BNK * 128, &tmKV, bar_v, 2 * H + h, (j + 1) * BNK, b);
-    }
-#pragma unroll
-    for (int c = 0; c < HD / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(tO + lane_off + half * HD + c * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] += __uint_as_float(r[i]);
-    }
-    tc_fence_before();
-    __syncthreads();  // (3) O consumed before the next iteration's MMAs overwrite S / O; xch reusable
-    tc_fence_after();
-  }
-
-  // combine the two halves' partial row sums
-  xch[half * 128 + rowi] = l_run;
-  __syncthreads();
-  const float l_tot = l_run + xch[(half ^ 1) * 128 + rowi];
-  if (qi < S) {
-    const float inv = 1.f / l_tot;
-    bf16* op = out + (((long long)b * S + qi) * H + h) * DH + half * HD;
-#pragma unroll
-    for (int e = 0; e < HD; e += 8) {
-      uint4 q;
-      q.x = pack_bf16x2(o_acc[e] * inv, o_acc[e + 1] * inv);
-      q.y = pack_bf16x2(o_acc[e + 2] * inv, o_acc[e + 3] * inv);
-      q.z = pack_bf16x2(o_acc[e + 4] * inv, o_acc[e + 5] * inv);
-      q.w = pack_bf16x2(o_acc[e + 6] * inv, o_acc[e + 7] * inv);
-      *reinterpret_cast<uint4*>(op + e) = q;
-    }
-    if (half == 0) lse_out[((long long)b * H + h) * S + qi] = m_run * scale + logf(l_tot);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 256);
-  }
-}
+int attn_fwd_ws_launch(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H, int dh,
+                       float scale);
+int attn_bwd_ws_launch(cudaStream_t stream, const void* qkv, const void* dout, const float* lse, const float* delta,
+                       void* dqkv, int B, int S, int H, int dh, float scale);
 
 // ------------------------------------------------------------------------------------------------------------------
 // backward: delta = rowsum(dO * O)
@@ -292,420 +55,6 @@ attn_delta_kernel(const bf16* __restrict__ o, const bf16* __restrict__ dout, flo
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// backward shared piece: from S and dP in TMEM build P and dS (bf16, swizzled [128 q rows][128 keys]) in smem.
-//   p  = exp(scale*s - lse)            (0 where key > query, or the query row is out of range)
-//   ds = p * (dp - delta) * scale
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bwd_make_p_ds(uint32_t tS, uint32_t tdP, uint32_t lane_off, uint32_t sP, uint32_t sdS,
-                                              bool write_p, int rowi, int half, int qi, int k0, bool need_mask,
-                                              bool row_ok, float lse_l2, float delta, float c1, float scale) {
-  // two threads share a query row: `half` selects key columns [64*half, 64*half + 64) = sub-tile `half`
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    const int col0 = half * 64 + c * 32;
-    uint32_t rs[32], rd[32];
-    tmem_ld_x32(tS + lane_off + col0, rs);
-    tmem_ld_x32(tdP + lane_off + col0, rd);
-    tmem_ld_wait();
-    uint32_t pk[16], dk[16];
-    if (!row_ok) {  // out-of-range query row: contributes nothing
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = dk[i] = 0u;
-    } else if (need_mask && (k0 + col0 + 31) > qi) {  // chunk crosses the diagonal: per-element causal mask
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        float p0 = ex2(fmaf(__uint_as_float(rs[i]), c1, -lse_l2));
-        float p1 = ex2(fmaf(__uint_as_float(rs[i + 1]), c1, -lse_l2));
-        if ((k0 + col0 + i) > qi) p0 = 0.f;
-        if ((k0 + col0 + i + 1) > qi) p1 = 0.f;
-        pk[i >> 1] = pack_bf16x2(p0, p1);
-        dk[i >> 1] = pack_bf16x2((p0 * scale) * (__uint_as_float(rd[i]) - delta),
-                                 (p1 * scale) * (__uint_as_float(rd[i + 1]) - delta));
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 32; i += 2) {
-        const float p0 = ex2(fmaf(__uint_as_float(rs[i]), c1, -lse_l2));
-        const float p1 = ex2(fmaf(__uint_as_float(rs[i + 1]), c1, -lse_l2));
-        pk[i >> 1] = pack_bf16x2(p0, p1);
-        dk[i >> 1] = pack_bf16x2((p0 * scale) * (__uint_as_float(rd[i]) - delta),
-                                 (p1 * scale) * (__uint_as_float(rd[i + 1]) - delta));
-      }
-    }
-    const uint32_t sub_off = half * (128 * 128);
-    const int cc = c * 32;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const uint32_t off = sub_off + sw128_offset(rowi, cc + g * 8);
-      if (write_p) st_shared_v4(sP + off, pk[g * 4], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]);
-      st_shared_v4(sdS + off, dk[g * 4], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]);
-    }
-  }
-}
-
-constexpr uint32_t T128 = 128 * 128;  // bytes of one [128 rows][64] sub-tile
-
-// ------------------------------------------------------------------------------------------------------------------
-// backward dK / dV
-// ------------------------------------------------------------------------------------------------------------------
-template <int DH>
-struct BwdCfg {
-  static constexpr uint32_t TILE = 128 * DH * 2;   // a [128][DH] operand tile
-  static constexpr uint32_t PT = 128 * 128 * 2;    // P / dS tile
-  static constexpr size_t SMEM_DKDV = 1024 + 4 * TILE + 2 * PT + 128;
-  static constexpr size_t SMEM_DQ = 1024 + 4 * TILE + PT + 128;
-};
-
-template <int DH>
-__global__ void __launch_bounds__(256, 1)
-attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                     const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S,
-                     int H, float scale) {
-  using C = BwdCfg<DH>;
-  constexpr int NT = DH / 64;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sK = base, sV = sK + C::TILE, sQ = sV + C::TILE, sdO = sQ + C::TILE, sP = sdO + C::TILE,
-                 sdS = sP + C::PT;
-  const uint32_t bars = sdS + C::PT;
-  const uint32_t bar_kv = bars, bar_q = bars + 8, bar_do = bars + 16, bar_a = bars + 24, bar_b = bars + 32;
-  const uint32_t tmem_slot = bars + 40;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int rowi = tid & 127, half = tid >> 7;
-  const int jb = blockIdx.x;  // kv block (block 0 has the most work and is scheduled first)
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int k0 = jb * 128;
-  const int n_q = (S + 127) / 128;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQKV);
-    tma_prefetch_desc(&tmDO);
-    mbar_init(bar_kv, 1); mbar_init(bar_q, 1); mbar_init(bar_do, 1); mbar_init(bar_a, 1); mbar_init(bar_b, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot_ptr;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 256 + DH;
-  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
-
-  if (tid == 0) {
-    mbar_expect_tx(bar_kv, 2 * C::TILE);
-    tma_load_tile<DH>(sK, T128, &tmQKV, bar_kv, 1 * H + h, k0, b);
-    tma_load_tile<DH>(sV, T128, &tmQKV, bar_kv, 2 * H + h, k0, b);
-    mbar_expect_tx(bar_q, C::TILE);
-    tma_load_tile<DH>(sQ, T128, &tmQKV, bar_q, 0 * H + h, jb * 128, b);
-    mbar_expect_tx(bar_do, C::TILE);
-    tma_load_tile<DH>(sdO, T128, &tmDO, bar_do, h, jb * 128, b);
-  }
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T, dP = dO V^T
-  constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 1, 1);   // dV = P^T dO, dK = dS^T Q  (both MN-major)
-  const float c1 = scale * LOG2E;
-
-  mbar_wait(bar_kv, 0);
-  int it = 0;
-  for (int ib = jb; ib < n_q; ++ib, ++it) {
-    const uint32_t ph = it & 1;
-    const int q0 = ib * 128;
-    const int qi = q0 + rowi;
-    const bool row_ok = qi < S;
-    float lse_l2 = 0.f, dl = 0.f;
-    if (row_ok) {
-      lse_l2 = lse[((long long)b * H + h) * S + qi] * LOG2E;
-      dl = delta[((long long)b * H + h) * S + qi];
-    }
-    if (tid == 0) {
-      mbar_wait(bar_q, ph);
-      mbar_wait(bar_do, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk) {
-        const uint32_t o = (kk / 4) * T128 + (kk % 4) * 32;
-        umma_bf16_ss(tS, umma_smem_desc_sw128(sQ + o, 0, 1024), umma_smem_desc_sw128(sK + o, 0, 1024), idesc_s,
-                     kk > 0);
-      }
-#pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk) {
-        const uint32_t o = (kk / 4) * T128 + (kk % 4) * 32;
-        umma_bf16_ss(tdP, umma_smem_desc_sw128(sdO + o, 0, 1024), umma_smem_desc_sw128(sV + o, 0, 1024), idesc_s,
-                     kk > 0);
-      }
-      umma_commit(bar_a);
-      if (ib + 1 < n_q) {  // the smem buffers are single: at least pull the next Q / dO tiles into L2 now
-        tma_prefetch_tile<DH>(&tmQKV, 0 * H + h, (ib + 1) * 128, b);
-        tma_prefetch_tile<DH>(&tmDO, h, (ib + 1) * 128, b);
-      }
-    }
-    mbar_wait(bar_a, ph);
-    tc_fence_after();
-    bwd_make_p_ds(tS, tdP, lane_off, sP, sdS, true, rowi, half, qi, k0, /*need_mask=*/ib == jb, row_ok, lse_l2, dl,
-                  c1, scale);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      // dV += P^T dO ; dK += dS^T Q      (K dimension = the 128 query rows of this block)
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        umma_bf16_ss(tdV, umma_smem_desc_sw128(sP + kk * 2048, T128, 1024),
-                     umma_smem_desc_sw128(sdO + kk * 2048, T128, 1024), idesc_g, (it > 0 || kk > 0));
-      }
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {
-        umma_bf16_ss(tdK, umma_smem_desc_sw128(sdS + kk * 2048, T128, 1024),
-                     umma_smem_desc_sw128(sQ + kk * 2048, T128, 1024), idesc_g, (it > 0 || kk > 0));
-      }
-      umma_commit(bar_b);
-    }
-    mbar_wait(bar_b, ph);
-    tc_fence_after();
-    if (tid == 0 && ib + 1 < n_q) {  // Q / dO / P / dS buffers are free again
-      mbar_expect_tx(bar_q, C::TILE);
-      tma_load_tile<DH>(sQ, T128, &tmQKV, bar_q, 0 * H + h, (ib + 1) * 128, b);
-      mbar_expect_tx(bar_do, C::TILE);
-      tma_load_tile<DH>(sdO, T128, &tmDO, bar_do, h, (ib + 1) * 128, b);
-    }
-    (void)NT;
-  }
-  // ---- write dK, dV rows (thread pair = key row; each thread writes DH/2 columns)
-  const int ki = k0 + rowi;
-#pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    const uint32_t tsrc = which == 0 ? tdK : tdV;
-    bf16* dst = dqkv + ((((long long)b * S + ki) * 3 + (which == 0 ? 1 : 2)) * H + h) * DH + half * (DH / 2);
-#pragma unroll 1
-    for (int c = 0; c < DH / 64; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(tsrc + lane_off + half * (DH / 2) + c * 32, r);
-      tmem_ld_wait();
-      if (ki < S) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 q;
-          q.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
-          q.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
-          q.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
-          q.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = q;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// backward dQ
-// ------------------------------------------------------------------------------------------------------------------
-template <int DH>
-__global__ void __launch_bounds__(256, 1)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S,
-                   int H, float scale) {
-  using C = BwdCfg<DH>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t sQ = base, sdO = sQ + C::TILE, sK = sdO + C::TILE, sV = sK + C::TILE, sdS = sV + C::TILE;
-  const uint32_t bars = sdS + C::PT;
-  const uint32_t bar_q = bars, bar_k = bars + 8, bar_v = bars + 16, bar_a = bars + 24, bar_b = bars + 32;
-  const uint32_t tmem_slot = bars + 40;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int rowi = tid & 127, half = tid >> 7;
-  const int ib = gridDim.x - 1 - blockIdx.x;  // heavy query blocks first
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int q0 = ib * 128;
-
-  if (tid == 0) {
-    tma_prefetch_desc(&tmQKV);
-    tma_prefetch_desc(&tmDO);
-    mbar_init(bar_q, 1); mbar_init(bar_k, 1); mbar_init(bar_v, 1); mbar_init(bar_a, 1); mbar_init(bar_b, 1);
-    fence_mbar_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot_ptr;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
-  const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
-
-  if (tid == 0) {
-    mbar_expect_tx(bar_q, 2 * C::TILE);
-    tma_load_tile<DH>(sQ, T128, &tmQKV, bar_q, 0 * H + h, q0, b);
-    tma_load_tile<DH>(sdO, T128, &tmDO, bar_q, h, q0, b);
-    mbar_expect_tx(bar_k, C::TILE);
-    tma_load_tile<DH>(sK, T128, &tmQKV, bar_k, 1 * H + h, 0, b);
-    mbar_expect_tx(bar_v, C::TILE);
-    tma_load_tile<DH>(sV, T128, &tmQKV, bar_v, 2 * H + h, 0, b);
-  }
-  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);
-  constexpr uint32_t idesc_q = umma_idesc_bf16(128, DH, 0, 1);  // dQ = dS K : A K-major (K = keys), B MN-major
-  const float c1 = scale * LOG2E;
-  const int qi = q0 + rowi;
-  const bool row_ok = qi < S;
-  float lse_l2 = 0.f, dl = 0.f;
-  if (row_ok) {
-    lse_l2 = lse[((long long)b * H + h) * S + qi] * LOG2E;
-    dl = delta[((long long)b * H + h) * S + qi];
-  }
-  mbar_wait(bar_q, 0);
-  for (int jb = 0; jb <= ib; ++jb) {
-    const uint32_t ph = jb & 1;
-    if (tid == 0) {
-      mbar_wait(bar_k, ph);
-      mbar_wait(bar_v, ph);
-      tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk) {
-        const uint32_t o = (kk / 4) * T128 + (kk % 4) * 32;
-        umma_bf16_ss(tS, umma_smem_desc_sw128(sQ + o, 0, 1024), umma_smem_desc_sw128(sK + o, 0, 1024), idesc_s,
-                     kk > 0);
-      }
-#pragma unroll
-      for (int kk = 0; kk < DH / 16; ++kk) {
-        const uint32_t o = (kk / 4) * T128 + (kk % 4) * 32;
-        umma_bf16_ss(tdP, umma_smem_desc_sw128(sdO + o, 0, 1024), umma_smem_desc_sw128(sV + o, 0, 1024), idesc_s,
-                     kk > 0);
-      }
-      umma_commit(bar_a);
-    }
-    mbar_wait(bar_a, ph);
-    tc_fence_after();
-    if (tid == 0 && jb + 1 <= ib) {  // V is no longer needed by this iteration
-      mbar_expect_tx(bar_v, C::TILE);
-      tma_load_tile<DH>(sV, T128, &tmQKV, bar_v, 2 * H + h, (jb + 1) * 128, b);
-    }
-    bwd_make_p_ds(tS, tdP, lane_off, 0, sdS, false, rowi, half, qi, jb * 128, /*need_mask=*/jb == ib, row_ok, lse_l2,
-                  dl, c1, scale);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int kk = 0; kk < 8; ++kk) {  // K dimension = the 128 keys of this block
-        umma_bf16_ss(tdQ, umma_smem_desc_sw128(sdS + (kk / 4) * T128 + (kk % 4) * 32, 0, 1024),
-                     umma_smem_desc_sw128(sK + kk * 2048, T128, 1024), idesc_q, (jb > 0 || kk > 0));
-      }
-      umma_commit(bar_b);
-    }
-    mbar_wait(bar_b, ph);
-    tc_fence_after();
-    if (tid == 0 && jb + 1 <= ib) {
-      mbar_expect_tx(bar_k, C::TILE);
-      tma_load_tile<DH>(sK, T128, &tmQKV, bar_k, 1 * H + h, (jb + 1) * 128, b);
-    }
-  }
-  bf16* dst = dqkv + ((((long long)b * S + qi) * 3 + 0) * H + h) * DH + half * (DH / 2);
-#pragma unroll 1
-  for (int c = 0; c < DH / 64; ++c) {
-    uint32_t r[32];
-    tmem_ld_x32(tdQ + lane_off + half * (DH / 2) + c * 32, r);
-    tmem_ld_wait();
-    if (row_ok) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 q;
-        q.x = pack_bf16x2(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]));
-        q.y = pack_bf16x2(__uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3]));
-        q.z = pack_bf16x2(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]));
-        q.w = pack_bf16x2(__uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7]));
-        *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = q;
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// host side
-// ------------------------------------------------------------------------------------------------------------------
-// Warp-specialised kernels (attn_ws.cu).  DB200_ATTN_V1 (development A/B switch, read once): bit 0 = run the forward on
-// the first-generation kernel of this file instead, bit 1 = the backward.
-int attn_fwd_ws_launch(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H, int dh,
-                       float scale);
-int attn_bwd_ws_launch(cudaStream_t stream, const void* qkv, const void* dout, const float* lse, const float* delta,
-                       void* dqkv, int B, int S, int H, int dh, float scale);
-static int attn_v1_bits() {
-  static const int bits = [] { const char* e = getenv("DB200_ATTN_V1"); return e ? atoi(e) : 0; }();
-  return bits;
-}
-
-static int make_qkv_map(CUtensorMap* tm, const void* qkv, int B, int S, int H, int dh, uint32_t box_rows) {
-  uint64_t dims[4] = {(uint64_t)dh, (uint64_t)3 * H, (uint64_t)S, (uint64_t)B};
-  uint64_t strides[3] = {(uint64_t)dh * 2, (uint64_t)3 * H * dh * 2, (uint64_t)S * 3 * H * dh * 2};
-  uint32_t box[4] = {64, 1, box_rows, 1};
-  return make_tmap_bf16(tm, qkv, 4, dims, strides, box);
-}
-static int make_o_map(CUtensorMap* tm, const void* o, int B, int S, int H, int dh, uint32_t box_rows) {
-  uint64_t dims[4] = {(uint64_t)dh, (uint64_t)H, (uint64_t)S, (uint64_t)B};
-  uint64_t strides[3] = {(uint64_t)dh * 2, (uint64_t)H * dh * 2, (uint64_t)S * H * dh * 2};
-  uint32_t box[4] = {64, 1, box_rows, 1};
-  return make_tmap_bf16(tm, o, 4, dims, strides, box);
-}
-
-template <int DH>
-static int fwd_launch(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H, float scale) {
-  using C = FwdCfg<DH>;
-  CUtensorMap tmQ, tmKV;
-  int rc = make_qkv_map(&tmQ, qkv, B, S, H, DH, 128);
-  if (rc != DB200_OK) return rc;
-  rc = make_qkv_map(&tmKV, qkv, B, S, H, DH, C::BNK);
-  if (rc != DB200_OK) return rc;
-  static bool attr = false;
-  if (!attr) {
-    DB200_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    attr = true;
-  }
-  dim3 grid((S + 127) / 128, H, B);
-  attn_fwd_kernel<DH><<<grid, 256, C::SMEM, stream>>>(tmQ, tmKV, (bf16*)out, lse, S, H, scale);
-  return check_launch("attn_fwd_kernel");
-}
-
-template <int DH>
-static int bwd_launch(cudaStream_t stream, const void* qkv, const void* dout, const float* lse, const float* delta,
-                      void* dqkv, int B, int S, int H, float scale) {
-  using C = BwdCfg<DH>;
-  CUtensorMap tmQKV, tmDO;
-  int rc = make_qkv_map(&tmQKV, qkv, B, S, H, DH, 128);
-  if (rc != DB200_OK) return rc;
-  rc = make_o_map(&tmDO, dout, B, S, H, DH, 128);
-  if (rc != DB200_OK) return rc;
-  static bool attr = false;
-  if (!attr) {
-    DB200_CUDA(cudaFuncSetAttribute(attn_bwd_dkdv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)C::SMEM_DKDV));
-    DB200_CUDA(
-        cudaFuncSetAttribute(attn_bwd_dq_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_DQ));
-    attr = true;
-  }
-  dim3 grid((S + 127) / 128, H, B);
-  attn_bwd_dkdv_kernel<DH><<<grid, 256, C::SMEM_DKDV, stream>>>(tmQKV, tmDO, lse, delta, (bf16*)dqkv, S, H, scale);
-  rc = check_launch("attn_bwd_dkdv_kernel");
-  if (rc != DB200_OK) return rc;
-  attn_bwd_dq_kernel<DH><<<grid, 256, C::SMEM_DQ, stream>>>(tmQKV, tmDO, lse, delta, (bf16*)dqkv, S, H, scale);
-  return check_launch("attn_bwd_dq_kernel");
-}
 
 }  // namespace db200
 
@@ -719,9 +68,7 @@ extern "C" int db200_attn_causal_fwd(db200_stream_t stream_, const void* qkv, vo
                 "attn_fwd: NULL or unaligned pointer");
   DB200_REQUIRE(scale > 0.f, DB200_E_INVALID, "attn_fwd: scale must be > 0");
   if (dh != 64 && dh != 128) return set_error(DB200_E_UNSUPPORTED, "attn: head_dim %d not in {64,128}", dh);
-  if (!(attn_v1_bits() & 1)) return attn_fwd_ws_launch(stream, qkv, out, lse, B, S, H, dh, scale);
-  if (dh == 128) return fwd_launch<128>(stream, qkv, out, lse, B, S, H, scale);
-  return fwd_launch<64>(stream, qkv, out, lse, B, S, H, scale);
+  return attn_fwd_ws_launch(stream, qkv, out, lse, B, S, H, dh, scale);
 }
 
 extern "C" int db200_attn_causal_bwd(db200_stream_t stream_, const void* qkv, const void* out, const void* dout,
@@ -746,7 +93,5 @@ extern "C" int db200_attn_causal_bwd(db200_stream_t stream_, const void* qkv, co
   }
   int rc = check_launch("attn_delta_kernel");
   if (rc != DB200_OK) return rc;
-  if (!(attn_v1_bits() & 2)) return attn_bwd_ws_launch(stream, qkv, dout, lse, delta, dqkv, B, S, H, dh, scale);
-  if (dh == 128) return bwd_launch<128>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
-  return bwd_launch<64>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
+  return attn_bwd_ws_launch(stream, qkv, dout, lse, delta, dqkv, B, S, H, dh, scale);
 }
