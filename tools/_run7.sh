@@ -13,3 +13,7 @@ echo "=== bench N=1" >> $L
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r02_n1b.json 2> gpurun_out/bench_r02_n1b.err; echo "exit=$?" >> $L
 head -c 3000 gpurun_out/bench_r02_n1b.json >> $L
 tail -150 $L
+echo "=== ncu full: tokenizer convs + first GEMMs of a step" >> $L
+timeout 420 ncu --set full --clock-control none --import-source on -k regex:'conv_tc|conv_first' -c 15 -o gpurun_out/prof_convtc_r02 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extra >> $L 2>&1; echo "exit=$?" >> $L
+timeout 420 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 78 -c 14 -o gpurun_out/prof_gemm_r02 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extra >> $L 2>&1; echo "exit=$?" >> $L
+tail -12 $L
