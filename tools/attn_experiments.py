@@ -23,7 +23,19 @@ for (B, S, H, dh) in ((32, 1280, 4, 128), (16, 1280, 16, 64)):
         ops.attn_fwd(qkv, out, lse, B, S, H, dh, 1.0)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
-    print(f"  dh={dh}: {ms*1e3:7.1f} us  {4.0*S*S*dh*B*H/2/ms/1e9:7.1f} TFLOP/s", flush=True)
+    print(f"  dh={dh}: fwd {ms*1e3:7.1f} us  {4.0*S*S*dh*B*H/2/ms/1e9:7.1f} TFLOP/s", flush=True)
+    if os.environ.get("DB200_ATTN_EXP", "0") == "0":
+        dout = torch.randn(B, S, H, dh, device="cuda").to(torch.bfloat16)
+        dqkv = torch.zeros_like(qkv); delta = torch.zeros(B, H, S, device="cuda"); acc = torch.zeros(1, device="cuda")
+        for _ in range(3):
+            ops.attn_bwd(qkv, out, dout, lse, acc, delta, dqkv, B, S, H, dh, 1.0)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            ops.attn_bwd(qkv, out, dout, lse, acc, delta, dqkv, B, S, H, dh, 1.0)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        print(f"  dh={dh}: bwd {ms*1e3:7.1f} us  {2.5*4.0*S*S*dh*B*H/2/ms/1e9:7.1f} TFLOP/s (incl. delta pre-pass)", flush=True)
 ''' % ROOT
 
 for ng in ("4", "2"):
