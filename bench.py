@@ -472,6 +472,8 @@ def main():
     ap.add_argument("--n-layers", type=int, default=0,
                     help="override the workload's layer count (smoke runs only; the line's config names the override)")
     ap.add_argument("--no-extra", action="store_true", help="skip the bounded dalle_coco / vae_coco side measurements")
+    ap.add_argument("--vae-example", action="store_true",
+                    help="measure only configs/vae_example.json (BASELINE configs[0]: 32x32, fp32, batch 32)")
     ap.add_argument("--vae-coco", action="store_true",
                     help="measure configs/vae_coco_b200.json (256x256, K=8192, bf16, 16 images per GPU) instead")
     args = ap.parse_args()
@@ -493,9 +495,12 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={dp.world}: launch with torch.distributed.run")
     L.require_device()
     device = torch.device("cuda", torch.cuda.current_device())
-    if args.vae_coco:
-        line = vae_example_rate(dp, device, steps=args.steps, warmup=args.warmup, config="vae_coco_b200",
-                                per_gpu_batch=16)
+    if args.vae_coco or args.vae_example:
+        if args.vae_coco:
+            line = vae_example_rate(dp, device, steps=args.steps, warmup=args.warmup, config="vae_coco_b200",
+                                    per_gpu_batch=16)
+        else:
+            line = vae_example_rate(dp, device, steps=args.steps, warmup=args.warmup)
         line.update({"n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup})
         if dp.rank == 0:
             print(json.dumps(line), flush=True)

@@ -40,6 +40,38 @@ namespace {
 constexpr float LOG2E_F = 1.4426950408889634f;
 constexpr uint32_t T128B = 128 * 128;  // bytes of one [128 rows][64] swizzled sub-tile
 
+// Development builds only (make DEV=1): per-CTA event timeline.  Every TRACE_STRIDE-th CTA records (code, SM clock)
+// pairs from lane 0 of four of its warps (role 0 = TMA, 1 = MMA issuer, 2 = first math warp, 3 = last math warp) into
+// the buffer set with db200_dev_attn_trace(); tools/attn_trace.py prints them.  Compiled out of the shipped library.
+#ifdef DB200_DEV_KNOBS
+constexpr int TRACE_EV = 160, TRACE_STRIDE = 37;
+__device__ unsigned long long* g_attn_trace = nullptr;
+__device__ int g_attn_trace_slots = 0;
+struct Tracer {
+  unsigned long long* p;
+  int n;
+  __device__ __forceinline__ void init(int role, int lane) {
+    p = nullptr; n = 0;
+    const int slot = (int)blockIdx.x / TRACE_STRIDE;
+    if (g_attn_trace && lane == 0 && role >= 0 && (int)blockIdx.x % TRACE_STRIDE == 0 && slot < g_attn_trace_slots) {
+      p = g_attn_trace + ((size_t)slot * 4 + role) * TRACE_EV;
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p[0] = ((unsigned long long)(0xF00000u | smid) << 40) | ((unsigned long long)blockIdx.x & 0xFFFFFFFFFFull);
+      n = 1;
+    }
+  }
+  __device__ __forceinline__ void ev(int type, int j) {
+    if (p && n < TRACE_EV) p[n++] = ((unsigned long long)((type << 12) | (j & 0xFFF)) << 40) | ((unsigned long long)clock64() & 0xFFFFFFFFFFull);
+  }
+};
+#else
+struct Tracer {
+  __device__ __forceinline__ void init(int, int) {}
+  __device__ __forceinline__ void ev(int, int) {}
+};
+#endif
+
 // MUFU.EX2 directly: arguments are <= 8 after the running-max subtraction; ex2.approx(-inf) = +0.
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -117,14 +149,18 @@ __device__ __forceinline__ void store_row_bf16(bf16* dst, const uint32_t* r, flo
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
-template <int DH, int NG>
+// DEEP: deeper K / V rings (all of the 227 KiB): a V slot is only released when its P.V product has retired, so with two
+// slots the load of V_{j+2} has one logits product + one softmax (~1.5 k cycles) to cross L2 -> smem (32 KiB at dh = 128).
+template <int DH, int NG, int DEEP = 0>
 struct FwdWs {
-  static constexpr int NK = (DH == 128) ? 3 : 4;   // K ring depth (128-key blocks): logits run two blocks ahead
-  static constexpr int NV = (DH == 128) ? 2 : 4;   // V ring depth
+  static constexpr int NK = (DH == 128) ? 3 : (DEEP ? 6 : 4);   // K ring depth (128-key blocks): logits run two blocks ahead
+  static constexpr int NV = (DH == 128) ? (DEEP ? 3 : 2) : (DEEP ? 6 : 4);   // V ring depth
   static constexpr uint32_t TILE = 128 * DH * 2;   // one [128][DH] bf16 operand tile
   static constexpr uint32_t XCH_BYTES = 2 * NG * 128 * 4;
   static constexpr uint32_t BAR_BYTES = 256;
-  static constexpr size_t SMEM = 1024 + TILE + (NK + NV) * TILE + XCH_BYTES + BAR_BYTES;
+  // dynamic shared memory is declared 1024-byte aligned (the 128-byte swizzle needs it): no alignment slack
+  static constexpr size_t SMEM = TILE + (NK + NV) * TILE + XCH_BYTES + BAR_BYTES;
+  static_assert(SMEM <= 232448, "forward attention: shared memory over the 227 KiB per-CTA limit");
   static constexpr int THREADS = (4 * NG + 2) * 32;  // NG math warpgroups + TMA warp + MMA warp
 };
 
@@ -133,21 +169,21 @@ struct FwdWs {
 // NG = number of softmax warpgroups = column groups of every 128-key block (2: 64 columns per thread, 4: 32).  More
 // groups = more resident warps per scheduler: the per-warp instruction stream is a chain of dependent fp32 / MUFU ops,
 // and with two math warps per scheduler it issues once every ~6 cycles (ncu, profiles/ncu_attn_r02.md).
-template <int DH, int NG>
+template <int DH, int NG, int DEEP>
 __global__ void __launch_bounds__((4 * NG + 2) * 32, 1)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out,
                    int S, int H, float scale, int xflags) {
 #ifndef DB200_DEV_KNOBS
   xflags = 0;  // timing experiments exist in development builds only (make DEV=1); results are wrong under them
 #endif
-  using C = FwdWs<DH, NG>;
+  using C = FwdWs<DH, NG, DEEP>;
   constexpr int NK = C::NK, NV = C::NV;
   constexpr int CG = 128 / NG;       // key columns of a block per group (= per thread)
   constexpr int OG = DH / NG;        // output columns per group
   constexpr int TMA_WARP = 4 * NG, MMA_WARP = 4 * NG + 1;
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t base = raw;                             // 1024-byte aligned (checked below)
   const uint32_t sQ = base, sK = sQ + C::TILE, sV = sK + NK * C::TILE;
   const uint32_t sX = sV + NV * C::TILE;                 // [2 parities][NG groups][128 rows] f32 maxima / sums
   const uint32_t bars = sX + C::XCH_BYTES;
@@ -173,6 +209,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   const int n_kv = qt + 1;  // key blocks 0 .. qt; block qt is the diagonal one
 
   if (tid == 0) {
+    if (raw & 1023u) __trap();  // the 128-byte swizzle needs 1024-byte aligned tiles
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
     for (int i = 0; i < NK; ++i) { mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1); }
@@ -188,6 +225,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tO = tmem + 256;
 
+  Tracer tr;
+  tr.init(warp == TMA_WARP ? 0 : warp == MMA_WARP ? 1 : warp == 0 ? 2 : warp == 4 * NG - 1 ? 3 : -1, lane);
+  tr.ev(1, n_kv);   // roles start (after barrier init / TMEM allocation)
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -200,12 +240,14 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
           const int sk = jk % NK;
           mbar_expect_tx(k_full + 8 * sk, C::TILE);
           ws_load_tile<DH>(sK + sk * C::TILE, &tmQKV, k_full + 8 * sk, 1 * H + h, jk * 128, b);
+          tr.ev(2, jk);
           ++jk;
         }
         if (jv < n_kv && mbar_try_wait(v_empty + 8 * (jv % NV), ((uint32_t)(jv / NV) & 1u) ^ 1u)) {
           const int sv = jv % NV;
           mbar_expect_tx(v_full + 8 * sv, C::TILE);
           ws_load_tile<DH>(sV + sv * C::TILE, &tmQKV, v_full + 8 * sv, 2 * H + h, jv * 128, b);
+          tr.ev(3, jv);
           ++jv;
         }
       }
@@ -220,6 +262,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       const uint64_t dq = desc_k_base(sQ);
       auto issue_s = [&](int j) {
         const int sk = j % NK;
+        tr.ev(9, j);    // about to wait for K_j
         mbar_wait(k_full + 8 * sk, (uint32_t)(j / NK) & 1u);
         tc_fence_after();
         const uint64_t dk = desc_k_base(sK + sk * C::TILE);
@@ -232,6 +275,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
           umma_commit(k_empty + 8 * sk);
         }
         __syncwarp();
+        tr.ev(4, j);    // S_j issued
       };
       mbar_wait(q_full, 0);
       issue_s(0);
@@ -239,7 +283,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       for (int j = 0; j < n_kv; ++j) {
         const int sv = j % NV;
         mbar_wait(v_full + 8 * sv, (uint32_t)(j / NV) & 1u);
+        tr.ev(11, j);   // V_j has landed
         mbar_wait(p_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
+        tr.ev(12, j);   // P_j is in TMEM
         tc_fence_after();
         const uint64_t dv = desc_mn_base(sV + sv * C::TILE);
         const uint32_t tP = tmem + (j & 1) * 128;
@@ -251,6 +297,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
           umma_commit(v_empty + 8 * sv);
         }
         __syncwarp();
+        tr.ev(5, j);    // P.V_j issued
         if (j + 2 < n_kv) issue_s(j + 2);  // into the buffer whose P the product above has just been queued to consume
       }
     }
@@ -266,6 +313,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     for (int j = 0; j < n_kv; ++j) {
       const uint32_t tS = tmem + (j & 1) * 128 + CG * g + lane_off;
       mbar_wait(s_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
+      tr.ev(6, j);      // S_j complete (seen by this math warp)
       tc_fence_after();
       if (xflags & 2) {  // experiment: pure hand-off chain, no softmax work at all
         warp_arrive(p_ready + 8 * (j & 1), lane);
@@ -342,12 +390,14 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       l_run += l0 + l1;
       tmem_st_wait();
       warp_arrive(p_ready + 8 * (j & 1), lane);
+      tr.ev(7, j);      // this warp's share of P_j written
     }
     // ---- epilogue: O / l -> bf16 (this group's share of the columns), lse
     float* xp = xch + (n_kv & 1) * (NG * 128);  // the parity the last block did not use
     if (xflags & 2) m_used = 0.f;
     xp[g * 128 + row] = l_run;
     mbar_wait(o_done, (uint32_t)(n_kv - 1) & 1u);
+    tr.ev(8, 0);        // last P.V retired: epilogue starts
     tc_fence_after();
     math_bar_sync<NG>();
     float l_tot = 0.f;
@@ -365,12 +415,14 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     }
     if (qi < S && g == 0) lse_out[((long long)b * H + h) * S + qi] = m_used * scale + logf(l_tot);
   }
+  tr.ev(10, 0);         // role done
   tc_fence_before();
   __syncthreads();
   if (warp == TMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+  tr.ev(13, 0);         // CTA about to exit
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -457,6 +509,9 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tST = tmem + 256, tdPT = tmem + 384;
 
+  Tracer tr;
+  tr.init(warp == TMA_WARP ? 0 : warp == MMA_WARP ? 1 : warp == 0 ? 2 : warp == 4 * NG - 1 ? 3 : -1, lane);
+  tr.ev(1, n_it);
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
@@ -469,12 +524,14 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           const int st = ia % NA;
           mbar_expect_tx(a_full + 8 * st, C::TILE);
           ws_load_tile<DH>(sQr + st * C::TILE, &tmQKV, a_full + 8 * st, 0 * H + h, (jb + ia) * 128, b);   // Q_i
+          tr.ev(2, ia);
           ++ia;
         }
         if (ib < n_it && mbar_try_wait(b_empty + 8 * (ib % NB), ((uint32_t)(ib / NB) & 1u) ^ 1u)) {
           const int st = ib % NB;
           mbar_expect_tx(b_full + 8 * st, C::TILE);
           ws_load_tile<DH>(sOr + st * C::TILE, &tmDO, b_full + 8 * st, h, (jb + ib) * 128, b);            // dO_i
+          tr.ev(3, ib);
           ++ib;
         }
       }
@@ -498,6 +555,7 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           umma_commit(sa_ready);
         }
         __syncwarp();
+        tr.ev(4, it);    // S^T issued
       };
       auto issue_dp = [&](int it) {  // dP^T = V dO_i^T
         const int st = it % NB;
@@ -511,6 +569,7 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           umma_commit(sb_ready);
         }
         __syncwarp();
+        tr.ev(14, it);   // dP^T issued
       };
       mbar_wait(x_full, 0);
       issue_s(0);
@@ -519,6 +578,7 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         const uint64_t q = desc_mn_base(sQr + (it % NA) * C::TILE), o = desc_mn_base(sOr + (it % NB) * C::TILE);
         const uint32_t acc = it > 0 ? 1u : 0u;
         mbar_wait(pa_ready, (uint32_t)it & 1u);
+        tr.ev(12, it);   // P^T is in TMEM
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
@@ -527,8 +587,10 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           umma_commit(b_empty + 8 * (it % NB));  // dO_i is free
         }
         __syncwarp();
+        tr.ev(5, it);    // dV issued
         if (it + 1 < n_it) issue_s(it + 1);      // runs under phase B of this block
         mbar_wait(pb_ready, (uint32_t)it & 1u);
+        tr.ev(15, it);   // dS^T is in TMEM
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
@@ -538,6 +600,7 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           if (it == n_it - 1) umma_commit(acc_done);
         }
         __syncwarp();
+        tr.ev(16, it);   // dK issued
         if (it + 1 < n_it) issue_dp(it + 1);     // runs under phase A of the next block
       }
     }
@@ -577,6 +640,7 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       // ---- phase A: P^T = 2^(c1 s - lse2[query]); pair dropped where key > query (only the first block is diagonal)
       mbar_wait(stat_full + 8 * st, (uint32_t)(it >> 1) & 1u);
       mbar_wait(sa_ready, (uint32_t)it & 1u);
+      tr.ev(6, it);
       tc_fence_after();
       uint32_t pk[CG / 2];
       const int lim = (it == 0) ? row - CG * g : -1;  // columns c < lim are queries before this key
@@ -602,8 +666,10 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       tmem_st_n<CG / 2>(tS, pk);
       tmem_st_wait();
       warp_arrive(pa_ready, lane);
+      tr.ev(7, it);
       // ---- phase B: dS^T = (P^T * scale) (dP^T - delta[query])
       mbar_wait(sb_ready, (uint32_t)it & 1u);
+      tr.ev(17, it);
       tc_fence_after();
       uint32_t dk[CG / 2];
 #pragma unroll
@@ -625,9 +691,11 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       tmem_st_n<CG / 2>(tdP, dk);
       tmem_st_wait();
       warp_arrive(pb_ready, lane);
+      tr.ev(18, it);
     }
     // ---- epilogue: the 2 dh accumulator columns (dV | dK) are split evenly over the groups
     mbar_wait(acc_done, 0);
+    tr.ev(8, 0);
     tc_fence_after();
     constexpr int EG = 2 * DH / NG;                 // columns per group
     const int acc_i = (g * EG) / DH;                // 0: dV, 1: dK
@@ -641,12 +709,14 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       if (ki < S) store_cols_bf16<32>(dst + c * 32, r, 1.f);
     }
   }
+  tr.ev(10, 0);
   tc_fence_before();
   __syncthreads();
   if (warp == TMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
+  tr.ev(13, 0);
 }
 
 // dQ: CTA = 128 queries (TMEM lanes), loop over the 128-key blocks j <= its own.  TMEM: dQ [0,dh) S [128,256)
@@ -868,30 +938,40 @@ static int attn_ng() {
   return ng;
 }
 
-template <int DH, int NG>
+// DB200_ATTN_DEEP (development A/B switch, read once): forward with the deeper K / V rings (two math warpgroups)
+static int attn_deep() {
+  static const int v = [] { const char* e = getenv("DB200_ATTN_DEEP"); return (e && atoi(e) != 0) ? 1 : 0; }();
+  return v;
+}
+
+template <int DH, int NG, int DEEP>
 static int fwd_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H,
                            float scale) {
-  using C = FwdWs<DH, NG>;
+  using C = FwdWs<DH, NG, DEEP>;
   CUtensorMap tm;
   int rc = ws_qkv_map(&tm, qkv, B, S, H, DH);
   if (rc != DB200_OK) return rc;
-  static const cudaError_t attr = cudaFuncSetAttribute(attn_fwd_ws_kernel<DH, NG>,
+  static const cudaError_t attr = cudaFuncSetAttribute(attn_fwd_ws_kernel<DH, NG, DEEP>,
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   DB200_CUDA(attr);
   dim3 grid(((S + 127) / 128) * H * B);
   static const int xflags = [] { const char* e = getenv("DB200_ATTN_EXP"); return e ? atoi(e) : 0; }();  // DEV builds only
-  attn_fwd_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, scale, xflags);
+  attn_fwd_ws_kernel<DH, NG, DEEP><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, scale, xflags);
   return check_launch("attn_fwd_ws_kernel");
 }
 
 int attn_fwd_ws_launch(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H, int dh,
                        float scale) {
-  if (attn_ng() == 2) {
-    if (dh == 128) return fwd_ws_launch_t<128, 2>(stream, qkv, out, lse, B, S, H, scale);
-    return fwd_ws_launch_t<64, 2>(stream, qkv, out, lse, B, S, H, scale);
+  if (attn_deep()) {
+    if (dh == 128) return fwd_ws_launch_t<128, 2, 1>(stream, qkv, out, lse, B, S, H, scale);
+    return fwd_ws_launch_t<64, 2, 1>(stream, qkv, out, lse, B, S, H, scale);
   }
-  if (dh == 128) return fwd_ws_launch_t<128, 4>(stream, qkv, out, lse, B, S, H, scale);
-  return fwd_ws_launch_t<64, 4>(stream, qkv, out, lse, B, S, H, scale);
+  if (attn_ng() == 2) {
+    if (dh == 128) return fwd_ws_launch_t<128, 2, 0>(stream, qkv, out, lse, B, S, H, scale);
+    return fwd_ws_launch_t<64, 2, 0>(stream, qkv, out, lse, B, S, H, scale);
+  }
+  if (dh == 128) return fwd_ws_launch_t<128, 4, 0>(stream, qkv, out, lse, B, S, H, scale);
+  return fwd_ws_launch_t<64, 4, 0>(stream, qkv, out, lse, B, S, H, scale);
 }
 
 template <int DH, int NG>
@@ -916,6 +996,15 @@ static int bwd_ws_launch_t(cudaStream_t stream, const void* qkv, const void* dou
   return check_launch("attn_bwd_dq_ws_kernel");
 }
 
+#ifdef DB200_DEV_KNOBS
+int attn_trace_set(void* buf, int slots) {
+  unsigned long long* p = reinterpret_cast<unsigned long long*>(buf);
+  DB200_CUDA(cudaMemcpyToSymbol(g_attn_trace, &p, sizeof(p)));
+  DB200_CUDA(cudaMemcpyToSymbol(g_attn_trace_slots, &slots, sizeof(slots)));
+  return DB200_OK;
+}
+#endif
+
 int attn_bwd_ws_launch(cudaStream_t stream, const void* qkv, const void* dout, const float* lse, const float* delta,
                        void* dqkv, int B, int S, int H, int dh, float scale) {
   if (attn_ng() == 2) {
@@ -927,3 +1016,8 @@ int attn_bwd_ws_launch(cudaStream_t stream, const void* qkv, const void* dout, c
 }
 
 }  // namespace db200
+
+#ifdef DB200_DEV_KNOBS
+// development library only: device buffer of slots x 4 roles x 160 events (u64) for the attention timeline
+extern "C" int db200_dev_attn_trace(void* buf, int slots) { return db200::attn_trace_set(buf, slots); }
+#endif

@@ -17,11 +17,21 @@
 
 namespace db200 {
 
+// Five 32 KiB pipeline stages + TWO 4 KiB epilogue staging buffers per epilogue warp: the second buffer lets the
+// residual / ReLU-mask operand of the next 32 x 64 block arrive by cp.async while the current block is processed.
+// (DB200_G2_OLD, development builds only: the previous 6-stage / single-buffer / synchronous-fetch configuration.)
+#ifdef DB200_G2_OLD
 constexpr int G2_STAGES = 6;
+constexpr int G2_STG_BUFS = 1;
+#else
+constexpr int G2_STAGES = 5;
+constexpr int G2_STG_BUFS = 2;
+#endif
+constexpr bool G2_PF = G2_STG_BUFS == 2;
 constexpr uint32_t G2_A_BYTES = 128 * 64 * 2;  // this CTA's 128 rows of A
 constexpr uint32_t G2_B_BYTES = 128 * 64 * 2;  // this CTA's 128 columns of B
 constexpr uint32_t G2_STAGE = G2_A_BYTES + G2_B_BYTES;
-constexpr size_t G2_SMEM = 1024 + size_t(G2_STAGES) * G2_STAGE + 256 + 8 * 4096;
+constexpr size_t G2_SMEM = 1024 + size_t(G2_STAGES) * G2_STAGE + 256 + 8 * G2_STG_BUFS * 4096;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -224,7 +234,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int wq = ew & 3;
     const int half = ew >> 2;
     constexpr int CH = BN / 64;
-    const uint32_t stg = stg_base + ew * STG_BYTES;
+    const uint32_t stg = stg_base + ew * (G2_STG_BUFS * STG_BYTES);
+    const uint32_t stg2 = stg + STG_BYTES;   // only touched when G2_PF
+    // per-element operand with the output's layout: residual (STORE) or saved activation (RELU_BWD)
+    const bf16* pf_src = p.mode == DB200_EPI_RELU_BWD ? p.aux : (p.mode == DB200_EPI_STORE ? p.residual : nullptr);
+    const long long pf_ld = p.mode == DB200_EPI_RELU_BWD ? p.ldaux : p.ldr;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = cid; tile < total_tiles; tile += n_clusters) {
       const Tile2 t = decode_tile2(p, m_tiles2, tile);
@@ -249,13 +263,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (BN == 256 && cbase + 64 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 64));
         }
       }
+      if (G2_PF && pf_src && cbase < p.N) {  // block 0 of this half tile: in flight under the accumulator wait
+        stage_prefetch_bf16(stg, pf_src, pf_ld, row0, cbase, p.M, p.N, lane);
+        cp_async_commit();
+      }
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + acc * BN + half * (BN / 2) + (uint32_t(wq * 32) << 16);
       switch (p.mode) {
-        case DB200_EPI_STORE:    epi_store<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
+        case DB200_EPI_STORE:    epi_store<CH, G2_PF>(p, t_addr, row, row_ok, cbase, stg, row0, lane, stg2); break;
         case DB200_EPI_ATOMIC:   epi_atomic<CH>(p, t_addr, row, row_ok, cbase); break;
-        case DB200_EPI_RELU_BWD: epi_relu_bwd<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
+        case DB200_EPI_RELU_BWD: epi_relu_bwd<CH, G2_PF>(p, t_addr, row, row_ok, cbase, stg, row0, lane, stg2); break;
         case DB200_EPI_CE_STATS: epi_ce_stats<CH>(p, t_addr, row, row_ok, cbase, t.n_blk * 2 + half); break;
         case DB200_EPI_CE_GRAD:  epi_ce_grad<CH>(p, t_addr, row, row_ok, cbase, stg, row0, lane); break;
         default: break;  // mode -1 (DB200_GEMM_NOEPI=1, timing experiments only): drain nothing

@@ -184,6 +184,42 @@ __device__ __forceinline__ void stage_fetch_bf16(uint32_t stg, const bf16* src, 
   __syncwarp();
 }
 
+// Asynchronous variant (cp.async, L2 -> smem without registers): the epilogue operand of the NEXT block is brought in
+// while the current one is processed, and the first block of a tile while the warp still waits for the accumulator —
+// the ncu source page showed the epilogues with a residual / ReLU-mask operand spending half of their time on the
+// long scoreboard of exactly these loads (one DRAM / L2 round trip per 32 x 64 block on the critical path).
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool ok) {
+  const uint32_t sz = ok ? 16u : 0u;  // src-size 0: nothing is read, the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void stage_prefetch_bf16(uint32_t stg, const bf16* src, long long ld, int row0, int col0, int M,
+                                                    int N, int lane) {
+  const int slot = lane & 7, rsub = lane >> 3;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + rsub;
+    const int row = row0 + r, col = col0 + slot * 8;
+    const bool ok = row < M && col + 8 <= N;
+    cp_async16_zfill(stg_addr(stg, r, slot), ok ? src + (long long)row * ld + col : src, ok);
+  }
+}
+// block `pc` of a half tile lives in buffer (pc & 1); called with the operand of block pc already requested:
+// requests block pc + 1 (if any), then waits for block pc
+template <int NBLK>
+__device__ __forceinline__ uint32_t stage_pipeline_step(uint32_t stg0, uint32_t stg1, const bf16* src, long long ld, int row0,
+                                                        int cbase, int pc, int M, int N, int lane) {
+  const bool more = pc + 1 < NBLK && cbase + (pc + 1) * 64 < N;   // warp-uniform
+  if (more) stage_prefetch_bf16((pc & 1) ? stg0 : stg1, src, ld, row0, cbase + (pc + 1) * 64, M, N, lane);
+  cp_async_commit();
+  cp_async_wait<1>();   // everything but the group just committed (empty when there is no next block)
+  __syncwarp();
+  return (pc & 1) ? stg1 : stg0;
+}
+
 // column sums of the staged [32 rows][64 bf16] block (the values exactly as they are written to D), accumulated into
 // colsum[col0 .. col0+64): lane l owns columns 2l, 2l+1.  Rows >= M hold zeros (their `o` was zeroed).
 __device__ __forceinline__ void stage_colsum_bf16(uint32_t stg, float* colsum, int col0, int N, int lane) {
@@ -211,9 +247,11 @@ __device__ __forceinline__ void stage_colsum_bf16(uint32_t stg, float* colsum, i
   if (col + 1 < N) atomicAdd(colsum + col + 1, s1 + s3);
 }
 
-template <int CH>
+// PF: the residual of block 0 was requested with stage_prefetch_bf16 into `stg_` before the accumulator wait (caller),
+// blocks alternate between `stg_` and `stg2`.
+template <int CH, bool PF = false>
 __device__ __forceinline__ void epi_store(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase,
-                                          uint32_t stg, int row0, int lane) {
+                                          uint32_t stg_, int row0, int lane, uint32_t stg2 = 0) {
   static_assert(CH % 2 == 0, "epilogue works on pairs of 32-column chunks");
 #pragma unroll 1
   for (int pc = 0; pc < CH / 2; ++pc) {
@@ -222,7 +260,9 @@ __device__ __forceinline__ void epi_store(const GemmParams& p, uint32_t t_addr, 
     uint32_t rr2[2][32];  // both chunks of the pair in flight, one wait: halves the exposed TMEM-load latency
     tmem_ld_x32(t_addr + (pc * 2) * 32, rr2[0]);
     tmem_ld_x32(t_addr + (pc * 2 + 1) * 32, rr2[1]);
-    if (p.residual) stage_fetch_bf16(stg, p.residual, p.ldr, row0, colp, p.M, p.N, lane);
+    uint32_t stg = stg_;
+    if (PF && p.residual) stg = stage_pipeline_step<CH / 2>(stg_, stg2, p.residual, p.ldr, row0, cbase, pc, p.M, p.N, lane);
+    else if (p.residual) stage_fetch_bf16(stg, p.residual, p.ldr, row0, colp, p.M, p.N, lane);
     tmem_ld_wait();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -302,9 +342,9 @@ __device__ __forceinline__ void epi_atomic(const GemmParams& p, uint32_t t_addr,
   }
 }
 
-template <int CH>
+template <int CH, bool PF = false>
 __device__ __forceinline__ void epi_relu_bwd(const GemmParams& p, uint32_t t_addr, int row, bool row_ok, int cbase,
-                                             uint32_t stg, int row0, int lane) {
+                                             uint32_t stg_, int row0, int lane, uint32_t stg2 = 0) {
 #pragma unroll 1
   for (int pc = 0; pc < CH / 2; ++pc) {
     const int colp = cbase + pc * 64;
@@ -312,7 +352,9 @@ __device__ __forceinline__ void epi_relu_bwd(const GemmParams& p, uint32_t t_add
     uint32_t rr2[2][32];
     tmem_ld_x32(t_addr + (pc * 2) * 32, rr2[0]);
     tmem_ld_x32(t_addr + (pc * 2 + 1) * 32, rr2[1]);
-    stage_fetch_bf16(stg, p.aux, p.ldaux, row0, colp, p.M, p.N, lane);
+    uint32_t stg = stg_;
+    if (PF) stg = stage_pipeline_step<CH / 2>(stg_, stg2, p.aux, p.ldaux, row0, cbase, pc, p.M, p.N, lane);
+    else    stage_fetch_bf16(stg, p.aux, p.ldaux, row0, colp, p.M, p.N, lane);
     tmem_ld_wait();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {

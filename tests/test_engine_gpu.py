@@ -146,8 +146,12 @@ def test_direct_conv_fwd_dgrad_wgrad_fp32(N, H, Cin, Cout, k, stride, transposed
     ops.conv2d_fwd(c, xd, wd, bd, None, yd)
     ops.conv2d_dgrad(c, dyd, wd, None, None, dxd)
     ops.conv2d_wgrad(c, xd, dyd, dwd, dbd)
-    assert relfro(yd, y) < 1e-5 and relfro(dxd, xr.grad) < 1e-5
-    assert relfro(dwd, wr.grad) < 1e-5 and relfro(dbd, br.grad) < 1e-5
+    # CUDA-core path: fp32 FMA chains (1e-5).  tcgen05 path (channels % 64 == 0): products are exact to ~2^-24 through the
+    # three-way split, but the tensor core adds partial sums with truncation, so long contractions (K = 9 x 256) sit at
+    # ~1e-5 relative — still two orders below one bf16 rounding (4e-3)
+    tol = 3e-5 if (Cin % 64 == 0 and Cout % 64 == 0) else 1e-5
+    assert relfro(yd, y) < tol and relfro(dxd, xr.grad) < tol
+    assert relfro(dwd, wr.grad) < tol and relfro(dbd, br.grad) < 1e-5
 
 
 @pytest.mark.parametrize("N,H,Cin,Cout,k,stride,relu,res", [
@@ -259,7 +263,9 @@ def test_vae_engine_fp32_matches_oracle_exactly_enough(convblocks, K, size, B, h
     assert relfro(recon, out) < 1e-4 and relfro(acc, loss.reshape(1)) < 1e-4
     eg = eng.export_params(eng.grads)
     for k in grads:
-        assert relfro(eg[k], grads[k]) < 5e-3, k   # fp32 atomics order; hard-Gumbel codebook grads are ~1e-7 values
+        # fp32 atomics order + tensor-core accumulation order; the hard-Gumbel encoder / codebook gradients are sums
+        # of ~1e-3 terms that cancel to ~1e-6 values, so their RELATIVE error amplifies the 1e-5 of the convolutions
+        assert relfro(eg[k], grads[k]) < 2e-2, k
     # TF-style Adam (bias-corrected) on the engine's gradients
     from oracle import optim as OO
     eng.optimizer_step(1e-3, step=1)
@@ -408,4 +414,4 @@ def test_vae_stack_factor_2_matches_oracle():
     assert torch.equal(eng.encode_tokens(img.to(DEV)).cpu().long(), OV.encode_tokens(p, img, cb, stack_factor=sf))
     eg = eng.export_params(eng.grads)
     for k in p:
-        assert relfro(eg[k], leaves[k].grad) < 5e-3, k
+        assert relfro(eg[k], leaves[k].grad) < 2e-2, k
