@@ -44,7 +44,7 @@ constexpr uint32_t T128B = 128 * 128;  // bytes of one [128 rows][64] swizzled s
 // pairs from lane 0 of four of its warps (role 0 = TMA, 1 = MMA issuer, 2 = first math warp, 3 = last math warp) into
 // the buffer set with db200_dev_attn_trace(); tools/attn_trace.py prints them.  Compiled out of the shipped library.
 #ifdef DB200_DEV_KNOBS
-constexpr int TRACE_EV = 160, TRACE_STRIDE = 37;
+constexpr int TRACE_EV = 320, TRACE_STRIDE = 37;
 __device__ unsigned long long* g_attn_trace = nullptr;
 __device__ int g_attn_trace_slots = 0;
 struct Tracer {
@@ -134,18 +134,6 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
   if (lane == 0) mbar_arrive(bar);
 }
 
-__device__ __forceinline__ void store_row_bf16(bf16* dst, const uint32_t* r, float mul) {
-#pragma unroll
-  for (int e = 0; e < 32; e += 8) {
-    uint4 q;
-    q.x = pack_bf16x2(__uint_as_float(r[e]) * mul, __uint_as_float(r[e + 1]) * mul);
-    q.y = pack_bf16x2(__uint_as_float(r[e + 2]) * mul, __uint_as_float(r[e + 3]) * mul);
-    q.z = pack_bf16x2(__uint_as_float(r[e + 4]) * mul, __uint_as_float(r[e + 5]) * mul);
-    q.w = pack_bf16x2(__uint_as_float(r[e + 6]) * mul, __uint_as_float(r[e + 7]) * mul);
-    *reinterpret_cast<uint4*>(dst + e) = q;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------------
@@ -157,7 +145,7 @@ struct FwdWs {
   static constexpr int NV = (DH == 128) ? (DEEP ? 3 : 2) : (DEEP ? 6 : 4);   // V ring depth
   static constexpr uint32_t TILE = 128 * DH * 2;   // one [128][DH] bf16 operand tile
   static constexpr uint32_t XCH_BYTES = 2 * NG * 128 * 4;
-  static constexpr uint32_t BAR_BYTES = 256;
+  static constexpr uint32_t BAR_BYTES = 320;
   // dynamic shared memory is declared 1024-byte aligned (the 128-byte swizzle needs it): no alignment slack
   static constexpr size_t SMEM = TILE + (NK + NV) * TILE + XCH_BYTES + BAR_BYTES;
   static_assert(SMEM <= 232448, "forward attention: shared memory over the 227 KiB per-CTA limit");
@@ -169,10 +157,23 @@ struct FwdWs {
 // NG = number of softmax warpgroups = column groups of every 128-key block (2: 64 columns per thread, 4: 32).  More
 // groups = more resident warps per scheduler: the per-warp instruction stream is a chain of dependent fp32 / MUFU ops,
 // and with two math warps per scheduler it issues once every ~6 cycles (ncu, profiles/ncu_attn_r02.md).
+//
+// PERSISTENT: the grid is one CTA per SM; CTA c walks the work items c, c + G, c + 2G, ... of the list ordered by
+// decreasing work (item w = (query tile n_qt-1 - w / (B H), head, batch)), so barrier initialisation, the TMEM
+// allocation and — above all — the exposed latency of the first loads are paid once per SM instead of once per
+// 128-query tile (1 280 tiles of 1..10 key blocks at the bench shape: the fixed cost per tile was as large as its work).
+// Every barrier therefore runs on GLOBAL use counters that continue across items:
+//   kc / vc   K / V ring uses         slot = c % N, parity (c / N) & 1
+//   bc        key blocks processed    S / P buffer bc & 1, parity (bc >> 1) & 1;  o_done completes once per P.V: the
+//                                     product of block bc has parity bc & 1
+//   it        items of this CTA       Q buffer parity it & 1; O accumulator it & 1 (double-buffered: the epilogue of
+//                                     item `it` overlaps the first products of item it + 1), o_free[it & 1]
+// The TMA warp is a free-running stream of (Q, K_j, V_j) requests over all items: the loads of the next tile are in
+// flight while the current one finishes.
 template <int DH, int NG, int DEEP>
 __global__ void __launch_bounds__((4 * NG + 2) * 32, 1)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out,
-                   int S, int H, float scale, int xflags) {
+                   int S, int H, int n_items, float scale, int xflags) {
 #ifndef DB200_DEV_KNOBS
   xflags = 0;  // timing experiments exist in development builds only (make DEV=1); results are wrong under them
 #endif
@@ -188,33 +189,37 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   const uint32_t sX = sV + NV * C::TILE;                 // [2 parities][NG groups][128 rows] f32 maxima / sums
   const uint32_t bars = sX + C::XCH_BYTES;
   const uint32_t q_full = bars;
-  const uint32_t k_full = bars + 8;                // [NK]
+  const uint32_t q_empty = bars + 8;               // every logits product of the item has retired: Q may be replaced
+  const uint32_t k_full = bars + 16;               // [NK]
   const uint32_t k_empty = k_full + 8 * NK;        // [NK]
   const uint32_t v_full = k_empty + 8 * NK;        // [NV]
   const uint32_t v_empty = v_full + 8 * NV;        // [NV]
-  const uint32_t s_ready = v_empty + 8 * NV;       // [2]  S buffer b holds block j (j & 1 == b)
+  const uint32_t s_ready = v_empty + 8 * NV;       // [2]  S buffer b holds the block with (bc & 1) == b
   const uint32_t p_ready = s_ready + 16;           // [2]
-  const uint32_t o_done = p_ready + 16;            // P.V of block j has landed in O
-  const uint32_t tmem_slot = o_done + 8;
+  const uint32_t o_done = p_ready + 16;            // a P.V product has landed in O
+  const uint32_t o_free = o_done + 8;              // [2]  the epilogue has read O accumulator b
+  const uint32_t tmem_slot = o_free + 16;
+  static_assert(8 * (2 + 2 * NK + 2 * NV + 2 + 2 + 1 + 2) + 8 <= C::BAR_BYTES, "barrier area");
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* xch = reinterpret_cast<float*>(smem_raw + (sX - raw));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // 1-D grid ordered by work: CTAs are dispatched in linear order, so ALL (batch, head) instances of the latest query
-  // tile (the most key blocks) come first and the light tiles fill the tail (LPT scheduling)
   const int n_qt = (S + 127) >> 7;
-  const int n_bh = gridDim.x / n_qt;
-  const int qt = n_qt - 1 - (int)blockIdx.x / n_bh;
-  const int h = ((int)blockIdx.x % n_bh) % H, b = ((int)blockIdx.x % n_bh) / H;
-  const int n_kv = qt + 1;  // key blocks 0 .. qt; block qt is the diagonal one
+  const int n_bh = n_items / n_qt;
+  const int G = (int)gridDim.x;
 
   if (tid == 0) {
     if (raw & 1023u) __trap();  // the 128-byte swizzle needs 1024-byte aligned tiles
     tma_prefetch_desc(&tmQKV);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
     for (int i = 0; i < NK; ++i) { mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1); }
     for (int i = 0; i < NV; ++i) { mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(s_ready + 8 * i, 1); mbar_init(p_ready + 8 * i, 4 * NG); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_ready + 8 * i, 1);
+      mbar_init(p_ready + 8 * i, 4 * NG);
+      mbar_init(o_free + 8 * i, 4 * NG);
+    }
     mbar_init(o_done, 1);
     fence_mbar_init();
   }
@@ -223,32 +228,40 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
-  const uint32_t tO = tmem + 256;
 
   Tracer tr;
   tr.init(warp == TMA_WARP ? 0 : warp == MMA_WARP ? 1 : warp == 0 ? 2 : warp == 4 * NG - 1 ? 3 : -1, lane);
-  tr.ev(1, n_kv);   // roles start (after barrier init / TMEM allocation)
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, C::TILE);
-      ws_load_tile<DH>(sQ, &tmQKV, q_full, 0 * H + h, qt * 128, b);
-      // the two rings advance independently (K is consumed two blocks ahead of V): poll both, never block on one
-      int jk = 0, jv = 0;
-      while (jk < n_kv || jv < n_kv) {
-        if (jk < n_kv && mbar_try_wait(k_empty + 8 * (jk % NK), ((uint32_t)(jk / NK) & 1u) ^ 1u)) {
-          const int sk = jk % NK;
-          mbar_expect_tx(k_full + 8 * sk, C::TILE);
-          ws_load_tile<DH>(sK + sk * C::TILE, &tmQKV, k_full + 8 * sk, 1 * H + h, jk * 128, b);
-          tr.ev(2, jk);
-          ++jk;
+      // three independent request streams over this CTA's items (Q per item, K_j and V_j per key block); each advances
+      // when its slot is free — polled, never blocking on one
+      int wq = (int)blockIdx.x, itq = 0;
+      int wk = (int)blockIdx.x, jk = 0, kc = 0;
+      int wv = (int)blockIdx.x, jv = 0, vc = 0;
+      while (wq < n_items || wk < n_items || wv < n_items) {
+        if (wq < n_items && mbar_try_wait(q_empty, ((uint32_t)itq & 1u) ^ 1u)) {
+          const int qt = n_qt - 1 - wq / n_bh, bh = wq % n_bh;
+          mbar_expect_tx(q_full, C::TILE);
+          ws_load_tile<DH>(sQ, &tmQKV, q_full, 0 * H + bh % H, qt * 128, bh / H);
+          tr.ev(1, qt + 1);
+          wq += G; ++itq;
         }
-        if (jv < n_kv && mbar_try_wait(v_empty + 8 * (jv % NV), ((uint32_t)(jv / NV) & 1u) ^ 1u)) {
-          const int sv = jv % NV;
+        if (wk < n_items && mbar_try_wait(k_empty + 8 * (kc % NK), ((uint32_t)(kc / NK) & 1u) ^ 1u)) {
+          const int qt = n_qt - 1 - wk / n_bh, bh = wk % n_bh, sk = kc % NK;
+          mbar_expect_tx(k_full + 8 * sk, C::TILE);
+          ws_load_tile<DH>(sK + sk * C::TILE, &tmQKV, k_full + 8 * sk, 1 * H + bh % H, jk * 128, bh / H);
+          tr.ev(2, jk);
+          ++kc;
+          if (++jk > qt) { jk = 0; wk += G; }
+        }
+        if (wv < n_items && mbar_try_wait(v_empty + 8 * (vc % NV), ((uint32_t)(vc / NV) & 1u) ^ 1u)) {
+          const int qt = n_qt - 1 - wv / n_bh, bh = wv % n_bh, sv = vc % NV;
           mbar_expect_tx(v_full + 8 * sv, C::TILE);
-          ws_load_tile<DH>(sV + sv * C::TILE, &tmQKV, v_full + 8 * sv, 2 * H + h, jv * 128, b);
+          ws_load_tile<DH>(sV + sv * C::TILE, &tmQKV, v_full + 8 * sv, 2 * H + bh % H, jv * 128, bh / H);
           tr.ev(3, jv);
-          ++jv;
+          ++vc;
+          if (++jv > qt) { jv = 0; wv += G; }
         }
       }
     }
@@ -256,39 +269,47 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     // ------------------------------------------------------------------------------------------- MMA issuer
     // The whole warp runs this loop convergently (waits, descriptor arithmetic in uniform registers); only the tensor
     // instructions are predicated on the leader lane.
-    {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T : both K-major (K = dh)
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);   // O = P V   : A from TMEM, B MN-major (K = keys)
-      const uint64_t dq = desc_k_base(sQ);
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T : both K-major (K = dh)
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);   // O = P V   : A from TMEM, B MN-major (K = keys)
+    const uint64_t dq = desc_k_base(sQ);
+    uint32_t kc = 0, vc = 0, sc = 0, pc = 0;  // K uses, V uses, logits products issued, P.V products issued
+    int it = 0;
+    for (int w = (int)blockIdx.x; w < n_items; w += G, ++it) {
+      const int n_kv = n_qt - w / n_bh;       // key blocks 0 .. qt
+      const uint32_t tO = tmem + 256 + (it & 1) * DH;
       auto issue_s = [&](int j) {
-        const int sk = j % NK;
+        const uint32_t sk = kc % NK;
         tr.ev(9, j);    // about to wait for K_j
-        mbar_wait(k_full + 8 * sk, (uint32_t)(j / NK) & 1u);
+        mbar_wait(k_full + 8 * sk, (kc / NK) & 1u);
         tc_fence_after();
         const uint64_t dk = desc_k_base(sK + sk * C::TILE);
-        const uint32_t tS = tmem + (j & 1) * 128;
+        const uint32_t tS = tmem + (sc & 1u) * 128;
         if (elect_one_sync()) {
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk)
             umma_bf16_ss(tS, dq + kstep_k(kk), dk + kstep_k(kk), idesc_s, kk > 0 ? 1u : 0u);
-          umma_commit(s_ready + 8 * (j & 1));
+          umma_commit(s_ready + 8 * (sc & 1u));
           umma_commit(k_empty + 8 * sk);
+          if (j == n_kv - 1) umma_commit(q_empty);   // the item's last logits product: Q is free when it retires
         }
         __syncwarp();
+        ++kc; ++sc;
         tr.ev(4, j);    // S_j issued
       };
-      mbar_wait(q_full, 0);
+      mbar_wait(q_full, (uint32_t)it & 1u);
+      tr.ev(1, n_kv);
       issue_s(0);
       if (n_kv > 1) issue_s(1);
       for (int j = 0; j < n_kv; ++j) {
-        const int sv = j % NV;
-        mbar_wait(v_full + 8 * sv, (uint32_t)(j / NV) & 1u);
+        const uint32_t sv = vc % NV;
+        mbar_wait(v_full + 8 * sv, (vc / NV) & 1u);
         tr.ev(11, j);   // V_j has landed
-        mbar_wait(p_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
+        mbar_wait(p_ready + 8 * (pc & 1u), (pc >> 1) & 1u);
         tr.ev(12, j);   // P_j is in TMEM
+        if (j == 0) mbar_wait(o_free + 8 * (it & 1), ((uint32_t)(it >> 1) & 1u) ^ 1u);  // the epilogue of item it-2 is done
         tc_fence_after();
         const uint64_t dv = desc_mn_base(sV + sv * C::TILE);
-        const uint32_t tP = tmem + (j & 1) * 128;
+        const uint32_t tP = tmem + (pc & 1u) * 128;
         if (elect_one_sync()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
@@ -297,6 +318,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
           umma_commit(v_empty + 8 * sv);
         }
         __syncwarp();
+        ++vc; ++pc;
         tr.ev(5, j);    // P.V_j issued
         if (j + 2 < n_kv) issue_s(j + 2);  // into the buffer whose P the product above has just been queued to consume
       }
@@ -305,117 +327,132 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     // ------------------------------------------------------------------------------------------- softmax warpgroups
     const int g = warp >> 2;                       // column group of every key block / of the output
     const int row = tid & 127;                     // query row inside the tile = TMEM lane
-    const int qi = qt * 128 + row;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const float c1 = scale * LOG2E_F;
-    float m_used = -INFINITY;  // the maximum the accumulated P / O / l are scaled by (identical in all groups)
-    float l_run = 0.f;         // partial row sum over this group's key columns
-    for (int j = 0; j < n_kv; ++j) {
-      const uint32_t tS = tmem + (j & 1) * 128 + CG * g + lane_off;
-      mbar_wait(s_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
-      tr.ev(6, j);      // S_j complete (seen by this math warp)
+    uint32_t bc = 0, xc = 0;   // key blocks processed (S / P buffer + o_done parity), exchange-buffer uses
+    int it = 0;
+    for (int w = (int)blockIdx.x; w < n_items; w += G, ++it) {
+      const int qt = n_qt - 1 - w / n_bh, bh = w % n_bh;
+      const int h = bh % H, b = bh / H;
+      const int n_kv = qt + 1;
+      const int qi = qt * 128 + row;
+      const uint32_t tO = tmem + 256 + (it & 1) * DH;
+      float m_used = -INFINITY;  // the maximum the accumulated P / O / l are scaled by (identical in all groups)
+      float l_run = 0.f;         // partial row sum over this group's key columns
+      tr.ev(1, n_kv);
+      for (int j = 0; j < n_kv; ++j, ++bc) {
+        const uint32_t sb = bc & 1u;
+        const uint32_t tS = tmem + sb * 128 + CG * g + lane_off;
+        mbar_wait(s_ready + 8 * sb, (bc >> 1) & 1u);
+        tr.ev(6, j);      // S_j complete (seen by this math warp)
+        tc_fence_after();
+        if (xflags & 2) {  // experiment: pure hand-off chain, no softmax work at all
+          warp_arrive(p_ready + 8 * sb, lane);
+          continue;
+        }
+        uint32_t sv[CG];
+#pragma unroll
+        for (int c = 0; c < CG / 32; ++c) tmem_ld_x32(tS + c * 32, sv + c * 32);
+        tmem_ld_wait();
+        if (j == qt) {  // diagonal block: keys after the query are masked (src/dalle_mtf/models.py:221-227)
+          const int lim = row - CG * g;  // columns c > lim of this slice are in the future
+#pragma unroll
+          for (int c = 0; c < CG; ++c)
+            if (c > lim) sv[c] = 0xff800000u;  // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < CG; c += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(sv[c]));
+          mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
+        }
+        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        float* xp = xch + (xc & 1u) * (NG * 128);
+        ++xc;
+        if (!(xflags & 4)) {  // (experiment bit 2: no cross-group exchange)
+          xp[g * 128 + row] = mx;
+          math_bar_sync<NG>();  // all groups' maxima visible; every group holds its S values in registers
+#pragma unroll
+          for (int o = 1; o < NG; ++o) mx = fmaxf(mx, xp[((g + o) % NG) * 128 + row]);  // finite: key 0 is always visible
+        }
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          const bool need = (mx - m_used) * c1 > 8.f;  // same decision in every thread of a row
+          if (__any_sync(0xffffffffu, need)) {         // tcgen05.ld / st are warp-collective
+            mbar_wait(o_done, (bc - 1u) & 1u);          // the previous P.V has landed in O
+            tc_fence_after();
+            const float alpha = need ? ex2f((m_used - mx) * c1) : 1.f;
+            constexpr int W = OG >= 32 ? 32 : 16;  // this group's share of the output columns
+#pragma unroll
+            for (int c = 0; c < OG / W; ++c) {
+              uint32_t r[W];
+              const uint32_t ta = tO + lane_off + g * OG + c * W;
+              tmem_ld_n<W>(ta, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < W; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_n<W>(ta, r);
+            }
+            if (need) {
+              l_run *= alpha;
+              m_used = mx;
+            }
+          }
+        }
+        // P_j = 2^(c1 (s - m_used)) -> bf16 pairs -> the first CG/2 columns of this group's slice of the S buffer
+        const float mc = m_used * c1;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CG / 32; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = fmaf(__uint_as_float(sv[c * 32 + i]), c1, -mc);
+            float p1 = fmaf(__uint_as_float(sv[c * 32 + i + 1]), c1, -mc);
+            if (!(xflags & 1)) { p0 = ex2f(p0); p1 = ex2f(p1); }  // (experiment bit 0: no MUFU)
+            l0 += p0;
+            l1 += p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_x16(tS + c * 16, pk);
+        }
+        l_run += l0 + l1;
+        tmem_st_wait();
+        warp_arrive(p_ready + 8 * sb, lane);
+        tr.ev(7, j);      // this warp's share of P_j written
+      }
+      // ---- epilogue: O / l -> bf16 (this group's share of the columns), lse.  The exchange slot is the one the last
+      // block did not use; the next block (of the next item) takes the other one, so every reuse of a slot is separated
+      // from its last readers by a math_bar_sync.
+      float* xp = xch + (xc & 1u) * (NG * 128);
+      ++xc;
+      if (xflags & 2) m_used = 0.f;
+      xp[g * 128 + row] = l_run;
+      mbar_wait(o_done, (bc - 1u) & 1u);   // the item's last P.V
+      tr.ev(8, 0);        // last P.V retired: epilogue starts
       tc_fence_after();
-      if (xflags & 2) {  // experiment: pure hand-off chain, no softmax work at all
-        warp_arrive(p_ready + 8 * (j & 1), lane);
-        continue;
+      math_bar_sync<NG>();
+      float l_tot = 0.f;
+#pragma unroll
+      for (int o = 0; o < NG; ++o) l_tot += xp[o * 128 + row];  // same order in every group: identical 1 / l
+      const float inv = 1.f / l_tot;
+      bf16* op = out + (((long long)b * S + qi) * H + h) * DH + g * OG;
+      constexpr int W = OG >= 32 ? 32 : 16;
+#pragma unroll
+      for (int c = 0; c < OG / W; ++c) {
+        uint32_t r[W];
+        tmem_ld_n<W>(tO + lane_off + g * OG + c * W, r);
+        tmem_ld_wait();
+        if (qi < S) store_cols_bf16<W>(op + c * W, r, inv);
       }
-      uint32_t sv[CG];
-#pragma unroll
-      for (int c = 0; c < CG / 32; ++c) tmem_ld_x32(tS + c * 32, sv + c * 32);
-      tmem_ld_wait();
-      if (j == qt) {  // diagonal block: keys after the query are masked (src/dalle_mtf/models.py:221-227)
-        const int lim = row - CG * g;  // columns c > lim of this slice are in the future
-#pragma unroll
-        for (int c = 0; c < CG; ++c)
-          if (c > lim) sv[c] = 0xff800000u;  // -inf
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < CG; c += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sv[c]));
-        mx1 = fmaxf(mx1, __uint_as_float(sv[c + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sv[c + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sv[c + 3]));
-      }
-      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      float* xp = xch + (j & 1) * (NG * 128);
-      if (!(xflags & 4)) {  // (experiment bit 2: no cross-group exchange)
-      xp[g * 128 + row] = mx;
-      math_bar_sync<NG>();  // all groups' maxima visible; every group holds its S values in registers
-#pragma unroll
-      for (int o = 1; o < NG; ++o) mx = fmaxf(mx, xp[((g + o) % NG) * 128 + row]);  // finite: key 0 is always visible
-      }
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        const bool need = (mx - m_used) * c1 > 8.f;  // same decision in every thread of a row
-        if (__any_sync(0xffffffffu, need)) {         // tcgen05.ld / st are warp-collective
-          mbar_wait(o_done, (uint32_t)(j - 1) & 1u);  // the previous P.V has landed in O
-          tc_fence_after();
-          const float alpha = need ? ex2f((m_used - mx) * c1) : 1.f;
-          constexpr int W = OG >= 32 ? 32 : 16;  // this group's share of the output columns
-#pragma unroll
-          for (int c = 0; c < OG / W; ++c) {
-            uint32_t r[W];
-            const uint32_t ta = tO + lane_off + g * OG + c * W;
-            tmem_ld_n<W>(ta, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < W; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-            tmem_st_n<W>(ta, r);
-          }
-          if (need) {
-            l_run *= alpha;
-            m_used = mx;
-          }
-        }
-      }
-      // P_j = 2^(c1 (s - m_used)) -> bf16 pairs -> the first CG/2 columns of this group's slice of the S buffer
-      const float mc = m_used * c1;
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < CG / 32; ++c) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = fmaf(__uint_as_float(sv[c * 32 + i]), c1, -mc);
-          float p1 = fmaf(__uint_as_float(sv[c * 32 + i + 1]), c1, -mc);
-          if (!(xflags & 1)) { p0 = ex2f(p0); p1 = ex2f(p1); }  // (experiment bit 0: no MUFU)
-          l0 += p0;
-          l1 += p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        tmem_st_x16(tS + c * 16, pk);
-      }
-      l_run += l0 + l1;
-      tmem_st_wait();
-      warp_arrive(p_ready + 8 * (j & 1), lane);
-      tr.ev(7, j);      // this warp's share of P_j written
+      warp_arrive(o_free + 8 * (it & 1), lane);   // this O accumulator may be overwritten (item it + 2)
+      if (qi < S && g == 0) lse_out[((long long)b * H + h) * S + qi] = m_used * scale + logf(l_tot);
+      tr.ev(10, 0);       // item done
     }
-    // ---- epilogue: O / l -> bf16 (this group's share of the columns), lse
-    float* xp = xch + (n_kv & 1) * (NG * 128);  // the parity the last block did not use
-    if (xflags & 2) m_used = 0.f;
-    xp[g * 128 + row] = l_run;
-    mbar_wait(o_done, (uint32_t)(n_kv - 1) & 1u);
-    tr.ev(8, 0);        // last P.V retired: epilogue starts
-    tc_fence_after();
-    math_bar_sync<NG>();
-    float l_tot = 0.f;
-#pragma unroll
-    for (int o = 0; o < NG; ++o) l_tot += xp[o * 128 + row];  // same order in every group: identical 1 / l
-    const float inv = 1.f / l_tot;
-    bf16* op = out + (((long long)b * S + qi) * H + h) * DH + g * OG;
-    constexpr int W = OG >= 32 ? 32 : 16;
-#pragma unroll
-    for (int c = 0; c < OG / W; ++c) {
-      uint32_t r[W];
-      tmem_ld_n<W>(tO + lane_off + g * OG + c * W, r);
-      tmem_ld_wait();
-      if (qi < S) store_cols_bf16<W>(op + c * W, r, inv);
-    }
-    if (qi < S && g == 0) lse_out[((long long)b * H + h) * S + qi] = m_used * scale + logf(l_tot);
   }
-  tr.ev(10, 0);         // role done
   tc_fence_before();
   __syncthreads();
   if (warp == TMA_WARP) {
@@ -445,13 +482,18 @@ struct BwdWs {
 };
 }  // namespace
 
-// dK / dV: CTA = 128 keys (TMEM lanes), loop over the 128-query blocks i >= its own.  TMEM: dV [0,dh) dK [dh,2dh)
-// S^T [256,384) dP^T [384,512).
+// dK / dV: work item = 128 keys (TMEM lanes) of one (batch, head), loop over the 128-query blocks i >= its own.
+// TMEM: dV [0,dh) dK [dh,2dh) S^T [256,384) dP^T [384,512).
+// Persistent like the forward: CTA c walks items c, c + G, ... of the list ordered by decreasing work (item w = key
+// block w / (B H), heaviest = block 0).  Global use counters: ac / bc2 (Q_i / dO_i ring uses), gb (query blocks processed:
+// S^T / dP^T / P^T / dS^T hand-offs have parity gb & 1, the lse / delta staging slot is gb & 1), itm (items: resident
+// K | V pair and the accumulators, parity itm & 1).  The accumulators are single-buffered (TMEM is full): the first dV
+// product of an item waits for the previous epilogue (acc_free); the item's logits products and phase A run before that.
 template <int DH, int NG>
 __global__ void __launch_bounds__((4 * NG + 4) * 32, 1)
 attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                         const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv,
-                        int S, int H, float scale) {
+                        int S, int H, int n_items, float scale) {
   using C = BwdWs<DH, NG>;
   constexpr int NA = C::NA, NB = C::NB;
   constexpr int CG = 128 / NG;       // query columns of a block per group (= per thread)
@@ -464,42 +506,42 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   const uint32_t sOr = sQr + NA * C::TILE;      // dO_i ring (NB deep): released after dV of its block
   const uint32_t sStat = sOr + NB * C::TILE;    // [2][lse2 128 | delta 128]
   const uint32_t bars = sStat + C::STAT_BYTES;
-  const uint32_t x_full = bars;
-  const uint32_t a_full = bars + 8;             // [NA]
+  const uint32_t x_full = bars;                 // this item's K | V pair has landed
+  const uint32_t x_empty = bars + 8;            // every logits product that reads it has retired
+  const uint32_t a_full = bars + 16;            // [NA]
   const uint32_t a_empty = a_full + 8 * NA;     // [NA]
   const uint32_t b_full = a_empty + 8 * NA;     // [NB]
   const uint32_t b_empty = b_full + 8 * NB;     // [NB]
   const uint32_t stat_full = b_empty + 8 * NB;  // [2]
-  const uint32_t sa_ready = stat_full + 16;     // S^T of block it in TMEM
+  const uint32_t sa_ready = stat_full + 16;     // S^T of the block in TMEM
   const uint32_t sb_ready = sa_ready + 8;       // dP^T
   const uint32_t pa_ready = sb_ready + 8;       // P^T written (all math warps)
   const uint32_t pb_ready = pa_ready + 8;       // dS^T written
-  const uint32_t acc_done = pb_ready + 8;
-  const uint32_t tmem_slot = acc_done + 8;
+  const uint32_t acc_done = pb_ready + 8;       // the item's last dK product has retired
+  const uint32_t acc_free = acc_done + 8;       // the epilogue has read dV | dK (all math warps)
+  const uint32_t tmem_slot = acc_free + 8;
+  static_assert(8 * (2 + 2 * NA + 2 * NB + 2 + 4 + 2) + 8 <= C::BAR_BYTES, "barrier area");
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   const float* stat = reinterpret_cast<const float*>(smem_raw + (sStat - raw));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // 1-D grid, heaviest first: key block 0 is seen by every query block
   const int n_blk = (S + 127) >> 7;
-  const int n_bh = gridDim.x / n_blk;
-  const int jb = (int)blockIdx.x / n_bh;
-  const int h = ((int)blockIdx.x % n_bh) % H, b = ((int)blockIdx.x % n_bh) / H;
-  const int r0 = jb * 128;
-  const int n_it = n_blk - jb;
-  const long long bh = (long long)b * H + h;
+  const int n_bh = n_items / n_blk;
+  const int G = (int)gridDim.x;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     if (raw & 1023u) __trap();  // the 128-byte swizzle needs 1024-byte aligned tiles
     mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
     for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) mbar_init(stat_full + 8 * i, 1);
     mbar_init(sa_ready, 1); mbar_init(sb_ready, 1);
     mbar_init(pa_ready, 4 * NG); mbar_init(pb_ready, 4 * NG);
     mbar_init(acc_done, 1);
+    mbar_init(acc_free, 4 * NG);
     fence_mbar_init();
   }
   if (warp == TMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -511,41 +553,54 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
   Tracer tr;
   tr.init(warp == TMA_WARP ? 0 : warp == MMA_WARP ? 1 : warp == 0 ? 2 : warp == 4 * NG - 1 ? 3 : -1, lane);
-  tr.ev(1, n_it);
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      mbar_expect_tx(x_full, 2 * C::TILE);
-      ws_load_tile<DH>(sK, &tmQKV, x_full, 1 * H + h, r0, b);
-      ws_load_tile<DH>(sV, &tmQKV, x_full, 2 * H + h, r0, b);
-      int ia = 0, ib = 0;  // the rings advance independently: poll both, never block on one
-      while (ia < n_it || ib < n_it) {
-        if (ia < n_it && mbar_try_wait(a_empty + 8 * (ia % NA), ((uint32_t)(ia / NA) & 1u) ^ 1u)) {
-          const int st = ia % NA;
-          mbar_expect_tx(a_full + 8 * st, C::TILE);
-          ws_load_tile<DH>(sQr + st * C::TILE, &tmQKV, a_full + 8 * st, 0 * H + h, (jb + ia) * 128, b);   // Q_i
-          tr.ev(2, ia);
-          ++ia;
+      // three request streams over this CTA's items: the resident K | V pair, Q_i, dO_i — polled, never blocking
+      int wx = (int)blockIdx.x, itx = 0;
+      int wa = (int)blockIdx.x, ia = 0, ac = 0;
+      int wb = (int)blockIdx.x, ib = 0, bc2 = 0;
+      while (wx < n_items || wa < n_items || wb < n_items) {
+        if (wx < n_items && mbar_try_wait(x_empty, ((uint32_t)itx & 1u) ^ 1u)) {
+          const int jb = wx / n_bh, bh = wx % n_bh;
+          mbar_expect_tx(x_full, 2 * C::TILE);
+          ws_load_tile<DH>(sK, &tmQKV, x_full, 1 * H + bh % H, jb * 128, bh / H);
+          ws_load_tile<DH>(sV, &tmQKV, x_full, 2 * H + bh % H, jb * 128, bh / H);
+          tr.ev(1, n_blk - jb);
+          wx += G; ++itx;
         }
-        if (ib < n_it && mbar_try_wait(b_empty + 8 * (ib % NB), ((uint32_t)(ib / NB) & 1u) ^ 1u)) {
-          const int st = ib % NB;
+        if (wa < n_items && mbar_try_wait(a_empty + 8 * (ac % NA), ((uint32_t)(ac / NA) & 1u) ^ 1u)) {
+          const int jb = wa / n_bh, bh = wa % n_bh, st = ac % NA;
+          mbar_expect_tx(a_full + 8 * st, C::TILE);
+          ws_load_tile<DH>(sQr + st * C::TILE, &tmQKV, a_full + 8 * st, 0 * H + bh % H, (jb + ia) * 128, bh / H);   // Q_i
+          tr.ev(2, ia);
+          ++ac;
+          if (++ia >= n_blk - jb) { ia = 0; wa += G; }
+        }
+        if (wb < n_items && mbar_try_wait(b_empty + 8 * (bc2 % NB), ((uint32_t)(bc2 / NB) & 1u) ^ 1u)) {
+          const int jb = wb / n_bh, bh = wb % n_bh, st = bc2 % NB;
           mbar_expect_tx(b_full + 8 * st, C::TILE);
-          ws_load_tile<DH>(sOr + st * C::TILE, &tmDO, b_full + 8 * st, h, (jb + ib) * 128, b);            // dO_i
+          ws_load_tile<DH>(sOr + st * C::TILE, &tmDO, b_full + 8 * st, bh % H, (jb + ib) * 128, bh / H);            // dO_i
           tr.ev(3, ib);
-          ++ib;
+          ++bc2;
+          if (++ib >= n_blk - jb) { ib = 0; wb += G; }
         }
       }
     }
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     // convergent warp: waits and descriptor arithmetic by all lanes (uniform registers), tensor instructions predicated
-    {
-      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);  // logits: both operands K-major (K = dh)
-      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // gradients: A from TMEM, B MN-major (K = queries)
-      const uint64_t dkk = desc_k_base(sK), dvk = desc_k_base(sV);
+    constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);  // logits: both operands K-major (K = dh)
+    constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // gradients: A from TMEM, B MN-major (K = queries)
+    const uint64_t dkk = desc_k_base(sK), dvk = desc_k_base(sV);
+    uint32_t sa = 0, sb = 0;   // S^T / dP^T products issued (= Q_i / dO_i ring uses consumed by them)
+    uint32_t gb = 0;           // query blocks whose gradient products were issued
+    int itm = 0;
+    for (int w = (int)blockIdx.x; w < n_items; w += G, ++itm) {
+      const int n_it = n_blk - w / n_bh;
       auto issue_s = [&](int it) {   // S^T = K Q_i^T
-        const int st = it % NA;
-        mbar_wait(a_full + 8 * st, (uint32_t)(it / NA) & 1u);
+        const uint32_t st = sa % NA;
+        mbar_wait(a_full + 8 * st, (sa / NA) & 1u);
         tc_fence_after();
         const uint64_t q = desc_k_base(sQr + st * C::TILE);
         if (elect_one_sync()) {
@@ -555,11 +610,12 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           umma_commit(sa_ready);
         }
         __syncwarp();
+        ++sa;
         tr.ev(4, it);    // S^T issued
       };
       auto issue_dp = [&](int it) {  // dP^T = V dO_i^T
-        const int st = it % NB;
-        mbar_wait(b_full + 8 * st, (uint32_t)(it / NB) & 1u);
+        const uint32_t st = sb % NB;
+        mbar_wait(b_full + 8 * st, (sb / NB) & 1u);
         tc_fence_after();
         const uint64_t o = desc_k_base(sOr + st * C::TILE);
         if (elect_one_sync()) {
@@ -567,36 +623,41 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           for (int kk = 0; kk < DH / 16; ++kk)
             umma_bf16_ss(tdPT, dvk + kstep_k(kk), o + kstep_k(kk), idesc_l, kk > 0 ? 1u : 0u);
           umma_commit(sb_ready);
+          if (it == n_it - 1) umma_commit(x_empty);   // the item's last logits product: K | V may be replaced
         }
         __syncwarp();
+        ++sb;
         tr.ev(14, it);   // dP^T issued
       };
-      mbar_wait(x_full, 0);
+      mbar_wait(x_full, (uint32_t)itm & 1u);
+      tr.ev(1, n_it);
       issue_s(0);
       issue_dp(0);
-      for (int it = 0; it < n_it; ++it) {
-        const uint64_t q = desc_mn_base(sQr + (it % NA) * C::TILE), o = desc_mn_base(sOr + (it % NB) * C::TILE);
+      for (int it = 0; it < n_it; ++it, ++gb) {
+        const uint32_t sta = gb % NA, stb = gb % NB;   // ring slots of this block's Q_i / dO_i (use counter = block counter)
+        const uint64_t q = desc_mn_base(sQr + sta * C::TILE), o = desc_mn_base(sOr + stb * C::TILE);
         const uint32_t acc = it > 0 ? 1u : 0u;
-        mbar_wait(pa_ready, (uint32_t)it & 1u);
+        mbar_wait(pa_ready, gb & 1u);
         tr.ev(12, it);   // P^T is in TMEM
+        if (it == 0) mbar_wait(acc_free, ((uint32_t)itm & 1u) ^ 1u);   // the previous item's epilogue has read dV | dK
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i
             umma_bf16_ts(tmem, tST + ts_split_col<NG>(kk), o + kstep_mn(kk), idesc_g, kk > 0 ? 1u : acc);
-          umma_commit(b_empty + 8 * (it % NB));  // dO_i is free
+          umma_commit(b_empty + 8 * stb);  // dO_i is free
         }
         __syncwarp();
         tr.ev(5, it);    // dV issued
         if (it + 1 < n_it) issue_s(it + 1);      // runs under phase B of this block
-        mbar_wait(pb_ready, (uint32_t)it & 1u);
+        mbar_wait(pb_ready, gb & 1u);
         tr.ev(15, it);   // dS^T is in TMEM
         tc_fence_after();
         if (elect_one_sync()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
             umma_bf16_ts(tmem + DH, tdPT + ts_split_col<NG>(kk), q + kstep_mn(kk), idesc_g, kk > 0 ? 1u : acc);
-          umma_commit(a_empty + 8 * (it % NA));  // Q_i is free
+          umma_commit(a_empty + 8 * sta);  // Q_i is free
           if (it == n_it - 1) umma_commit(acc_done);
         }
         __syncwarp();
@@ -607,109 +668,122 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   } else if (warp == STAT_WARP) {
     // ------------------------------------------------------------------------------------------- lse / delta stager
     float* stat_w = reinterpret_cast<float*>(smem_raw + (sStat - raw));
-    for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1;
-      // slot `st` was last read by phase B of block it-2, which precedes the dK product that frees Q_{it-2}
-      if (it >= 2) mbar_wait(a_empty + 8 * ((it - 2) % NA), (uint32_t)((it - 2) / NA) & 1u);
+    uint32_t gb = 0;
+    for (int w = (int)blockIdx.x; w < n_items; w += G) {
+      const int jb = w / n_bh, n_it = n_blk - jb;
+      const long long bh = w % n_bh;   // = b * H + h
+      for (int it = 0; it < n_it; ++it, ++gb) {
+        const uint32_t st = gb & 1u;
+        // slot `st` was last read by phase B of block gb-2, which precedes the dK product that frees that block's Q
+        if (gb >= 2) mbar_wait(a_empty + 8 * ((gb - 2) % NA), ((gb - 2) / NA) & 1u);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = lane + 32 * u, q = (jb + it) * 128 + c;
-        float l2 = INFINITY, d = 0.f;  // out-of-range query: p = 2^(-inf) = 0
-        if (q < S) {
-          l2 = lse[bh * S + q] * LOG2E_F;
-          d = delta[bh * S + q];
+        for (int u = 0; u < 4; ++u) {
+          const int c = lane + 32 * u, q = (jb + it) * 128 + c;
+          float l2 = INFINITY, d = 0.f;  // out-of-range query: p = 2^(-inf) = 0
+          if (q < S) {
+            l2 = lse[bh * S + q] * LOG2E_F;
+            d = delta[bh * S + q];
+          }
+          stat_w[st * 256 + c] = l2;
+          stat_w[st * 256 + 128 + c] = d;
         }
-        stat_w[st * 256 + c] = l2;
-        stat_w[st * 256 + 128 + c] = d;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(stat_full + 8 * st);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(stat_full + 8 * st);
     }
   } else if (warp < 4 * NG) {
     // ------------------------------------------------------------------------------------------- gradient warpgroups
     const int g = warp >> 2;            // query columns [CG g, CG g + CG) of every block
     const int row = tid & 127;          // key row = TMEM lane
-    const int ki = r0 + row;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const uint32_t tS = tST + CG * g + lane_off, tdP = tdPT + CG * g + lane_off;
     const float c1 = scale * LOG2E_F;
-    for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1;
-      const float4* sl = reinterpret_cast<const float4*>(stat + st * 256 + CG * g);
-      const float4* sd = reinterpret_cast<const float4*>(stat + st * 256 + 128 + CG * g);
-      // ---- phase A: P^T = 2^(c1 s - lse2[query]); pair dropped where key > query (only the first block is diagonal)
-      mbar_wait(stat_full + 8 * st, (uint32_t)(it >> 1) & 1u);
-      mbar_wait(sa_ready, (uint32_t)it & 1u);
-      tr.ev(6, it);
-      tc_fence_after();
-      uint32_t pk[CG / 2];
-      const int lim = (it == 0) ? row - CG * g : -1;  // columns c < lim are queries before this key
+    uint32_t gb = 0;
+    int itm = 0;
+    for (int w = (int)blockIdx.x; w < n_items; w += G, ++itm) {
+      const int jb = w / n_bh, n_it = n_blk - jb;
+      const int h = (w % n_bh) % H, b = (w % n_bh) / H;
+      const int ki = jb * 128 + row;
+      tr.ev(1, n_it);
+      for (int it = 0; it < n_it; ++it, ++gb) {
+        const uint32_t st = gb & 1u;
+        const float4* sl = reinterpret_cast<const float4*>(stat + st * 256 + CG * g);
+        const float4* sd = reinterpret_cast<const float4*>(stat + st * 256 + 128 + CG * g);
+        // ---- phase A: P^T = 2^(c1 s - lse2[query]); pair dropped where key > query (only the first block is diagonal)
+        mbar_wait(stat_full + 8 * st, (gb >> 1) & 1u);
+        mbar_wait(sa_ready, gb & 1u);
+        tr.ev(6, it);
+        tc_fence_after();
+        uint32_t pk[CG / 2];
+        const int lim = (it == 0) ? row - CG * g : -1;  // columns c < lim are queries before this key
 #pragma unroll
-      for (int c = 0; c < CG / 32; ++c) {
-        uint32_t rs[32];
-        tmem_ld_x32(tS + c * 32, rs);
-        tmem_ld_wait();
+        for (int c = 0; c < CG / 32; ++c) {
+          uint32_t rs[32];
+          tmem_ld_x32(tS + c * 32, rs);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 a = sl[(c * 32 + i) >> 2];
-          float p0 = ex2f(fmaf(__uint_as_float(rs[i]), c1, -a.x)), p1 = ex2f(fmaf(__uint_as_float(rs[i + 1]), c1, -a.y));
-          float p2 = ex2f(fmaf(__uint_as_float(rs[i + 2]), c1, -a.z)), p3 = ex2f(fmaf(__uint_as_float(rs[i + 3]), c1, -a.w));
-          const int cc = c * 32 + i;
-          if (cc < lim) p0 = 0.f;
-          if (cc + 1 < lim) p1 = 0.f;
-          if (cc + 2 < lim) p2 = 0.f;
-          if (cc + 3 < lim) p3 = 0.f;
-          pk[(cc >> 1)] = pack_bf16x2(p0, p1);
-          pk[(cc >> 1) + 1] = pack_bf16x2(p2, p3);
+          for (int i = 0; i < 32; i += 4) {
+            const float4 a = sl[(c * 32 + i) >> 2];
+            float p0 = ex2f(fmaf(__uint_as_float(rs[i]), c1, -a.x)), p1 = ex2f(fmaf(__uint_as_float(rs[i + 1]), c1, -a.y));
+            float p2 = ex2f(fmaf(__uint_as_float(rs[i + 2]), c1, -a.z)), p3 = ex2f(fmaf(__uint_as_float(rs[i + 3]), c1, -a.w));
+            const int cc = c * 32 + i;
+            if (cc < lim) p0 = 0.f;
+            if (cc + 1 < lim) p1 = 0.f;
+            if (cc + 2 < lim) p2 = 0.f;
+            if (cc + 3 < lim) p3 = 0.f;
+            pk[(cc >> 1)] = pack_bf16x2(p0, p1);
+            pk[(cc >> 1) + 1] = pack_bf16x2(p2, p3);
+          }
         }
-      }
-      tmem_st_n<CG / 2>(tS, pk);
-      tmem_st_wait();
-      warp_arrive(pa_ready, lane);
-      tr.ev(7, it);
-      // ---- phase B: dS^T = (P^T * scale) (dP^T - delta[query])
-      mbar_wait(sb_ready, (uint32_t)it & 1u);
-      tr.ev(17, it);
-      tc_fence_after();
-      uint32_t dk[CG / 2];
+        tmem_st_n<CG / 2>(tS, pk);
+        tmem_st_wait();
+        warp_arrive(pa_ready, lane);
+        tr.ev(7, it);
+        // ---- phase B: dS^T = (P^T * scale) (dP^T - delta[query])
+        mbar_wait(sb_ready, gb & 1u);
+        tr.ev(17, it);
+        tc_fence_after();
+        uint32_t dk[CG / 2];
 #pragma unroll
-      for (int c = 0; c < CG / 32; ++c) {
-        uint32_t rd[32];
-        tmem_ld_x32(tdP + c * 32, rd);
-        tmem_ld_wait();
+        for (int c = 0; c < CG / 32; ++c) {
+          uint32_t rd[32];
+          tmem_ld_x32(tdP + c * 32, rd);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 d4 = sd[(c * 32 + i) >> 2];
-          const int cc = c * 32 + i;
-          const float2 pa = unpack_bf16x2(pk[cc >> 1]), pb = unpack_bf16x2(pk[(cc >> 1) + 1]);
-          dk[cc >> 1] = pack_bf16x2((pa.x * scale) * (__uint_as_float(rd[i]) - d4.x),
-                                    (pa.y * scale) * (__uint_as_float(rd[i + 1]) - d4.y));
-          dk[(cc >> 1) + 1] = pack_bf16x2((pb.x * scale) * (__uint_as_float(rd[i + 2]) - d4.z),
-                                          (pb.y * scale) * (__uint_as_float(rd[i + 3]) - d4.w));
+          for (int i = 0; i < 32; i += 4) {
+            const float4 d4 = sd[(c * 32 + i) >> 2];
+            const int cc = c * 32 + i;
+            const float2 pa = unpack_bf16x2(pk[cc >> 1]), pb = unpack_bf16x2(pk[(cc >> 1) + 1]);
+            dk[cc >> 1] = pack_bf16x2((pa.x * scale) * (__uint_as_float(rd[i]) - d4.x),
+                                      (pa.y * scale) * (__uint_as_float(rd[i + 1]) - d4.y));
+            dk[(cc >> 1) + 1] = pack_bf16x2((pb.x * scale) * (__uint_as_float(rd[i + 2]) - d4.z),
+                                            (pb.y * scale) * (__uint_as_float(rd[i + 3]) - d4.w));
+          }
         }
+        tmem_st_n<CG / 2>(tdP, dk);
+        tmem_st_wait();
+        warp_arrive(pb_ready, lane);
+        tr.ev(18, it);
       }
-      tmem_st_n<CG / 2>(tdP, dk);
-      tmem_st_wait();
-      warp_arrive(pb_ready, lane);
-      tr.ev(18, it);
-    }
-    // ---- epilogue: the 2 dh accumulator columns (dV | dK) are split evenly over the groups
-    mbar_wait(acc_done, 0);
-    tr.ev(8, 0);
-    tc_fence_after();
-    constexpr int EG = 2 * DH / NG;                 // columns per group
-    const int acc_i = (g * EG) / DH;                // 0: dV, 1: dK
-    const int col0 = (g * EG) % DH;
-    bf16* dst = dqkv + ((((long long)b * S + ki) * 3 + (acc_i == 0 ? 2 : 1)) * H + h) * DH + col0;
+      // ---- epilogue: the 2 dh accumulator columns (dV | dK) are split evenly over the groups
+      mbar_wait(acc_done, (uint32_t)itm & 1u);
+      tr.ev(8, 0);
+      tc_fence_after();
+      constexpr int EG = 2 * DH / NG;                 // columns per group
+      const int acc_i = (g * EG) / DH;                // 0: dV, 1: dK
+      const int col0 = (g * EG) % DH;
+      bf16* dst = dqkv + ((((long long)b * S + ki) * 3 + (acc_i == 0 ? 2 : 1)) * H + h) * DH + col0;
 #pragma unroll 1
-    for (int c = 0; c < EG / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_x32(tmem + lane_off + g * EG + c * 32, r);
-      tmem_ld_wait();
-      if (ki < S) store_cols_bf16<32>(dst + c * 32, r, 1.f);
+      for (int c = 0; c < EG / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(tmem + lane_off + g * EG + c * 32, r);
+        tmem_ld_wait();
+        if (ki < S) store_cols_bf16<32>(dst + c * 32, r, 1.f);
+      }
+      warp_arrive(acc_free, lane);   // dV | dK may be overwritten by the next item
+      tr.ev(10, 0);
     }
   }
-  tr.ev(10, 0);
   tc_fence_before();
   __syncthreads();
   if (warp == TMA_WARP) {
@@ -719,13 +793,16 @@ attn_bwd_dkdv_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   tr.ev(13, 0);
 }
 
-// dQ: CTA = 128 queries (TMEM lanes), loop over the 128-key blocks j <= its own.  TMEM: dQ [0,dh) S [128,256)
-// dP [256,384) dS [384,448) [448,512).
+// dQ: work item = 128 queries (TMEM lanes) of one (batch, head), loop over the 128-key blocks j <= its own.
+// TMEM: dQ [0,dh) S [128,256) dP [256,384) dS [384,448) [448,512).  Persistent (see the forward): item w = query tile
+// n_blk-1 - w / (B H); global counters la (logits pairs issued = K_j / V_j ring uses), gb (key blocks whose dQ product
+// was issued / processed: S | dP hand-offs have parity gb & 1, the dS slot is gb & 1), itm (items: resident Q | dO pair
+// and the dQ accumulator).
 template <int DH, int NG>
 __global__ void __launch_bounds__((4 * NG + 4) * 32, 1)
 attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                       const float* __restrict__ lse, const float* __restrict__ delta, bf16* __restrict__ dqkv, int S,
-                      int H, float scale) {
+                      int H, int n_items, float scale) {
   using C = BwdWs<DH, NG>;
   constexpr int NA = C::NA, NB = C::NB;
   constexpr int CG = 128 / NG;       // key columns of a block per group (= per thread)
@@ -737,40 +814,40 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   const uint32_t sKr = sdO + C::TILE;            // K_j ring (NA deep): needed until dQ of its block
   const uint32_t sVr = sKr + NA * C::TILE;       // V_j ring (NB deep): released right after dP of its block
   const uint32_t bars = sVr + NB * C::TILE + C::STAT_BYTES;
-  const uint32_t x_full = bars;
-  const uint32_t a_full = bars + 8;              // [NA]
+  const uint32_t x_full = bars;                  // this item's Q | dO pair has landed
+  const uint32_t x_empty = bars + 8;             // every logits product that reads it has retired
+  const uint32_t a_full = bars + 16;             // [NA]
   const uint32_t a_empty = a_full + 8 * NA;      // [NA]
   const uint32_t b_full = a_empty + 8 * NA;      // [NB]
   const uint32_t b_empty = b_full + 8 * NB;      // [NB]
-  const uint32_t sd_ready = b_empty + 8 * NB;    // S, dP of block j in TMEM
+  const uint32_t sd_ready = b_empty + 8 * NB;    // S, dP of the block in TMEM
   const uint32_t sd_loaded = sd_ready + 8;       // every group holds them in registers (all math warps)
-  const uint32_t ds_ready = sd_loaded + 8;       // [2] dS of block j written (all math warps)
+  const uint32_t ds_ready = sd_loaded + 8;       // [2] dS of the block written (all math warps)
   const uint32_t ds_free = ds_ready + 16;        // [2] the dQ product has consumed that dS slot
-  const uint32_t acc_done = ds_free + 16;
-  const uint32_t tmem_slot = acc_done + 8;
+  const uint32_t acc_done = ds_free + 16;        // the item's last dQ product has retired
+  const uint32_t acc_free = acc_done + 8;        // the epilogue has read dQ (all math warps)
+  const uint32_t tmem_slot = acc_free + 8;
+  static_assert(8 * (2 + 2 * NA + 2 * NB + 2 + 4 + 2) + 8 <= C::BAR_BYTES, "barrier area");
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // 1-D grid, heaviest first: the last query tile sees every key block
   const int n_blk = (S + 127) >> 7;
-  const int n_bh = gridDim.x / n_blk;
-  const int ib = n_blk - 1 - (int)blockIdx.x / n_bh;
-  const int h = ((int)blockIdx.x % n_bh) % H, b = ((int)blockIdx.x % n_bh) / H;
-  const int r0 = ib * 128;
-  const int n_it = ib + 1;
-  const long long bh = (long long)b * H + h;
+  const int n_bh = n_items / n_blk;
+  const int G = (int)gridDim.x;
 
   if (tid == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
     if (raw & 1023u) __trap();  // the 128-byte swizzle needs 1024-byte aligned tiles
     mbar_init(x_full, 1);
+    mbar_init(x_empty, 1);
     for (int i = 0; i < NA; ++i) { mbar_init(a_full + 8 * i, 1); mbar_init(a_empty + 8 * i, 1); }
     for (int i = 0; i < NB; ++i) { mbar_init(b_full + 8 * i, 1); mbar_init(b_empty + 8 * i, 1); }
     mbar_init(sd_ready, 1);
     mbar_init(sd_loaded, 4 * NG);
     for (int i = 0; i < 2; ++i) { mbar_init(ds_ready + 8 * i, 4 * NG); mbar_init(ds_free + 8 * i, 1); }
     mbar_init(acc_done, 1);
+    mbar_init(acc_free, 4 * NG);
     fence_mbar_init();
   }
   if (warp == TMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -783,37 +860,50 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
   if (warp == TMA_WARP) {
     // ------------------------------------------------------------------------------------------- TMA producer
     if (lane == 0) {
-      mbar_expect_tx(x_full, 2 * C::TILE);
-      ws_load_tile<DH>(sQ, &tmQKV, x_full, 0 * H + h, r0, b);
-      ws_load_tile<DH>(sdO, &tmDO, x_full, h, r0, b);
-      int ia = 0, ib2 = 0;  // the rings advance independently: poll both, never block on one
-      while (ia < n_it || ib2 < n_it) {
-        if (ia < n_it && mbar_try_wait(a_empty + 8 * (ia % NA), ((uint32_t)(ia / NA) & 1u) ^ 1u)) {
-          const int st = ia % NA;
-          mbar_expect_tx(a_full + 8 * st, C::TILE);
-          ws_load_tile<DH>(sKr + st * C::TILE, &tmQKV, a_full + 8 * st, 1 * H + h, ia * 128, b);   // K_j
-          ++ia;
+      // three request streams over this CTA's items: the resident Q | dO pair, K_j, V_j — polled, never blocking
+      int wx = (int)blockIdx.x, itx = 0;
+      int wa = (int)blockIdx.x, ia = 0, ac = 0;
+      int wb = (int)blockIdx.x, ib2 = 0, bc2 = 0;
+      while (wx < n_items || wa < n_items || wb < n_items) {
+        if (wx < n_items && mbar_try_wait(x_empty, ((uint32_t)itx & 1u) ^ 1u)) {
+          const int ib = n_blk - 1 - wx / n_bh, bh = wx % n_bh;
+          mbar_expect_tx(x_full, 2 * C::TILE);
+          ws_load_tile<DH>(sQ, &tmQKV, x_full, 0 * H + bh % H, ib * 128, bh / H);
+          ws_load_tile<DH>(sdO, &tmDO, x_full, bh % H, ib * 128, bh / H);
+          wx += G; ++itx;
         }
-        if (ib2 < n_it && mbar_try_wait(b_empty + 8 * (ib2 % NB), ((uint32_t)(ib2 / NB) & 1u) ^ 1u)) {
-          const int st = ib2 % NB;
+        if (wa < n_items && mbar_try_wait(a_empty + 8 * (ac % NA), ((uint32_t)(ac / NA) & 1u) ^ 1u)) {
+          const int ib = n_blk - 1 - wa / n_bh, bh = wa % n_bh, st = ac % NA;
+          mbar_expect_tx(a_full + 8 * st, C::TILE);
+          ws_load_tile<DH>(sKr + st * C::TILE, &tmQKV, a_full + 8 * st, 1 * H + bh % H, ia * 128, bh / H);   // K_j
+          ++ac;
+          if (++ia > ib) { ia = 0; wa += G; }
+        }
+        if (wb < n_items && mbar_try_wait(b_empty + 8 * (bc2 % NB), ((uint32_t)(bc2 / NB) & 1u) ^ 1u)) {
+          const int ib = n_blk - 1 - wb / n_bh, bh = wb % n_bh, st = bc2 % NB;
           mbar_expect_tx(b_full + 8 * st, C::TILE);
-          ws_load_tile<DH>(sVr + st * C::TILE, &tmQKV, b_full + 8 * st, 2 * H + h, ib2 * 128, b);  // V_j
-          ++ib2;
+          ws_load_tile<DH>(sVr + st * C::TILE, &tmQKV, b_full + 8 * st, 2 * H + bh % H, ib2 * 128, bh / H);  // V_j
+          ++bc2;
+          if (++ib2 > ib) { ib2 = 0; wb += G; }
         }
       }
     }
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------------------------------- MMA issuer
     // convergent warp: waits and descriptor arithmetic by all lanes (uniform registers), tensor instructions predicated
-    {
-      constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dQ = dS K : A from TMEM, B MN-major (K = keys)
-      const uint64_t dqk = desc_k_base(sQ), dok = desc_k_base(sdO);
+    constexpr uint32_t idesc_l = umma_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_g = umma_idesc_bf16(128, DH, 0, 1);   // dQ = dS K : A from TMEM, B MN-major (K = keys)
+    const uint64_t dqk = desc_k_base(sQ), dok = desc_k_base(sdO);
+    uint32_t la = 0, gb = 0;
+    int itm = 0;
+    for (int w = (int)blockIdx.x; w < n_items; w += G, ++itm) {
+      const int n_it = n_blk - w / n_bh;
       auto issue_l = [&](int j) {  // S = Q K_j^T, dP = dO V_j^T
-        mbar_wait(a_full + 8 * (j % NA), (uint32_t)(j / NA) & 1u);
-        mbar_wait(b_full + 8 * (j % NB), (uint32_t)(j / NB) & 1u);
+        const uint32_t sa = la % NA, sb = la % NB;
+        mbar_wait(a_full + 8 * sa, (la / NA) & 1u);
+        mbar_wait(b_full + 8 * sb, (la / NB) & 1u);
         tc_fence_after();
-        const uint64_t k = desc_k_base(sKr + (j % NA) * C::TILE), v = desc_k_base(sVr + (j % NB) * C::TILE);
+        const uint64_t k = desc_k_base(sKr + sa * C::TILE), v = desc_k_base(sVr + sb * C::TILE);
         if (elect_one_sync()) {
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk)
@@ -822,27 +912,31 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
           for (int kk = 0; kk < DH / 16; ++kk)
             umma_bf16_ss(tdPb, dok + kstep_k(kk), v + kstep_k(kk), idesc_l, kk > 0 ? 1u : 0u);
           umma_commit(sd_ready);
-          umma_commit(b_empty + 8 * (j % NB));  // V_j is free as soon as dP has consumed it
+          umma_commit(b_empty + 8 * sb);  // V_j is free as soon as dP has consumed it
+          if (j == n_it - 1) umma_commit(x_empty);   // the item's last logits pair: Q | dO may be replaced
         }
         __syncwarp();
+        ++la;
       };
-      mbar_wait(x_full, 0);
+      mbar_wait(x_full, (uint32_t)itm & 1u);
       issue_l(0);
-      for (int j = 0; j < n_it; ++j) {
+      for (int j = 0; j < n_it; ++j, ++gb) {
         if (j + 1 < n_it) {  // the groups hold block j in registers: the next logits run under their arithmetic
-          mbar_wait(sd_loaded, (uint32_t)j & 1u);
+          mbar_wait(sd_loaded, gb & 1u);
           issue_l(j + 1);
         }
-        mbar_wait(ds_ready + 8 * (j & 1), (uint32_t)(j >> 1) & 1u);
+        mbar_wait(ds_ready + 8 * (gb & 1u), (gb >> 1) & 1u);
+        if (j == 0) mbar_wait(acc_free, ((uint32_t)itm & 1u) ^ 1u);   // the previous item's epilogue has read dQ
         tc_fence_after();
-        const uint64_t k = desc_mn_base(sKr + (j % NA) * C::TILE);
-        const uint32_t tdS = tdSb + 64 * (j & 1);
+        const uint32_t sa = gb % NA;
+        const uint64_t k = desc_mn_base(sKr + sa * C::TILE);
+        const uint32_t tdS = tdSb + 64 * (gb & 1u);
         if (elect_one_sync()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
             umma_bf16_ts(tmem, tdS + kk * 8, k + kstep_mn(kk), idesc_g, (j > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(a_empty + 8 * (j % NA));  // K_j is free
-          umma_commit(ds_free + 8 * (j & 1));
+          umma_commit(a_empty + 8 * sa);  // K_j is free
+          umma_commit(ds_free + 8 * (gb & 1u));
           if (j == n_it - 1) umma_commit(acc_done);
         }
         __syncwarp();
@@ -852,60 +946,68 @@ attn_bwd_dq_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_co
     // ------------------------------------------------------------------------------------------- gradient warpgroups
     const int g = warp >> 2;            // key columns [CG g, CG g + CG) of every block
     const int row = tid & 127;          // query row = TMEM lane
-    const int qi = r0 + row;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const uint32_t tS = tSb + CG * g + lane_off, tdP = tdPb + CG * g + lane_off;
     const float c1 = scale * LOG2E_F;
-    float lse2 = INFINITY, dl = 0.f;    // out-of-range query row: p = 0
-    if (qi < S) {
-      lse2 = lse[bh * S + qi] * LOG2E_F;
-      dl = delta[bh * S + qi];
-    }
-    for (int j = 0; j < n_it; ++j) {
-      mbar_wait(sd_ready, (uint32_t)j & 1u);
-      tc_fence_after();
-      uint32_t rs[CG], rd[CG];
-#pragma unroll
-      for (int c = 0; c < CG / 32; ++c) {
-        tmem_ld_x32(tS + c * 32, rs + c * 32);
-        tmem_ld_x32(tdP + c * 32, rd + c * 32);
+    uint32_t gb = 0;
+    int itm = 0;
+    for (int w = (int)blockIdx.x; w < n_items; w += G, ++itm) {
+      const int ib = n_blk - 1 - w / n_bh, n_it = ib + 1;
+      const int h = (w % n_bh) % H, b = (w % n_bh) / H;
+      const long long bh = w % n_bh;
+      const int qi = ib * 128 + row;
+      float lse2 = INFINITY, dl = 0.f;    // out-of-range query row: p = 0
+      if (qi < S) {
+        lse2 = lse[bh * S + qi] * LOG2E_F;
+        dl = delta[bh * S + qi];
       }
-      tmem_ld_wait();
-      warp_arrive(sd_loaded, lane);      // S / dP may be overwritten by the next block's logits
-      const int lim = (j == ib) ? row - CG * g : CG;  // columns c > lim are keys after this query (diagonal block)
-      if (j >= 2) {                      // the dQ product of block j-2 has consumed this dS slot
-        mbar_wait(ds_free + 8 * (j & 1), (uint32_t)((j - 2) >> 1) & 1u);
+      for (int j = 0; j < n_it; ++j, ++gb) {
+        mbar_wait(sd_ready, gb & 1u);
         tc_fence_after();
-      }
-      const uint32_t tdS = tdSb + 64 * (j & 1) + (CG / 2) * g + lane_off;
+        uint32_t rs[CG], rd[CG];
 #pragma unroll
-      for (int c = 0; c < CG / 32; ++c) {
-        uint32_t dk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const int cc = c * 32 + i;
-          float p0 = ex2f(fmaf(__uint_as_float(rs[cc]), c1, -lse2)), p1 = ex2f(fmaf(__uint_as_float(rs[cc + 1]), c1, -lse2));
-          if (cc > lim) p0 = 0.f;
-          if (cc + 1 > lim) p1 = 0.f;
-          dk[i >> 1] = pack_bf16x2((p0 * scale) * (__uint_as_float(rd[cc]) - dl),
-                                   (p1 * scale) * (__uint_as_float(rd[cc + 1]) - dl));
+        for (int c = 0; c < CG / 32; ++c) {
+          tmem_ld_x32(tS + c * 32, rs + c * 32);
+          tmem_ld_x32(tdP + c * 32, rd + c * 32);
         }
-        tmem_st_x16(tdS + c * 16, dk);
+        tmem_ld_wait();
+        warp_arrive(sd_loaded, lane);      // S / dP may be overwritten by the next block's logits
+        const int lim = (j == ib) ? row - CG * g : CG;  // columns c > lim are keys after this query (diagonal block)
+        if (gb >= 2) {                     // the dQ product of block gb-2 has consumed this dS slot
+          mbar_wait(ds_free + 8 * (gb & 1u), ((gb - 2) >> 1) & 1u);
+          tc_fence_after();
+        }
+        const uint32_t tdS = tdSb + 64 * (gb & 1u) + (CG / 2) * g + lane_off;
+#pragma unroll
+        for (int c = 0; c < CG / 32; ++c) {
+          uint32_t dk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int cc = c * 32 + i;
+            float p0 = ex2f(fmaf(__uint_as_float(rs[cc]), c1, -lse2)), p1 = ex2f(fmaf(__uint_as_float(rs[cc + 1]), c1, -lse2));
+            if (cc > lim) p0 = 0.f;
+            if (cc + 1 > lim) p1 = 0.f;
+            dk[i >> 1] = pack_bf16x2((p0 * scale) * (__uint_as_float(rd[cc]) - dl),
+                                     (p1 * scale) * (__uint_as_float(rd[cc + 1]) - dl));
+          }
+          tmem_st_x16(tdS + c * 16, dk);
+        }
+        tmem_st_wait();
+        warp_arrive(ds_ready + 8 * (gb & 1u), lane);
       }
-      tmem_st_wait();
-      warp_arrive(ds_ready + 8 * (j & 1), lane);
-    }
-    // ---- epilogue: each group writes its share of the dQ columns
-    mbar_wait(acc_done, 0);
-    tc_fence_after();
-    constexpr int EG = DH / NG, W = EG >= 32 ? 32 : 16;
-    bf16* dst = dqkv + ((((long long)b * S + qi) * 3 + 0) * H + h) * DH + g * EG;
+      // ---- epilogue: each group writes its share of the dQ columns
+      mbar_wait(acc_done, (uint32_t)itm & 1u);
+      tc_fence_after();
+      constexpr int EG = DH / NG, W = EG >= 32 ? 32 : 16;
+      bf16* dst = dqkv + ((((long long)b * S + qi) * 3 + 0) * H + h) * DH + g * EG;
 #pragma unroll 1
-    for (int c = 0; c < EG / W; ++c) {
-      uint32_t r[W];
-      tmem_ld_n<W>(tmem + lane_off + g * EG + c * W, r);
-      tmem_ld_wait();
-      if (qi < S) store_cols_bf16<W>(dst + c * W, r, 1.f);
+      for (int c = 0; c < EG / W; ++c) {
+        uint32_t r[W];
+        tmem_ld_n<W>(tmem + lane_off + g * EG + c * W, r);
+        tmem_ld_wait();
+        if (qi < S) store_cols_bf16<W>(dst + c * W, r, 1.f);
+      }
+      warp_arrive(acc_free, lane);   // dQ may be overwritten by the next item
     }
   }
   tc_fence_before();
@@ -938,6 +1040,13 @@ static int attn_ng() {
   return ng;
 }
 
+// DB200_ATTN_PERSIST (development A/B switch, read once): bit 0 = forward, bit 1 = backward run as persistent kernels
+// (one CTA per SM walking the work items, default 3); 0 = one CTA per work item
+static int attn_persist_bits() {
+  static const int v = [] { const char* e = getenv("DB200_ATTN_PERSIST"); return e ? atoi(e) : 3; }();
+  return v;
+}
+
 // DB200_ATTN_DEEP (development A/B switch, read once): forward with the deeper K / V rings (two math warpgroups)
 static int attn_deep() {
   static const int v = [] { const char* e = getenv("DB200_ATTN_DEEP"); return (e && atoi(e) != 0) ? 1 : 0; }();
@@ -954,9 +1063,12 @@ static int fwd_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, floa
   static const cudaError_t attr = cudaFuncSetAttribute(attn_fwd_ws_kernel<DH, NG, DEEP>,
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   DB200_CUDA(attr);
-  dim3 grid(((S + 127) / 128) * H * B);
+  const int n_items = ((S + 127) / 128) * H * B;
+  // persistent: one CTA per SM walks the items in order of decreasing work (DB200_ATTN_PERSIST=0, development A/B
+  // switch: one CTA per item as before)
+  dim3 grid((attn_persist_bits() & 1) && n_items > sm_count() ? sm_count() : n_items);
   static const int xflags = [] { const char* e = getenv("DB200_ATTN_EXP"); return e ? atoi(e) : 0; }();  // DEV builds only
-  attn_fwd_ws_kernel<DH, NG, DEEP><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, scale, xflags);
+  attn_fwd_ws_kernel<DH, NG, DEEP><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, n_items, scale, xflags);
   return check_launch("attn_fwd_ws_kernel");
 }
 
@@ -988,11 +1100,14 @@ static int bwd_ws_launch_t(cudaStream_t stream, const void* qkv, const void* dou
                                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
   DB200_CUDA(a0);
   DB200_CUDA(a1);
-  dim3 grid(((S + 127) / 128) * H * B);
-  attn_bwd_dkdv_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tq, to, lse, delta, (bf16*)dqkv, S, H, scale);
+  const int n_items = ((S + 127) / 128) * H * B;
+  dim3 grid((attn_persist_bits() & 2) && n_items > sm_count() ? sm_count() : n_items);
+  attn_bwd_dkdv_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tq, to, lse, delta, (bf16*)dqkv, S, H, n_items,
+                                                                         scale);
   rc = check_launch("attn_bwd_dkdv_ws_kernel");
   if (rc != DB200_OK) return rc;
-  attn_bwd_dq_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tq, to, lse, delta, (bf16*)dqkv, S, H, scale);
+  attn_bwd_dq_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tq, to, lse, delta, (bf16*)dqkv, S, H, n_items,
+                                                                       scale);
   return check_launch("attn_bwd_dq_ws_kernel");
 }
 

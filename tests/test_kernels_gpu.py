@@ -300,7 +300,10 @@ def _ref_attn(qkv, scale):
                                                 (1, 333, 2, 128, 0.0884, 1.0), (1, 1, 1, 64, 1.0, 1.0),
                                                 (2, 1280, 4, 128, 1.0, 0.25), (1, 640, 2, 128, 1.0, 1.2),
                                                 (1, 520, 3, 64, 1.0, 1.5), (1, 129, 1, 128, 1.0, 0.5),
-                                                (2, 1280, 3, 64, 0.125, 1.0)])
+                                                (2, 1280, 3, 64, 0.125, 1.0),
+                                                # more work items than SMs: several items per persistent CTA
+                                                (8, 1280, 5, 128, 1.0, 0.25), (6, 1280, 8, 64, 0.125, 1.0),
+                                                (5, 640, 8, 128, 1.0, 1.2)])
 def test_causal_attention_fwd_bwd(ops, B, S, H, dh, scale, mag):
     g = torch.Generator().manual_seed(S + dh)
     qkv = bf(torch.randn(B, S, 3, H, dh, generator=g) * mag)

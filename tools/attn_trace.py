@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("DB200_LIB", os.path.join(ROOT, "dalle_mtf_b200", "libdalle_b200_dev.so"))
 from dalle_mtf_b200 import lib as L, ops  # noqa: E402
 
-EV, STRIDE, SLOTS = 160, 37, 40
+EV, STRIDE, SLOTS = 320, 37, 40
 ROLES = ["tma", "mma", "math0", "mathN"]
 
 
@@ -45,7 +45,7 @@ def dump(buf, title, want_cta):
         n_blocks = max(e[3] for e in evs if e[2] == 1)
         print(f"-- CTA {cta} on SM {sm}: {n_blocks} blocks, {dur} cycles from first to last event "
               f"({dur / max(n_blocks, 1):.0f} per block)")
-        if cta in want_cta:
+        if cta in want_cta or slot < 2:
             for c, role, typ, j in evs:
                 print(f"   {c - t0:8d}  {ROLES[role]:6s} type={typ:2d} j={j}")
     return per_sm
