@@ -17,15 +17,17 @@
 
 namespace db200 {
 
-// Five 32 KiB pipeline stages + TWO 4 KiB epilogue staging buffers per epilogue warp: the second buffer lets the
-// residual / ReLU-mask operand of the next 32 x 64 block arrive by cp.async while the current block is processed.
-// (DB200_G2_OLD, development builds only: the previous 6-stage / single-buffer / synchronous-fetch configuration.)
-#ifdef DB200_G2_OLD
-constexpr int G2_STAGES = 6;
-constexpr int G2_STG_BUFS = 1;
-#else
+// Six 32 KiB pipeline stages + one 4 KiB epilogue staging buffer per epilogue warp.
+// -DDB200_G2_PF (A/B builds only): five stages + TWO staging buffers, the residual / ReLU-mask operand of the next
+// 32 x 64 block arriving by cp.async while the current block is processed.  Measured in-step on B200: the epilogues with
+// such an operand gain 7-8 % (0.248 vs 0.270 ms, 0.708 vs 0.761 ms per step), every other GEMM loses 1-5 % to the
+// shallower pipeline — a wash on the step (17.49 vs 17.47 ms), so the deeper pipeline stays the default.
+#ifdef DB200_G2_PF
 constexpr int G2_STAGES = 5;
 constexpr int G2_STG_BUFS = 2;
+#else
+constexpr int G2_STAGES = 6;
+constexpr int G2_STG_BUFS = 1;
 #endif
 constexpr bool G2_PF = G2_STG_BUFS == 2;
 constexpr uint32_t G2_A_BYTES = 128 * 64 * 2;  // this CTA's 128 rows of A

@@ -38,10 +38,10 @@ for (B, S, H, dh) in ((32, 1280, 4, 128), (16, 1280, 16, 64)):
         print(f"  dh={dh}: bwd {ms*1e3:7.1f} us  {2.5*4.0*S*S*dh*B*H/2/ms/1e9:7.1f} TFLOP/s (incl. delta pre-pass)", flush=True)
 ''' % ROOT
 
-for ng, deep, persist in (("4", "0", "3"), ("4", "0", "0"), ("2", "0", "3"), ("2", "1", "3")):
+for ng, persist in (("2", "3"), ("2", "0"), ("4", "3")):
     for exp in ("0", "2"):
         env = dict(os.environ, DB200_LIB=os.path.join(ROOT, "dalle_mtf_b200", "libdalle_b200_dev.so"),
-                   DB200_ATTN_NG=ng, DB200_ATTN_DEEP=deep, DB200_ATTN_EXP=exp, DB200_ATTN_PERSIST=persist)
-        print(f"NG={ng} DEEP={deep} PERSIST={persist} EXP={exp}", flush=True)
+                   DB200_ATTN_NG=ng, DB200_ATTN_EXP=exp, DB200_ATTN_PERSIST=persist)
+        print(f"NG={ng} PERSIST={persist} EXP={exp}", flush=True)
         r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=300)
         print(r.stdout + r.stderr[-600:], flush=True)
