@@ -7,7 +7,9 @@
 // threads read the fp32 pixels / weights from global memory (coalesced, zero-filled outside the image), split them in
 // registers and store the three bf16 tiles straight into the 128-byte-swizzled shared-memory layout the UMMA
 // descriptors expect; there is no bf16 copy of anything in HBM and no TMA (the producer is the math threads).
-// Two stages: the loads of chunk c+1 are in flight while the MMAs of chunk c run.
+// Three smem stages and two register sets: the global loads of chunks c+1 and c+2 are in flight while chunk c is split
+// and stored and the MMAs of chunk c-1 run (with one chunk of look-ahead every chunk paid a full L2 round trip:
+// 1.7 us per chunk in the launch list of the first version).
 //
 //   gather-GEMM (forward, conv-transpose forward, both dgrads; the ConvGemmParams of conv.cu):
 //       D[128 pixels][64 channels] += A[128 pixels][64 k] * B[64 k][64 channels]      per (tap, 64-channel k chunk)
@@ -26,7 +28,8 @@ namespace {
 constexpr uint32_t FT_A_PART = 128 * 128;   // [128 rows][64 bf16] or 2 slabs of [64 rows][64 bf16]
 constexpr uint32_t FT_B_PART = 64 * 128;    // [64 rows][64 bf16]
 constexpr uint32_t FT_STAGE = 3 * FT_A_PART + 3 * FT_B_PART;   // 72 KiB
-constexpr size_t FT_SMEM = 1024 + 2 * FT_STAGE + 64;
+constexpr int FT_NSTAGE = 3;
+constexpr size_t FT_SMEM = 1024 + FT_NSTAGE * FT_STAGE + 64;
 
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -75,20 +78,20 @@ __device__ __forceinline__ void mma6(uint32_t tmem, const uint64_t (&ad)[3], con
 }
 
 struct FtSmem {
-  uint32_t stage[2];   // A parts at stage, B parts at stage + 3 * FT_A_PART
-  uint32_t bar[2];     // "MMAs that read this stage have retired"
+  uint32_t stage0;     // stage s at stage0 + s * FT_STAGE: A parts first, B parts at + 3 * FT_A_PART
+  uint32_t bar0;       // bar0 + 8 s: "the MMAs that read stage s have retired"
   uint32_t tmem_slot;
+  __device__ __forceinline__ uint32_t stage(int s) const { return stage0 + s * FT_STAGE; }
+  __device__ __forceinline__ uint32_t bar(int s) const { return bar0 + 8 * s; }
 };
 
 __device__ __forceinline__ FtSmem ft_carve(uint8_t* raw_ptr) {
   const uint32_t raw = smem_u32(raw_ptr);
   const uint32_t base = (raw + 1023u) & ~1023u;
   FtSmem s;
-  s.stage[0] = base;
-  s.stage[1] = base + FT_STAGE;
-  s.bar[0] = base + 2 * FT_STAGE;
-  s.bar[1] = s.bar[0] + 8;
-  s.tmem_slot = s.bar[0] + 16;
+  s.stage0 = base;
+  s.bar0 = base + FT_NSTAGE * FT_STAGE;
+  s.tmem_slot = s.bar0 + 8 * FT_NSTAGE;
   return s;
 }
 
@@ -110,8 +113,7 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
   const float* x = reinterpret_cast<const float*>(p.x);
 
   if (tid == 0) {
-    mbar_init(sm.bar[0], 1);
-    mbar_init(sm.bar[1], 1);
+    for (int i = 0; i < FT_NSTAGE; ++i) mbar_init(sm.bar(i), 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(sm.tmem_slot, 64);
@@ -137,8 +139,7 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
   const int kch = p.K >> 6;
   const int nchunk = p.ntaps * kch;
 
-  float4 ra[8], rb[4];
-  auto load_chunk = [&](int c) {
+  auto load_chunk = [&](int c, float4 (&ra)[8], float4 (&rb)[4]) {
     const int t = c / kch, k0 = (c - t * kch) << 6;
     const int iy = a_oy * p.in_stride + p.taps[t].dy, ix = a_ox * p.in_stride + p.taps[t].dx;
     const bool ok = a_ok && iy >= 0 && iy < p.in_H && ix >= 0 && ix < p.in_W;
@@ -158,8 +159,8 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) rb[j] = __ldg(wsrc + j);
   };
-  auto store_chunk = [&](int s) {
-    const uint32_t sA = sm.stage[s], sB = sm.stage[s] + 3 * FT_A_PART;
+  auto store_chunk = [&](int s, const float4 (&ra)[8], const float4 (&rb)[4]) {
+    const uint32_t sA = sm.stage(s), sB = sm.stage(s) + 3 * FT_A_PART;
 #pragma unroll
     for (int j = 0; j < 4; ++j) stage8(sA, FT_A_PART, a_row, a_seg0 + j, ra[2 * j], ra[2 * j + 1]);
 #pragma unroll
@@ -167,18 +168,19 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
   };
 
   const uint32_t idesc = umma_idesc_bf16(128, 64, 0, b_mn ? 1 : 0);
-  load_chunk(0);
-  for (int c = 0; c < nchunk; ++c) {
-    const int s = c & 1;
-    if (c >= 2) mbar_wait(sm.bar[s], (uint32_t)(((c >> 1) - 1) & 1));   // the MMAs of chunk c-2 have read this stage
-    store_chunk(s);
-    if (c + 1 < nchunk) load_chunk(c + 1);
+  // chunk c: registers -> stage c % 3 (once the MMAs of chunk c-3 have read it), refill the register set with chunk
+  // c+2, publish, issue the six-product MMA group
+  auto do_chunk = [&](int c, float4 (&ra)[8], float4 (&rb)[4]) {
+    const int s = c % FT_NSTAGE;
+    if (c >= FT_NSTAGE) mbar_wait(sm.bar(s), (uint32_t)((c / FT_NSTAGE - 1) & 1));
+    store_chunk(s, ra, rb);
+    if (c + 2 < nchunk) load_chunk(c + 2, ra, rb);
     fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma (async proxy)
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
-      const uint32_t sA = sm.stage[s], sB = sm.stage[s] + 3 * FT_A_PART;
+      const uint32_t sA = sm.stage(s), sB = sm.stage(s) + 3 * FT_A_PART;
       uint64_t ad[3], bd[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -188,12 +190,19 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
       }
       if (elect_one_sync()) {
         mma6(tmem, ad, bd, 2u, b_mn ? 128u : 2u, idesc, c == 0);
-        umma_commit(sm.bar[s]);
+        umma_commit(sm.bar(s));
       }
       __syncwarp();
     }
+  };
+  float4 ra0[8], rb0[4], ra1[8], rb1[4];
+  load_chunk(0, ra0, rb0);
+  if (nchunk > 1) load_chunk(1, ra1, rb1);
+  for (int c = 0; c < nchunk; c += 2) {
+    do_chunk(c, ra0, rb0);
+    if (c + 1 < nchunk) do_chunk(c + 1, ra1, rb1);
   }
-  mbar_wait(sm.bar[(nchunk - 1) & 1], (uint32_t)(((nchunk - 1) >> 1) & 1));   // in-order completion: everything retired
+  mbar_wait(sm.bar((nchunk - 1) % FT_NSTAGE), (uint32_t)(((nchunk - 1) / FT_NSTAGE) & 1));   // in-order: all retired
   tc_fence_after();
 
   // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .., columns 32 (w >> 2) ..; one pixel x 32 channels per thread
@@ -268,8 +277,7 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
   const WgradTap tap = p.taps[t];
 
   if (tid == 0) {
-    mbar_init(sm.bar[0], 1);
-    mbar_init(sm.bar[1], 1);
+    for (int i = 0; i < FT_NSTAGE; ++i) mbar_init(sm.bar(i), 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(sm.tmem_slot, 64);
@@ -285,8 +293,7 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
   const uint32_t p_slab = pq >> 1, p_seg0 = (pq & 1) * 4, q_seg0 = pq * 2;
   const bool pa_ok = a0 + (int)pq * 32 < p.pC;   // pC is a multiple of 64: a whole 32-channel run is in or out
 
-  float4 rp[8], rq[4];
-  auto load_chunk = [&](int c) {
+  auto load_chunk = [&](int c, float4 (&rp)[8], float4 (&rq)[4]) {
     const long long m = mbeg + (long long)c * 64 + row;
     bool pok = false, qok = false;
     const float *psrc = P, *qsrc = Q;
@@ -306,8 +313,8 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) rq[j] = qok ? __ldg(reinterpret_cast<const float4*>(qsrc) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  auto store_chunk = [&](int s) {
-    const uint32_t sA = sm.stage[s] + p_slab * FT_B_PART, sB = sm.stage[s] + 3 * FT_A_PART;
+  auto store_chunk = [&](int s, const float4 (&rp)[8], const float4 (&rq)[4]) {
+    const uint32_t sA = sm.stage(s) + p_slab * FT_B_PART, sB = sm.stage(s) + 3 * FT_A_PART;
 #pragma unroll
     for (int j = 0; j < 4; ++j) stage8(sA, FT_A_PART, row, p_seg0 + j, rp[2 * j], rp[2 * j + 1]);
 #pragma unroll
@@ -315,18 +322,17 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
   };
 
   constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);   // both operands MN-major (K = pixels)
-  if (nchunk > 0) load_chunk(0);
-  for (int c = 0; c < nchunk; ++c) {
-    const int s = c & 1;
-    if (c >= 2) mbar_wait(sm.bar[s], (uint32_t)(((c >> 1) - 1) & 1));
-    store_chunk(s);
-    if (c + 1 < nchunk) load_chunk(c + 1);
+  auto do_chunk = [&](int c, float4 (&rp)[8], float4 (&rq)[4]) {
+    const int s = c % FT_NSTAGE;
+    if (c >= FT_NSTAGE) mbar_wait(sm.bar(s), (uint32_t)((c / FT_NSTAGE - 1) & 1));
+    store_chunk(s, rp, rq);
+    if (c + 2 < nchunk) load_chunk(c + 2, rp, rq);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
-      const uint32_t sA = sm.stage[s], sB = sm.stage[s] + 3 * FT_A_PART;
+      const uint32_t sA = sm.stage(s), sB = sm.stage(s) + 3 * FT_A_PART;
       uint64_t ad[3], bd[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -335,13 +341,20 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
       }
       if (elect_one_sync()) {
         mma6(tmem, ad, bd, 128u, 128u, idesc, c == 0);    // 16 pixels = 16 rows x 128 B = 2 KiB per K-step
-        umma_commit(sm.bar[s]);
+        umma_commit(sm.bar(s));
       }
       __syncwarp();
     }
+  };
+  float4 rp0[8], rq0[4], rp1[8], rq1[4];
+  if (nchunk > 0) load_chunk(0, rp0, rq0);
+  if (nchunk > 1) load_chunk(1, rp1, rq1);
+  for (int c = 0; c < nchunk; c += 2) {
+    do_chunk(c, rp0, rq0);
+    if (c + 1 < nchunk) do_chunk(c + 1, rp1, rq1);
   }
   if (nchunk > 0) {
-    mbar_wait(sm.bar[(nchunk - 1) & 1], (uint32_t)(((nchunk - 1) >> 1) & 1));
+    mbar_wait(sm.bar((nchunk - 1) % FT_NSTAGE), (uint32_t)(((nchunk - 1) / FT_NSTAGE) & 1));
     tc_fence_after();
     const int q = warp & 3, half = warp >> 2;
     const int a = a0 + q * 32 + lane;
