@@ -38,6 +38,10 @@ class DataParallel:
 
     # CTAs NCCL may occupy while the persistent 148-CTA tcgen05 grids of backward are running (0 = NCCL's default).
     MAX_CTAS = int(os.environ.get("DB200_NCCL_MAX_CTAS", "8"))
+    # A second communicator without that cap carries the collectives that run when no compute is left to overlap with:
+    # the last gradient bucket ([wte | wpe], finished by the final kernel of backward), the ZeRO-1 parameter
+    # all-gather and the eval-loss reduction.  -1 disables it (everything on the capped communicator).
+    TAIL_CTAS = int(os.environ.get("DB200_NCCL_TAIL_CTAS", "0"))
 
     def __init__(self):
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -46,6 +50,7 @@ class DataParallel:
         self.handles = []
         self.enabled = self.world > 1
         self.comm = None          # db200_comm* (ctypes void pointer) when the C-ABI communicator is in use
+        self.comm_tail = None     # uncapped communicator for the exposed collectives (None: use self.comm)
         self.registered = False
 
     def init(self, backend=None):
@@ -68,16 +73,22 @@ class DataParallel:
         lib = L.load()
         path = _libnccl_path()
         L.check(lib.db200_comm_load_nccl(path.encode() if path else None), "comm_load_nccl")
-        uid = ctypes.create_string_buffer(128)
-        if self.rank == 0:
-            L.check(lib.db200_comm_unique_id(uid, 128), "comm_unique_id")
-        box = [uid.raw]
-        dist.broadcast_object_list(box, src=0)            # side channel (gloo): 128 bytes
-        uid = ctypes.create_string_buffer(box[0], 128)
-        comm = ctypes.c_void_p()
-        L.check(lib.db200_comm_create(torch.cuda.current_device(), self.rank, self.world, uid, self.MAX_CTAS,
-                                      ctypes.byref(comm)), "comm_create")
-        self.comm = comm
+
+        def create(max_ctas):
+            uid = ctypes.create_string_buffer(128)
+            if self.rank == 0:
+                L.check(lib.db200_comm_unique_id(uid, 128), "comm_unique_id")
+            box = [uid.raw]
+            dist.broadcast_object_list(box, src=0)            # side channel (gloo): 128 bytes
+            uid = ctypes.create_string_buffer(box[0], 128)
+            comm = ctypes.c_void_p()
+            L.check(lib.db200_comm_create(torch.cuda.current_device(), self.rank, self.world, uid, max_ctas,
+                                          ctypes.byref(comm)), "comm_create")
+            return comm
+
+        self.comm = create(self.MAX_CTAS)
+        if self.TAIL_CTAS >= 0 and self.TAIL_CTAS != self.MAX_CTAS:
+            self.comm_tail = create(self.TAIL_CTAS)
 
     def shard(self, global_batch):
         """Rows [rank*B/N, (rank+1)*B/N) of the global batch."""
@@ -87,12 +98,17 @@ class DataParallel:
         return self.rank * per, per
 
     # --- gradient buckets ------------------------------------------------------------------------------
-    def _launch(self, t):
-        """Asynchronous in-place SUM all-reduce of a contiguous fp32 / bf16 tensor (a slice of a flat buffer)."""
+    def _exposed_comm(self):
+        return self.comm_tail if self.comm_tail is not None else self.comm
+
+    def _launch(self, t, exposed=False):
+        """Asynchronous in-place SUM all-reduce of a contiguous fp32 / bf16 tensor (a slice of a flat buffer).
+        exposed: nothing is left to overlap with — use the communicator without the CTA cap."""
         if self.comm is not None:
             from . import lib as L
             dt = {torch.float32: 0, torch.bfloat16: 1}[t.dtype]
-            L.check(L.load().db200_bucket_allreduce_launch(self.comm, L.stream_ptr(), t.data_ptr(), t.numel(), dt),
+            comm = self._exposed_comm() if exposed else self.comm
+            L.check(L.load().db200_bucket_allreduce_launch(comm, L.stream_ptr(), t.data_ptr(), t.numel(), dt),
                     "bucket_allreduce_launch")
         else:
             self.handles.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
@@ -115,13 +131,15 @@ class DataParallel:
 
         def hook(start, end):
             end = min(end, flat.numel())
-            self._launch(flat[start:end])
+            # the flat buffers are laid out in forward order and backward finalises them from the tail: the range that
+            # starts at offset 0 is the last one, launched after the final kernel of backward
+            self._launch(flat[start:end], exposed=(start == 0))
 
         return hook
 
     def all_reduce_now(self, t):
         if self.enabled:
-            self._launch(t)
+            self._launch(t, exposed=True)
             self.wait()
         return t
 
@@ -134,8 +152,8 @@ class DataParallel:
         if self.comm is not None:
             from . import lib as L
             dt = {torch.float32: 0, torch.bfloat16: 1}[buf.dtype]
-            L.check(L.load().db200_bucket_all_gather_launch(self.comm, L.stream_ptr(), mine.data_ptr(), buf.data_ptr(),
-                                                            count_per_rank, dt), "bucket_all_gather_launch")
+            L.check(L.load().db200_bucket_all_gather_launch(self._exposed_comm(), L.stream_ptr(), mine.data_ptr(),
+                                                            buf.data_ptr(), count_per_rank, dt), "bucket_all_gather_launch")
             self.wait()
         else:
             dist.all_gather_into_tensor(buf[:self.world * count_per_rank], mine.clone())
@@ -146,6 +164,8 @@ class DataParallel:
         if self.comm is not None:
             from . import lib as L
             L.check(L.load().db200_bucket_allreduce_wait(self.comm, L.stream_ptr()), "bucket_allreduce_wait")
+            if self.comm_tail is not None:
+                L.check(L.load().db200_bucket_allreduce_wait(self.comm_tail, L.stream_ptr()), "bucket_allreduce_wait")
         for h in self.handles:
             h.wait()
         self.handles = []
@@ -167,6 +187,9 @@ class DataParallel:
         if self.comm is not None:
             from . import lib as L
             torch.cuda.synchronize()
+            if self.comm_tail is not None:
+                L.load().db200_comm_destroy(self.comm_tail)
+                self.comm_tail = None
             L.load().db200_comm_destroy(self.comm)
             self.comm = None
         if self.enabled and dist.is_initialized():
