@@ -100,19 +100,29 @@ class VaeEngine:
             self.cb_lo = torch.zeros(self.n_hid, self.K, dtype=BF16, device=dev)
         self._B = None
         self._grads_clean = False
+        self._views = {}
+        self._descs = {}
 
     # ------------------------------------------------------------------------------------------ parameters
+    def _view(self, buf, name):
+        # the per-name views are requested ~300 times per step (host time, not device time, bounds vae_example)
+        key = (buf.data_ptr(), name)
+        v = self._views.get(key)
+        if v is None:
+            v = self._views[key] = self.layout.view(buf, name)
+        return v
+
     def P(self, name):
-        return self.layout.view(self.master, name)
+        return self._view(self.master, name)
 
     def G(self, name):
-        return self.layout.view(self.grads, name)
+        return self._view(self.grads, name)
 
     def n_params(self):
         return sum(math.prod(shape) for _, shape in self.layout.entries.values())
 
     def W16(self, name):
-        return self.layout.view(self.shadow, name)
+        return self._view(self.shadow, name)
 
     def refresh_shadow(self):
         if self.shadow is not None:
@@ -231,8 +241,12 @@ class VaeEngine:
         self._b = b
 
     def _desc(self, B, res, cin, cout, k, stride, transposed=False, relu=False):
-        return ops.conv_desc(B, res, res, cin, cout, k, k, stride, transposed=transposed, act_f32=not self.use_bf16,
-                             relu=relu)
+        key = (B, res, cin, cout, k, stride, transposed, relu)
+        d = self._descs.get(key)
+        if d is None:
+            d = self._descs[key] = ops.conv_desc(B, res, res, cin, cout, k, k, stride, transposed=transposed,
+                                                 act_f32=not self.use_bf16, relu=relu)
+        return d
 
     def _to_act(self, src_f32, dst_act):
         if self.use_bf16:
