@@ -139,7 +139,7 @@ __device__ __forceinline__ void warp_arrive(uint32_t bar, int lane) {
 // ------------------------------------------------------------------------------------------------------------------
 template <int DH, int NG>
 struct FwdWs {
-  static constexpr int NK = (DH == 128) ? 3 : 4;   // K ring depth (128-key blocks): logits run three blocks ahead
+  static constexpr int NK = (DH == 128) ? 3 : 4;   // K ring depth (128-key blocks): logits run two blocks ahead
   static constexpr int NV = (DH == 128) ? 2 : 4;   // V ring depth
   static constexpr uint32_t TILE = 128 * DH * 2;   // one [128][DH] bf16 operand tile
   static constexpr uint32_t XCH_BYTES = 2 * NG * 128 * 4;
@@ -162,12 +162,10 @@ struct FwdWs {
 // 128-query tile (1 280 tiles of 1..10 key blocks at the bench shape: the fixed cost per tile was as large as its work).
 // Every barrier therefore runs on GLOBAL use counters that continue across items:
 //   kc / vc   K / V ring uses         slot = c % N, parity (c / N) & 1
-//   bc        key blocks processed    S / P buffer bc % 3, parity (bc / 3) & 1;  o_done completes once per P.V: the
+//   bc        key blocks processed    S / P buffer bc & 1, parity (bc >> 1) & 1;  o_done completes once per P.V: the
 //                                     product of block bc has parity bc & 1
-//   it        items of this CTA       Q buffer / O accumulator hand-back (o_free) parity it & 1
-// TMEM: three logits buffers [0,128) [128,256) [256,384) + O [384, 384 + dh).  The logits run THREE blocks ahead of the
-// softmax (S0 S1 S2 | PV0 S3 | PV1 S4 ...), so S_{j+1} is complete when the math warps start block j and its TMEM read
-// can be issued first and overlap the arithmetic of block j.
+//   it        items of this CTA       Q buffer parity it & 1; O accumulator it & 1 (double-buffered: the epilogue of
+//                                     item `it` overlaps the first products of item it + 1), o_free[it & 1]
 // The TMA warp is a free-running stream of (Q, K_j, V_j) requests over all items: the loads of the next tile are in
 // flight while the current one finishes.
 template <int DH, int NG>
@@ -194,12 +192,12 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
   const uint32_t k_empty = k_full + 8 * NK;        // [NK]
   const uint32_t v_full = k_empty + 8 * NK;        // [NV]
   const uint32_t v_empty = v_full + 8 * NV;        // [NV]
-  const uint32_t s_ready = v_empty + 8 * NV;       // [3]  S buffer b holds the block with bc % 3 == b
-  const uint32_t p_ready = s_ready + 24;           // [3]
-  const uint32_t o_done = p_ready + 24;            // a P.V product has landed in O
-  const uint32_t o_free = o_done + 8;              // the epilogue has read the O accumulator (all math warps)
-  const uint32_t tmem_slot = o_free + 8;
-  static_assert(8 * (2 + 2 * NK + 2 * NV + 3 + 3 + 1 + 1) + 8 <= C::BAR_BYTES, "barrier area");
+  const uint32_t s_ready = v_empty + 8 * NV;       // [2]  S buffer b holds the block with (bc & 1) == b
+  const uint32_t p_ready = s_ready + 16;           // [2]
+  const uint32_t o_done = p_ready + 16;            // a P.V product has landed in O
+  const uint32_t o_free = o_done + 8;              // [2]  the epilogue has read O accumulator b
+  const uint32_t tmem_slot = o_free + 16;
+  static_assert(8 * (2 + 2 * NK + 2 * NV + 2 + 2 + 1 + 2) + 8 <= C::BAR_BYTES, "barrier area");
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* xch = reinterpret_cast<float*>(smem_raw + (sX - raw));
 
@@ -215,12 +213,12 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     mbar_init(q_empty, 1);
     for (int i = 0; i < NK; ++i) { mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1); }
     for (int i = 0; i < NV; ++i) { mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1); }
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(s_ready + 8 * i, 1);
       mbar_init(p_ready + 8 * i, 4 * NG);
+      mbar_init(o_free + 8 * i, 4 * NG);
     }
     mbar_init(o_done, 1);
-    mbar_init(o_free, 4 * NG);
     fence_mbar_init();
   }
   if (warp == TMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -276,20 +274,19 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
     int it = 0;
     for (int w = (int)blockIdx.x; w < n_items; w += G, ++it) {
       const int n_kv = n_qt - w / n_bh;       // key blocks 0 .. qt
-      const uint32_t tO = tmem + 384;
+      const uint32_t tO = tmem + 256 + (it & 1) * DH;
       auto issue_s = [&](int j) {
         const uint32_t sk = kc % NK;
         tr.ev(9, j);    // about to wait for K_j
         mbar_wait(k_full + 8 * sk, (kc / NK) & 1u);
         tc_fence_after();
         const uint64_t dk = desc_k_base(sK + sk * C::TILE);
-        const uint32_t sbuf = sc % 3u;
-        const uint32_t tS = tmem + sbuf * 128;
+        const uint32_t tS = tmem + (sc & 1u) * 128;
         if (elect_one_sync()) {
 #pragma unroll
           for (int kk = 0; kk < DH / 16; ++kk)
             umma_bf16_ss(tS, dq + kstep_k(kk), dk + kstep_k(kk), idesc_s, kk > 0 ? 1u : 0u);
-          umma_commit(s_ready + 8 * sbuf);
+          umma_commit(s_ready + 8 * (sc & 1u));
           umma_commit(k_empty + 8 * sk);
           if (j == n_kv - 1) umma_commit(q_empty);   // the item's last logits product: Q is free when it retires
         }
@@ -301,18 +298,16 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       tr.ev(1, n_kv);
       issue_s(0);
       if (n_kv > 1) issue_s(1);
-      if (n_kv > 2) issue_s(2);
       for (int j = 0; j < n_kv; ++j) {
         const uint32_t sv = vc % NV;
         mbar_wait(v_full + 8 * sv, (vc / NV) & 1u);
         tr.ev(11, j);   // V_j has landed
-        const uint32_t pbuf = pc % 3u;
-        mbar_wait(p_ready + 8 * pbuf, (pc / 3u) & 1u);
+        mbar_wait(p_ready + 8 * (pc & 1u), (pc >> 1) & 1u);
         tr.ev(12, j);   // P_j is in TMEM
-        if (j == 0) mbar_wait(o_free, ((uint32_t)it & 1u) ^ 1u);  // the epilogue of the previous item has read O
+        if (j == 0) mbar_wait(o_free + 8 * (it & 1), ((uint32_t)(it >> 1) & 1u) ^ 1u);  // the epilogue of item it-2 is done
         tc_fence_after();
         const uint64_t dv = desc_mn_base(sV + sv * C::TILE);
-        const uint32_t tP = tmem + pbuf * 128;
+        const uint32_t tP = tmem + (pc & 1u) * 128;
         if (elect_one_sync()) {
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)
@@ -323,7 +318,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         __syncwarp();
         ++vc; ++pc;
         tr.ev(5, j);    // P.V_j issued
-        if (j + 3 < n_kv) issue_s(j + 3);  // into the buffer whose P the product above has just been queued to consume
+        if (j + 2 < n_kv) issue_s(j + 2);  // into the buffer whose P the product above has just been queued to consume
       }
     }
   } else {
@@ -339,33 +334,25 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
       const int h = bh % H, b = bh / H;
       const int n_kv = qt + 1;
       const int qi = qt * 128 + row;
-      const uint32_t tO = tmem + 384;
+      const uint32_t tO = tmem + 256 + (it & 1) * DH;
       float m_used = -INFINITY;  // the maximum the accumulated P / O / l are scaled by (identical in all groups)
       float l_run = 0.f;         // partial row sum over this group's key columns
       tr.ev(1, n_kv);
-      // The logits of block j+1 are fetched from TMEM (tcgen05.ld, asynchronous) BEFORE the arithmetic of block j: the
-      // TMEM read port moves 64 B/cycle per SM, i.e. a 128 x 128 fp32 block takes as long as its two MMA products, and
-      // with every math warp in the same phase the exp phase used to start only after that read (event timeline:
-      // 1 750 cycles from "S complete" to "P written" per block).  Two register sets, ping-pong.
-      auto load_s = [&](uint32_t (&dst)[CG], uint32_t blk, int j) {
-        const uint32_t sb = blk % 3u;
-        mbar_wait(s_ready + 8 * sb, (blk / 3u) & 1u);
+      for (int j = 0; j < n_kv; ++j, ++bc) {
+        const uint32_t sb = bc & 1u;
+        const uint32_t tS = tmem + sb * 128 + CG * g + lane_off;
+        mbar_wait(s_ready + 8 * sb, (bc >> 1) & 1u);
         tr.ev(6, j);      // S_j complete (seen by this math warp)
         tc_fence_after();
-        const uint32_t tS = tmem + sb * 128 + CG * g + lane_off;
-#pragma unroll
-        for (int c = 0; c < CG / 32; ++c) tmem_ld_x32(tS + c * 32, dst + c * 32);
-      };
-      auto step = [&](int j, uint32_t (&sv)[CG], uint32_t (&nx)[CG]) {   // sv = S_j (loaded), nx <- S_{j+1}
-        const uint32_t sb = bc % 3u;
-        const uint32_t tS = tmem + sb * 128 + CG * g + lane_off;
         if (xflags & 2) {  // experiment: pure hand-off chain, no softmax work at all
-          mbar_wait(s_ready + 8 * sb, (bc / 3u) & 1u);
-          tc_fence_after();
           warp_arrive(p_ready + 8 * sb, lane);
-          return;
+          continue;
         }
-        if (j + 1 < n_kv) load_s(nx, bc + 1u, j + 1);   // in flight during this block's arithmetic
+        uint32_t sv[CG];
+#pragma unroll
+        for (int c = 0; c < CG / 32; ++c) tmem_ld_x32(tS + c * 32, sv + c * 32);
+        tmem_ld_wait();
+        tr.ev(20, j);     // logits in registers
         if (j == qt) {  // diagonal block: keys after the query are masked (src/dalle_mtf/models.py:221-227)
           const int lim = row - CG * g;  // columns c > lim of this slice are in the future
 #pragma unroll
@@ -389,6 +376,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
 #pragma unroll
           for (int o = 1; o < NG; ++o) mx = fmaxf(mx, xp[((g + o) % NG) * 128 + row]);  // finite: key 0 is always visible
         }
+        tr.ev(21, j);     // row maximum known (after the cross-group exchange)
         if (j == 0) {
           m_used = mx;
         } else {
@@ -432,23 +420,10 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
           tmem_st_x16(tS + c * 16, pk);
         }
         l_run += l0 + l1;
+        tr.ev(22, j);     // exponentials computed, P stores issued
         tmem_st_wait();
         warp_arrive(p_ready + 8 * sb, lane);
         tr.ev(7, j);      // this warp's share of P_j written
-        if (j + 1 < n_kv) tmem_ld_wait();   // nx holds S_{j+1}
-      };
-      uint32_t svA[CG], svB[CG];
-      if (!(xflags & 2)) {
-        load_s(svA, bc, 0);
-        tmem_ld_wait();
-      }
-      for (int j = 0; j < n_kv; j += 2) {
-        step(j, svA, svB);
-        ++bc;
-        if (j + 1 < n_kv) {
-          step(j + 1, svB, svA);
-          ++bc;
-        }
       }
       // ---- epilogue: O / l -> bf16 (this group's share of the columns), lse.  The exchange slot is the one the last
       // block did not use; the next block (of the next item) takes the other one, so every reuse of a slot is separated
@@ -474,7 +449,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
         tmem_ld_wait();
         if (qi < S) store_cols_bf16<W>(op + c * W, r, inv);
       }
-      warp_arrive(o_free, lane);   // the O accumulator may be overwritten by the next item's first P.V
+      warp_arrive(o_free + 8 * (it & 1), lane);   // this O accumulator may be overwritten (item it + 2)
       if (qi < S && g == 0) lse_out[((long long)b * H + h) * S + qi] = m_used * scale + logf(l_tot);
       tr.ev(10, 0);       // item done
     }

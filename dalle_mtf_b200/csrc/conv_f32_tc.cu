@@ -7,9 +7,11 @@
 // threads read the fp32 pixels / weights from global memory (coalesced, zero-filled outside the image), split them in
 // registers and store the three bf16 tiles straight into the 128-byte-swizzled shared-memory layout the UMMA
 // descriptors expect; there is no bf16 copy of anything in HBM and no TMA (the producer is the math threads).
-// Three smem stages and two register sets: the global loads of chunks c+1 and c+2 are in flight while chunk c is split
-// and stored and the MMAs of chunk c-1 run (with one chunk of look-ahead every chunk paid a full L2 round trip:
-// 1.7 us per chunk in the launch list of the first version).
+// Nine warps: eight producers (load -> split -> store into one of three smem stages, two chunks of look-ahead in
+// registers) and one MMA-issuer warp that waits on the stage's "full" mbarrier, issues the six-product group and commits
+// the stage's "empty" barrier.  (The issue of 24 tcgen05.mma blocks for most of their execution time — the queue is
+// shallow — so with the issuer also being a producer warp and __syncthreads per chunk, every chunk cost the SUM of the
+// split and the MMA time: 1.7 us per chunk in the launch list of the first version.)
 //
 //   gather-GEMM (forward, conv-transpose forward, both dgrads; the ConvGemmParams of conv.cu):
 //       D[128 pixels][64 channels] += A[128 pixels][64 k] * B[64 k][64 channels]      per (tap, 64-channel k chunk)
@@ -77,12 +79,14 @@ __device__ __forceinline__ void mma6(uint32_t tmem, const uint64_t (&ad)[3], con
   }
 }
 
+constexpr int FT_THREADS = 288;   // 8 producer warps + 1 MMA-issuer warp
 struct FtSmem {
   uint32_t stage0;     // stage s at stage0 + s * FT_STAGE: A parts first, B parts at + 3 * FT_A_PART
-  uint32_t bar0;       // bar0 + 8 s: "the MMAs that read stage s have retired"
+  uint32_t bar0;       // bar0 + 8 s: "the MMAs that read stage s have retired";  bar0 + 8 (3 + s): "stage s is written"
   uint32_t tmem_slot;
   __device__ __forceinline__ uint32_t stage(int s) const { return stage0 + s * FT_STAGE; }
   __device__ __forceinline__ uint32_t bar(int s) const { return bar0 + 8 * s; }
+  __device__ __forceinline__ uint32_t full(int s) const { return bar0 + 8 * (FT_NSTAGE + s); }
 };
 
 __device__ __forceinline__ FtSmem ft_carve(uint8_t* raw_ptr) {
@@ -91,7 +95,7 @@ __device__ __forceinline__ FtSmem ft_carve(uint8_t* raw_ptr) {
   FtSmem s;
   s.stage0 = base;
   s.bar0 = base + FT_NSTAGE * FT_STAGE;
-  s.tmem_slot = s.bar0 + 8 * FT_NSTAGE;
+  s.tmem_slot = s.bar0 + 16 * FT_NSTAGE;
   return s;
 }
 
@@ -100,7 +104,7 @@ __device__ __forceinline__ FtSmem ft_carve(uint8_t* raw_ptr) {
 // ---------------------------------------------------------------------------------------------------------------
 // gather-GEMM
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FT_THREADS)
 conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
   extern __shared__ uint8_t ft_smem_raw[];
   const FtSmem sm = ft_carve(ft_smem_raw);
@@ -113,10 +117,10 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
   const float* x = reinterpret_cast<const float*>(p.x);
 
   if (tid == 0) {
-    for (int i = 0; i < FT_NSTAGE; ++i) mbar_init(sm.bar(i), 1);
+    for (int i = 0; i < FT_NSTAGE; ++i) { mbar_init(sm.bar(i), 1); mbar_init(sm.full(i), 8); }
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(sm.tmem_slot, 64);
+  if (warp == 8) tmem_alloc(sm.tmem_slot, 64);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -170,15 +174,11 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
   const uint32_t idesc = umma_idesc_bf16(128, 64, 0, b_mn ? 1 : 0);
   // chunk c: registers -> stage c % 3 (once the MMAs of chunk c-3 have read it), refill the register set with chunk
   // c+2, publish, issue the six-product MMA group
-  auto do_chunk = [&](int c, float4 (&ra)[8], float4 (&rb)[4]) {
-    const int s = c % FT_NSTAGE;
-    if (c >= FT_NSTAGE) mbar_wait(sm.bar(s), (uint32_t)((c / FT_NSTAGE - 1) & 1));
-    store_chunk(s, ra, rb);
-    if (c + 2 < nchunk) load_chunk(c + 2, ra, rb);
-    fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma (async proxy)
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
+  if (warp == 8) {
+    // ---------------------------------------------------------------------------------------------- MMA issuer
+    for (int c = 0; c < nchunk; ++c) {
+      const int s = c % FT_NSTAGE;
+      mbar_wait(sm.full(s), (uint32_t)((c / FT_NSTAGE) & 1));
       tc_fence_after();
       const uint32_t sA = sm.stage(s), sB = sm.stage(s) + 3 * FT_A_PART;
       uint64_t ad[3], bd[3];
@@ -194,16 +194,27 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
       }
       __syncwarp();
     }
-  };
-  float4 ra0[8], rb0[4], ra1[8], rb1[4];
-  load_chunk(0, ra0, rb0);
-  if (nchunk > 1) load_chunk(1, ra1, rb1);
-  for (int c = 0; c < nchunk; c += 2) {
-    do_chunk(c, ra0, rb0);
-    if (c + 1 < nchunk) do_chunk(c + 1, ra1, rb1);
-  }
-  mbar_wait(sm.bar((nchunk - 1) % FT_NSTAGE), (uint32_t)(((nchunk - 1) / FT_NSTAGE) & 1));   // in-order: all retired
-  tc_fence_after();
+  } else {
+    // ---------------------------------------------------------------------------------------------- producers
+    // chunk c: registers -> stage c % 3 (once the MMAs of chunk c-3 have read it), refill the register set with chunk c+2
+    auto do_chunk = [&](int c, float4 (&ra)[8], float4 (&rb)[4]) {
+      const int s = c % FT_NSTAGE;
+      if (c >= FT_NSTAGE) mbar_wait(sm.bar(s), (uint32_t)((c / FT_NSTAGE - 1) & 1));
+      store_chunk(s, ra, rb);
+      if (c + 2 < nchunk) load_chunk(c + 2, ra, rb);
+      fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.full(s));
+    };
+    float4 ra0[8], rb0[4], ra1[8], rb1[4];
+    load_chunk(0, ra0, rb0);
+    if (nchunk > 1) load_chunk(1, ra1, rb1);
+    for (int c = 0; c < nchunk; c += 2) {
+      do_chunk(c, ra0, rb0);
+      if (c + 1 < nchunk) do_chunk(c + 1, ra1, rb1);
+    }
+    mbar_wait(sm.bar((nchunk - 1) % FT_NSTAGE), (uint32_t)(((nchunk - 1) / FT_NSTAGE) & 1));   // in-order: all retired
+    tc_fence_after();
 
   // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .., columns 32 (w >> 2) ..; one pixel x 32 channels per thread
   {
@@ -249,9 +260,10 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
       }
     }
   }
+  }  // producers
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, 64);
   }
@@ -260,7 +272,7 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
 // ---------------------------------------------------------------------------------------------------------------
 // outer product (wgrad): CTA = (128 a-channels, 64 b-channels, one tap, one pixel range); red.add into dw
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(FT_THREADS)
 conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
   extern __shared__ uint8_t ft_smem_raw[];
   const FtSmem sm = ft_carve(ft_smem_raw);
@@ -277,10 +289,10 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
   const WgradTap tap = p.taps[t];
 
   if (tid == 0) {
-    for (int i = 0; i < FT_NSTAGE; ++i) mbar_init(sm.bar(i), 1);
+    for (int i = 0; i < FT_NSTAGE; ++i) { mbar_init(sm.bar(i), 1); mbar_init(sm.full(i), 8); }
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(sm.tmem_slot, 64);
+  if (warp == 8) tmem_alloc(sm.tmem_slot, 64);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -322,15 +334,11 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
   };
 
   constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);   // both operands MN-major (K = pixels)
-  auto do_chunk = [&](int c, float4 (&rp)[8], float4 (&rq)[4]) {
-    const int s = c % FT_NSTAGE;
-    if (c >= FT_NSTAGE) mbar_wait(sm.bar(s), (uint32_t)((c / FT_NSTAGE - 1) & 1));
-    store_chunk(s, rp, rq);
-    if (c + 2 < nchunk) load_chunk(c + 2, rp, rq);
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
+  if (warp == 8) {
+    // ---------------------------------------------------------------------------------------------- MMA issuer
+    for (int c = 0; c < nchunk; ++c) {
+      const int s = c % FT_NSTAGE;
+      mbar_wait(sm.full(s), (uint32_t)((c / FT_NSTAGE) & 1));
       tc_fence_after();
       const uint32_t sA = sm.stage(s), sB = sm.stage(s) + 3 * FT_A_PART;
       uint64_t ad[3], bd[3];
@@ -345,31 +353,42 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
       }
       __syncwarp();
     }
-  };
-  float4 rp0[8], rq0[4], rp1[8], rq1[4];
-  if (nchunk > 0) load_chunk(0, rp0, rq0);
-  if (nchunk > 1) load_chunk(1, rp1, rq1);
-  for (int c = 0; c < nchunk; c += 2) {
-    do_chunk(c, rp0, rq0);
-    if (c + 1 < nchunk) do_chunk(c + 1, rp1, rq1);
-  }
-  if (nchunk > 0) {
-    mbar_wait(sm.bar((nchunk - 1) % FT_NSTAGE), (uint32_t)(((nchunk - 1) / FT_NSTAGE) & 1));
-    tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
-    const int a = a0 + q * 32 + lane;
-    uint32_t r[32];
-    tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + half * 32, r);
-    tmem_ld_wait();
-    if (a < p.pC) {
-      float* dw = p.dw + tap.w_off + (long long)a * p.a_stride + (long long)(b0 + half * 32) * p.b_stride;
+  } else {
+    // ---------------------------------------------------------------------------------------------- producers
+    auto do_chunk = [&](int c, float4 (&rp)[8], float4 (&rq)[4]) {
+      const int s = c % FT_NSTAGE;
+      if (c >= FT_NSTAGE) mbar_wait(sm.bar(s), (uint32_t)((c / FT_NSTAGE - 1) & 1));
+      store_chunk(s, rp, rq);
+      if (c + 2 < nchunk) load_chunk(c + 2, rp, rq);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sm.full(s));
+    };
+    float4 rp0[8], rq0[4], rp1[8], rq1[4];
+    if (nchunk > 0) load_chunk(0, rp0, rq0);
+    if (nchunk > 1) load_chunk(1, rp1, rq1);
+    for (int c = 0; c < nchunk; c += 2) {
+      do_chunk(c, rp0, rq0);
+      if (c + 1 < nchunk) do_chunk(c + 1, rp1, rq1);
+    }
+    if (nchunk > 0) {
+      mbar_wait(sm.bar((nchunk - 1) % FT_NSTAGE), (uint32_t)(((nchunk - 1) / FT_NSTAGE) & 1));
+      tc_fence_after();
+      const int q = warp & 3, half = warp >> 2;
+      const int a = a0 + q * 32 + lane;
+      uint32_t r[32];
+      tmem_ld_x32(tmem + ((uint32_t)(q * 32) << 16) + half * 32, r);
+      tmem_ld_wait();
+      if (a < p.pC) {
+        float* dw = p.dw + tap.w_off + (long long)a * p.a_stride + (long long)(b0 + half * 32) * p.b_stride;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) atomicAdd(dw + (long long)e * p.b_stride, __uint_as_float(r[e]));
+        for (int e = 0; e < 32; ++e) atomicAdd(dw + (long long)e * p.b_stride, __uint_as_float(r[e]));
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem, 64);
   }
@@ -395,7 +414,7 @@ int conv_gemm_f32_tc_launch(cudaStream_t stream, const ConvGemmParams& p) {
   DB200_CUDA(attr_rc);
   const long long M = (long long)p.NB * p.OH * p.OW;
   dim3 grid((unsigned)((M + 127) / 128), (unsigned)(p.Nn / 64));
-  conv_gemm_f32_tc_kernel<<<grid, 256, FT_SMEM, stream>>>(p);
+  conv_gemm_f32_tc_kernel<<<grid, FT_THREADS, FT_SMEM, stream>>>(p);
   return check_launch("conv_gemm_f32_tc_kernel");
 }
 
@@ -416,7 +435,7 @@ int conv_wgrad_f32_tc_launch(cudaStream_t stream, ConvWgradParams& p) {
   if (splits < 1) splits = 1;
   p.splits = splits;
   dim3 grid((p.pC + 127) / 128, p.qC / 64, p.ntaps * splits);
-  conv_wgrad_f32_tc_kernel<<<grid, 256, FT_SMEM, stream>>>(p);
+  conv_wgrad_f32_tc_kernel<<<grid, FT_THREADS, FT_SMEM, stream>>>(p);
   return check_launch("conv_wgrad_f32_tc_kernel");
 }
 

@@ -2,7 +2,7 @@
 Prints, for a few traced CTAs, every recorded event as (role, type, block index, cycles since the CTA's first event).
 Event types — forward: 1 roles start, 2 K_j load issued, 3 V_j load issued, 9 MMA warp starts waiting for K_j,
 4 S_j issued, 11 V_j landed, 12 P_j in TMEM, 5 P.V_j issued, 6 math warp saw S_j, 7 math warp wrote its P_j share,
-8 epilogue starts, 10 role done, 13 CTA exit.  dK/dV: 2 Q_i / 3 dO_i load issued, 4 S^T issued, 14 dP^T issued,
+8 epilogue starts, 10 role done, 13 CTA exit; math detail: 20 logits in registers, 21 row maximum known, 22 exponentials done.  dK/dV: 2 Q_i / 3 dO_i load issued, 4 S^T issued, 14 dP^T issued,
 12 P^T in TMEM, 5 dV issued, 15 dS^T in TMEM, 16 dK issued, 6/7 phase A begin/end, 17/18 phase B begin/end."""
 import ctypes
 import os
