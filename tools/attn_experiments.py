@@ -38,8 +38,8 @@ for (B, S, H, dh) in ((32, 1280, 4, 128), (16, 1280, 16, 64)):
         print(f"  dh={dh}: bwd {ms*1e3:7.1f} us  {2.5*4.0*S*S*dh*B*H/2/ms/1e9:7.1f} TFLOP/s (incl. delta pre-pass)", flush=True)
 ''' % ROOT
 
-for ng, persist in (("2", "3"), ("2", "0"), ("4", "3")):
-    for exp in ("0", "2"):
+for ng, persist in (("2", "3"), ("4", "3"), ("2", "0")):
+    for exp in ("0", "1"):
         env = dict(os.environ, DB200_LIB=os.path.join(ROOT, "dalle_mtf_b200", "libdalle_b200_dev.so"),
                    DB200_ATTN_NG=ng, DB200_ATTN_EXP=exp, DB200_ATTN_PERSIST=persist)
         print(f"NG={ng} PERSIST={persist} EXP={exp}", flush=True)
