@@ -464,6 +464,294 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// forward, two query tiles per work item
+// ------------------------------------------------------------------------------------------------------------------
+// The event timeline of the kernel above shows the softmax chain as the critical path: per 128-key block the math warps
+// spend ~300 cycles waiting for the logits, ~500 reading them and exchanging row maxima across the column groups and
+// ~1 400 in the exponentials (MUFU runs at 16 / cycle / SM, i.e. 1 024 cycles for a 128 x 128 block) — every warp in
+// the same phase at the same time, the tensor pipe (1 024 cycles of products per block) waiting for P.
+// Here a work item is TWO consecutive 128-query tiles (A, B) of one (batch, head) that share every K / V tile, and each
+// softmax warpgroup owns one tile: thread r of warpgroup x owns row r of tile x with all its 128 key columns, so the
+// row maximum and the row sum are thread-local (no shared-memory exchange, no named barrier) and the two warpgroups are
+// naturally out of phase — while A's rows are in the exponentials, B's logits / P.V products run, and vice versa:
+//     S_A0 S_B0 | PV_A0 S_A1 | PV_B0 S_B1 | PV_A1 S_A2 | ...
+// TMEM: S_A [0,128) S_B [128,256) O_A [256,256+dh) O_B [384,384+dh); P overwrites the first 64 columns of its own S
+// buffer (the logits are read twice: a max pass and an exp pass of 32 columns at a time, the bf16 P chunk trailing the
+// read position).  Persistent: CTA c walks the items c, c + G, ... (item w = tile pair n_pairs-1 - w / (B H), heaviest
+// first); counters: kc / vc ring uses (one K and one V tile per key block, shared by the two tiles), cx key blocks of
+// tile x (parity of s_ready[x], p_ready[x], o_done[x]), ix items in which tile x existed (o_free[x]), it items (Q pair).
+namespace {
+template <int DH>
+struct Fwd2Ws {
+  static constexpr int NK = (DH == 128) ? 3 : 4;
+  static constexpr int NV = (DH == 128) ? 2 : 4;
+  static constexpr uint32_t TILE = 128 * DH * 2;
+  static constexpr uint32_t BAR_BYTES = 256;
+  static constexpr size_t SMEM = 2 * TILE + (NK + NV) * TILE + BAR_BYTES;
+  static_assert(SMEM <= 232448, "forward attention: shared memory over the 227 KiB per-CTA limit");
+  static constexpr int THREADS = 320;   // 2 softmax warpgroups + TMA warp + MMA warp
+};
+}  // namespace
+
+template <int DH>
+__global__ void __launch_bounds__(320, 1)
+attn_fwd2_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__ out, float* __restrict__ lse_out,
+                    int S, int H, int n_items, float scale) {
+  using C = Fwd2Ws<DH>;
+  constexpr int NK = C::NK, NV = C::NV;
+  constexpr int TMA_WARP = 8, MMA_WARP = 9;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t sQ = raw;                       // [2] Q_A, Q_B
+  const uint32_t sK = sQ + 2 * C::TILE, sV = sK + NK * C::TILE;
+  const uint32_t bars = sV + NV * C::TILE;
+  const uint32_t q_full = bars, q_empty = bars + 8;
+  const uint32_t k_full = bars + 16;               // [NK]
+  const uint32_t k_empty = k_full + 8 * NK;        // [NK]
+  const uint32_t v_full = k_empty + 8 * NK;        // [NV]
+  const uint32_t v_empty = v_full + 8 * NV;        // [NV]
+  const uint32_t s_ready = v_empty + 8 * NV;       // [2] per tile
+  const uint32_t p_ready = s_ready + 16;           // [2]
+  const uint32_t o_done = p_ready + 16;            // [2]
+  const uint32_t o_free = o_done + 16;             // [2]
+  const uint32_t tmem_slot = o_free + 16;
+  static_assert(8 * (2 + 2 * NK + 2 * NV + 8) + 8 <= C::BAR_BYTES, "barrier area");
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_qt = (S + 127) >> 7;
+  const int n_pairs = (n_qt + 1) >> 1;
+  const int n_bh = n_items / n_pairs;
+  const int G = (int)gridDim.x;
+
+  if (tid == 0) {
+    if (raw & 1023u) __trap();  // the 128-byte swizzle needs 1024-byte aligned tiles
+    tma_prefetch_desc(&tmQKV);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < NK; ++i) { mbar_init(k_full + 8 * i, 1); mbar_init(k_empty + 8 * i, 1); }
+    for (int i = 0; i < NV; ++i) { mbar_init(v_full + 8 * i, 1); mbar_init(v_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_ready + 8 * i, 1);
+      mbar_init(p_ready + 8 * i, 4);
+      mbar_init(o_done + 8 * i, 1);
+      mbar_init(o_free + 8 * i, 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == TMA_WARP) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == TMA_WARP) {
+    // ------------------------------------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      int wq = (int)blockIdx.x, itq = 0;
+      int wk = (int)blockIdx.x, jk = 0, kc = 0;
+      int wv = (int)blockIdx.x, jv = 0, vc = 0;
+      while (wq < n_items || wk < n_items || wv < n_items) {
+        if (wq < n_items && mbar_try_wait(q_empty, ((uint32_t)itq & 1u) ^ 1u)) {
+          const int pt = n_pairs - 1 - wq / n_bh, bh = wq % n_bh;
+          const bool has_b = 2 * pt + 1 < n_qt;
+          mbar_expect_tx(q_full, has_b ? 2 * C::TILE : C::TILE);
+          ws_load_tile<DH>(sQ, &tmQKV, q_full, 0 * H + bh % H, (2 * pt) * 128, bh / H);
+          if (has_b) ws_load_tile<DH>(sQ + C::TILE, &tmQKV, q_full, 0 * H + bh % H, (2 * pt + 1) * 128, bh / H);
+          wq += G; ++itq;
+        }
+        if (wk < n_items && mbar_try_wait(k_empty + 8 * (kc % NK), ((uint32_t)(kc / NK) & 1u) ^ 1u)) {
+          const int pt = n_pairs - 1 - wk / n_bh, bh = wk % n_bh, sk = kc % NK;
+          const int nmax = (2 * pt + 1 < n_qt) ? 2 * pt + 2 : 2 * pt + 1;   // key blocks of the pair
+          mbar_expect_tx(k_full + 8 * sk, C::TILE);
+          ws_load_tile<DH>(sK + sk * C::TILE, &tmQKV, k_full + 8 * sk, 1 * H + bh % H, jk * 128, bh / H);
+          ++kc;
+          if (++jk >= nmax) { jk = 0; wk += G; }
+        }
+        if (wv < n_items && mbar_try_wait(v_empty + 8 * (vc % NV), ((uint32_t)(vc / NV) & 1u) ^ 1u)) {
+          const int pt = n_pairs - 1 - wv / n_bh, bh = wv % n_bh, sv = vc % NV;
+          const int nmax = (2 * pt + 1 < n_qt) ? 2 * pt + 2 : 2 * pt + 1;
+          mbar_expect_tx(v_full + 8 * sv, C::TILE);
+          ws_load_tile<DH>(sV + sv * C::TILE, &tmQKV, v_full + 8 * sv, 2 * H + bh % H, jv * 128, bh / H);
+          ++vc;
+          if (++jv >= nmax) { jv = 0; wv += G; }
+        }
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    // ------------------------------------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);  // S = Q K^T : both K-major (K = dh)
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, DH, 0, 1);   // O = P V   : A from TMEM, B MN-major (K = keys)
+    uint32_t kc = 0, vc = 0;          // ring uses at the start of the current item
+    uint32_t cx[2] = {0, 0};          // P.V products issued per tile
+    uint32_t ix[2] = {0, 0};          // items in which the tile existed
+    int it = 0;
+    for (int w = (int)blockIdx.x; w < n_items; w += G, ++it) {
+      const int pt = n_pairs - 1 - w / n_bh;
+      const bool has_b = 2 * pt + 1 < n_qt;
+      const int nx[2] = {2 * pt + 1, has_b ? 2 * pt + 2 : 0};   // key blocks per tile
+      const int nmax = has_b ? nx[1] : nx[0];
+      const int last_tile_of = has_b ? 1 : 0;                   // for every block j < nmax the last active tile is this one
+      // logits of block j for tile x; releases K_j when x is the last tile that reads it
+      auto issue_s = [&](int x, int j) {
+        const uint32_t kuse = kc + (uint32_t)j, sk = kuse % NK;
+        mbar_wait(k_full + 8 * sk, (kuse / NK) & 1u);
+        tc_fence_after();
+        const uint64_t dq = desc_k_base(sQ + x * C::TILE), dk = desc_k_base(sK + sk * C::TILE);
+        const uint32_t tS = tmem + x * 128;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kk = 0; kk < DH / 16; ++kk)
+            umma_bf16_ss(tS, dq + kstep_k(kk), dk + kstep_k(kk), idesc_s, kk > 0 ? 1u : 0u);
+          umma_commit(s_ready + 8 * x);
+          if (x == last_tile_of) {
+            umma_commit(k_empty + 8 * sk);
+            if (j == nmax - 1) umma_commit(q_empty);   // the item's last logits product: the Q pair may be replaced
+          }
+        }
+        __syncwarp();
+      };
+      mbar_wait(q_full, (uint32_t)it & 1u);
+      issue_s(0, 0);
+      if (has_b) issue_s(1, 0);
+      for (int j = 0; j < nmax; ++j) {
+        const uint32_t vuse = vc + (uint32_t)j, sv = vuse % NV;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          if (j >= nx[x]) continue;    // tile A has one block less than tile B
+          mbar_wait(v_full + 8 * sv, (vuse / NV) & 1u);
+          mbar_wait(p_ready + 8 * x, cx[x] & 1u);
+          if (j == 0) mbar_wait(o_free + 8 * x, (ix[x] & 1u) ^ 1u);   // the previous epilogue of this tile slot has read O
+          tc_fence_after();
+          const uint64_t dv = desc_mn_base(sV + sv * C::TILE);
+          const uint32_t tP = tmem + x * 128, tO = tmem + 256 + x * 128;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_bf16_ts(tO, tP + kk * 8, dv + kstep_mn(kk), idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(o_done + 8 * x);
+            if (x == last_tile_of) umma_commit(v_empty + 8 * sv);
+          }
+          __syncwarp();
+          ++cx[x];
+          if (j + 1 < nx[x]) issue_s(x, j + 1);   // overwrites P_j of this tile, which the product above has consumed
+        }
+      }
+      kc += (uint32_t)nmax;
+      vc += (uint32_t)nmax;
+      ++ix[0];
+      if (has_b) ++ix[1];
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------- softmax warpgroups
+    const int x = warp >> 2;                       // tile A (warps 0-3) or B (warps 4-7)
+    const int row = tid & 127;                     // query row inside the tile = TMEM lane
+    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + x * 128 + lane_off, tO = tmem + 256 + x * 128 + lane_off;
+    const float c1 = scale * LOG2E_F;
+    uint32_t cb = 0;   // key blocks of this tile slot processed
+    for (int w = (int)blockIdx.x; w < n_items; w += G) {
+      const int pt = n_pairs - 1 - w / n_bh, bh = w % n_bh;
+      const int qt = 2 * pt + x;
+      if (qt >= n_qt) continue;                    // odd number of tiles: the last pair has no tile B
+      const int h = bh % H, b = bh / H;
+      const int n_kv = qt + 1;
+      const int qi = qt * 128 + row;
+      float m_used = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_kv; ++j, ++cb) {
+        mbar_wait(s_ready + 8 * x, cb & 1u);
+        tc_fence_after();
+        const int lim = (j == qt) ? row : 128;     // diagonal block: columns c > lim are keys after this query
+        // ---- pass 1: row maximum
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t rs[32];
+          tmem_ld_x32(tS + c * 32, rs);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int cc = c * 32 + i;
+            mx0 = fmaxf(mx0, cc <= lim ? __uint_as_float(rs[i]) : -INFINITY);
+            mx1 = fmaxf(mx1, cc + 1 <= lim ? __uint_as_float(rs[i + 1]) : -INFINITY);
+            mx2 = fmaxf(mx2, cc + 2 <= lim ? __uint_as_float(rs[i + 2]) : -INFINITY);
+            mx3 = fmaxf(mx3, cc + 3 <= lim ? __uint_as_float(rs[i + 3]) : -INFINITY);
+          }
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));   // finite: column 0 is always visible
+        if (j == 0) {
+          m_used = mx;
+        } else {
+          const bool need = (mx - m_used) * c1 > 8.f;
+          if (__any_sync(0xffffffffu, need)) {          // tcgen05.ld / st are warp-collective
+            mbar_wait(o_done + 8 * x, (cb - 1u) & 1u);  // the previous P.V of this tile has landed in O
+            tc_fence_after();
+            const float alpha = need ? ex2f((m_used - mx) * c1) : 1.f;
+#pragma unroll
+            for (int c = 0; c < DH / 32; ++c) {
+              uint32_t r[32];
+              tmem_ld_x32(tO + c * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+              tmem_st_x32(tO + c * 32, r);
+            }
+            if (need) {
+              l_run *= alpha;
+              m_used = mx;
+            }
+          }
+        }
+        // ---- pass 2: P = 2^(c1 (s - m_used)) -> bf16 pairs, 16 packed columns per 32 logits, trailing the read position
+        const float mc = m_used * c1;
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t rs[32], pk[16];
+          tmem_ld_x32(tS + c * 32, rs);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int cc = c * 32 + i;
+            float p0 = ex2f(fmaf(__uint_as_float(rs[i]), c1, -mc));
+            float p1 = ex2f(fmaf(__uint_as_float(rs[i + 1]), c1, -mc));
+            if (cc > lim) p0 = 0.f;
+            if (cc + 1 > lim) p1 = 0.f;
+            l0 += p0;
+            l1 += p1;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_x16(tS + c * 16, pk);
+        }
+        l_run += l0 + l1;
+        tmem_st_wait();
+        warp_arrive(p_ready + 8 * x, lane);
+      }
+      // ---- epilogue: O / l -> bf16, lse (both thread-local)
+      mbar_wait(o_done + 8 * x, (cb - 1u) & 1u);   // the tile's last P.V
+      tc_fence_after();
+      const float inv = 1.f / l_run;
+      bf16* op = out + (((long long)b * S + qi) * H + h) * DH;
+#pragma unroll
+      for (int c = 0; c < DH / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld_x32(tO + c * 32, r);
+        tmem_ld_wait();
+        if (qi < S) store_cols_bf16<32>(op + c * 32, r, inv);
+      }
+      warp_arrive(o_free + 8 * x, lane);   // the O accumulator may be overwritten by the next item's first P.V
+      if (qi < S) lse_out[((long long)b * H + h) * S + qi] = m_used * scale + logf(l_run);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // backward
 //   p  = exp(scale*s - lse)   (0 where key > query or the query is out of range)
 //   ds = p * (dp - delta) * scale
@@ -1067,8 +1355,35 @@ static int fwd_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, floa
   return check_launch("attn_fwd_ws_kernel");
 }
 
+// DB200_ATTN_FWD2 (development A/B switch, read once): 1 = the two-tile forward kernel
+static int attn_fwd2_on() {
+  static const int v = [] { const char* e = getenv("DB200_ATTN_FWD2"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
+template <int DH>
+static int fwd2_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H,
+                            float scale) {
+  using C = Fwd2Ws<DH>;
+  CUtensorMap tm;
+  int rc = ws_qkv_map(&tm, qkv, B, S, H, DH);
+  if (rc != DB200_OK) return rc;
+  static const cudaError_t attr = cudaFuncSetAttribute(attn_fwd2_ws_kernel<DH>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+  DB200_CUDA(attr);
+  const int n_qt = (S + 127) / 128;
+  const int n_items = ((n_qt + 1) / 2) * H * B;
+  dim3 grid(n_items > sm_count() ? sm_count() : n_items);
+  attn_fwd2_ws_kernel<DH><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, n_items, scale);
+  return check_launch("attn_fwd2_ws_kernel");
+}
+
 int attn_fwd_ws_launch(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H, int dh,
                        float scale) {
+  if (attn_fwd2_on()) {
+    if (dh == 128) return fwd2_ws_launch_t<128>(stream, qkv, out, lse, B, S, H, scale);
+    return fwd2_ws_launch_t<64>(stream, qkv, out, lse, B, S, H, scale);
+  }
   if (attn_ng() == 2) {
     if (dh == 128) return fwd_ws_launch_t<128, 2>(stream, qkv, out, lse, B, S, H, scale);
     return fwd_ws_launch_t<64, 2>(stream, qkv, out, lse, B, S, H, scale);
