@@ -37,7 +37,9 @@ class DataParallel:
     """
 
     # CTAs NCCL may occupy while the persistent 148-CTA tcgen05 grids of backward are running (0 = NCCL's default).
-    MAX_CTAS = int(os.environ.get("DB200_NCCL_MAX_CTAS", "8"))
+    # The same number of SMs is taken out of the persistent kernels' grids (db200_set_reserved_sms), so that the two fit
+    # side by side; the overlapped all-reduce only has to move 287 MB during ~10 ms of backward: four CTAs are plenty.
+    MAX_CTAS = int(os.environ.get("DB200_NCCL_MAX_CTAS", "4"))
     # A second communicator without that cap carries the collectives that run when no compute is left to overlap with:
     # the last gradient bucket ([wte | wpe], finished by the final kernel of backward), the ZeRO-1 parameter
     # all-gather and the eval-loss reduction.  -1 disables it (everything on the capped communicator).
@@ -87,6 +89,8 @@ class DataParallel:
             return comm
 
         self.comm = create(self.MAX_CTAS)
+        if self.MAX_CTAS > 0 and os.environ.get("DB200_RESERVE_SMS", "1") != "0":
+            L.check(lib.db200_set_reserved_sms(self.MAX_CTAS), "set_reserved_sms")
         if self.TAIL_CTAS >= 0 and self.TAIL_CTAS != self.MAX_CTAS:
             self.comm_tail = create(self.TAIL_CTAS)
 

@@ -98,6 +98,7 @@ _SIGNATURES = {
     "db200_comm_unique_id": [c_vp, c_sz],
     "db200_comm_create": [c_int, c_int, c_int, c_vp, c_int, ctypes.POINTER(c_vp)],
     "db200_comm_destroy": [c_vp],
+    "db200_set_reserved_sms": [c_int],
     "db200_comm_register": [c_vp, c_vp, c_sz, ctypes.POINTER(c_int)],
     "db200_comm_info": [c_vp, ctypes.POINTER(c_int), ctypes.POINTER(c_int), ctypes.POINTER(c_int)],
     "db200_bucket_allreduce_launch": [c_vp, c_vp, c_vp, c_sz, c_int],

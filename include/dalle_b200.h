@@ -319,6 +319,9 @@ int db200_space_to_depth_f32(db200_stream_t stream, const float* in, float* out,
  * ------------------------------------------------------------------------------------------------------------------ */
 #define DB200_F32 0
 #define DB200_BF16 1
+/* Persistent kernels size their grids to (SM count - n): leaves n SMs to a collective that runs concurrently (the
+ * data-parallel path reserves the CTA cap it gave NCCL).  0 <= n <= 64; process-wide. */
+int db200_set_reserved_sms(int n);
 typedef struct db200_comm db200_comm;
 int db200_comm_load_nccl(const char* libnccl_path);
 int db200_comm_unique_id(void* id_out, size_t bytes);
