@@ -464,8 +464,12 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// forward, two query tiles per work item
+// forward, two query tiles per work item — DEVELOPMENT builds only (make DEV=1, DB200_ATTN_FWD2=1): numerically validated
+// (same 65 diagnostic cases), not faster than the kernel above on B200 (96 vs 91 us at (32,1280,4,128)): with one
+// warpgroup per tile each scheduler holds a single math warp of the tile that is in its exponentials, and the chain of
+// dependent FFMA -> MUFU -> FADD per row is latency-bound; the shipped library does not contain it.
 // ------------------------------------------------------------------------------------------------------------------
+#ifdef DB200_DEV_KNOBS
 // The event timeline of the kernel above shows the softmax chain as the critical path: per 128-key block the math warps
 // spend ~300 cycles waiting for the logits, ~500 reading them and exchanging row maxima across the column groups and
 // ~1 400 in the exponentials (MUFU runs at 16 / cycle / SM, i.e. 1 024 cycles for a 128 x 128 block) — every warp in
@@ -750,6 +754,7 @@ attn_fwd2_ws_kernel(const __grid_constant__ CUtensorMap tmQKV, bf16* __restrict_
     tmem_dealloc(tmem, 512);
   }
 }
+#endif  // DB200_DEV_KNOBS
 
 // ------------------------------------------------------------------------------------------------------------------
 // backward
@@ -1323,18 +1328,27 @@ static int ws_o_map(CUtensorMap* tm, const void* o, int B, int S, int H, int dh)
   return make_tmap_bf16(tm, o, 4, dims, strides, box);
 }
 
-// DB200_ATTN_NG (development A/B switch, read once): number of math warpgroups per CTA, 2 (default) or 4
+// Development A/B switches (make DEV=1 only; the shipped library runs NG = 2, persistent kernels):
+//   DB200_ATTN_NG       number of math warpgroups per CTA, 2 or 4
+//   DB200_ATTN_PERSIST  bit 0 = forward, bit 1 = backward as persistent kernels (default 3); 0 = one CTA per work item
+//   DB200_ATTN_FWD2     1 = the two-tile forward kernel
+#ifdef DB200_DEV_KNOBS
 static int attn_ng() {
   static const int ng = [] { const char* e = getenv("DB200_ATTN_NG"); return (e && atoi(e) == 4) ? 4 : 2; }();
   return ng;
 }
-
-// DB200_ATTN_PERSIST (development A/B switch, read once): bit 0 = forward, bit 1 = backward run as persistent kernels
-// (one CTA per SM walking the work items, default 3); 0 = one CTA per work item
 static int attn_persist_bits() {
   static const int v = [] { const char* e = getenv("DB200_ATTN_PERSIST"); return e ? atoi(e) : 3; }();
   return v;
 }
+static int attn_fwd2_on() {
+  static const int v = [] { const char* e = getenv("DB200_ATTN_FWD2"); return e ? atoi(e) : 0; }();
+  return v;
+}
+#else
+static int attn_ng() { return 2; }
+static int attn_persist_bits() { return 3; }
+#endif
 
 template <int DH, int NG>
 static int fwd_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H,
@@ -1350,17 +1364,16 @@ static int fwd_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, floa
   // persistent: one CTA per SM walks the items in order of decreasing work (DB200_ATTN_PERSIST=0, development A/B
   // switch: one CTA per item as before)
   dim3 grid((attn_persist_bits() & 1) && n_items > sm_count() ? sm_count() : n_items);
-  static const int xflags = [] { const char* e = getenv("DB200_ATTN_EXP"); return e ? atoi(e) : 0; }();  // DEV builds only
+#ifdef DB200_DEV_KNOBS
+  static const int xflags = [] { const char* e = getenv("DB200_ATTN_EXP"); return e ? atoi(e) : 0; }();
+#else
+  const int xflags = 0;
+#endif
   attn_fwd_ws_kernel<DH, NG><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, n_items, scale, xflags);
   return check_launch("attn_fwd_ws_kernel");
 }
 
-// DB200_ATTN_FWD2 (development A/B switch, read once): 1 = the two-tile forward kernel
-static int attn_fwd2_on() {
-  static const int v = [] { const char* e = getenv("DB200_ATTN_FWD2"); return e ? atoi(e) : 0; }();
-  return v;
-}
-
+#ifdef DB200_DEV_KNOBS
 template <int DH>
 static int fwd2_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H,
                             float scale) {
@@ -1377,19 +1390,26 @@ static int fwd2_ws_launch_t(cudaStream_t stream, const void* qkv, void* out, flo
   attn_fwd2_ws_kernel<DH><<<grid, C::THREADS, C::SMEM, stream>>>(tm, (bf16*)out, lse, S, H, n_items, scale);
   return check_launch("attn_fwd2_ws_kernel");
 }
+#endif  // DB200_DEV_KNOBS
 
 int attn_fwd_ws_launch(cudaStream_t stream, const void* qkv, void* out, float* lse, int B, int S, int H, int dh,
                        float scale) {
+#ifdef DB200_DEV_KNOBS
   if (attn_fwd2_on()) {
     if (dh == 128) return fwd2_ws_launch_t<128>(stream, qkv, out, lse, B, S, H, scale);
     return fwd2_ws_launch_t<64>(stream, qkv, out, lse, B, S, H, scale);
   }
+#endif
   if (attn_ng() == 2) {
     if (dh == 128) return fwd_ws_launch_t<128, 2>(stream, qkv, out, lse, B, S, H, scale);
     return fwd_ws_launch_t<64, 2>(stream, qkv, out, lse, B, S, H, scale);
   }
+#ifdef DB200_DEV_KNOBS
   if (dh == 128) return fwd_ws_launch_t<128, 4>(stream, qkv, out, lse, B, S, H, scale);
   return fwd_ws_launch_t<64, 4>(stream, qkv, out, lse, B, S, H, scale);
+#else
+  return set_error(DB200_E_UNSUPPORTED, "attn_fwd: unreachable");
+#endif
 }
 
 template <int DH, int NG>
@@ -1432,8 +1452,12 @@ int attn_bwd_ws_launch(cudaStream_t stream, const void* qkv, const void* dout, c
     if (dh == 128) return bwd_ws_launch_t<128, 2>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
     return bwd_ws_launch_t<64, 2>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
   }
+#ifdef DB200_DEV_KNOBS
   if (dh == 128) return bwd_ws_launch_t<128, 4>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
   return bwd_ws_launch_t<64, 4>(stream, qkv, dout, lse, delta, dqkv, B, S, H, scale);
+#else
+  return set_error(DB200_E_UNSUPPORTED, "attn_bwd: unreachable");
+#endif
 }
 
 }  // namespace db200
