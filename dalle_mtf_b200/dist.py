@@ -53,6 +53,7 @@ class DataParallel:
         self.enabled = self.world > 1
         self.comm = None          # db200_comm* (ctypes void pointer) when the C-ABI communicator is in use
         self.comm_tail = None     # uncapped communicator for the exposed collectives (None: use self.comm)
+        self._reserve = 0         # SMs the persistent kernels leave free while bucket all-reduces may be in flight
         self.registered = False
 
     def init(self, backend=None):
@@ -89,8 +90,7 @@ class DataParallel:
             return comm
 
         self.comm = create(self.MAX_CTAS)
-        if self.MAX_CTAS > 0 and os.environ.get("DB200_RESERVE_SMS", "1") != "0":
-            L.check(lib.db200_set_reserved_sms(self.MAX_CTAS), "set_reserved_sms")
+        self._reserve = self.MAX_CTAS if (self.MAX_CTAS > 0 and os.environ.get("DB200_RESERVE_SMS", "1") != "0") else 0
         if self.TAIL_CTAS >= 0 and self.TAIL_CTAS != self.MAX_CTAS:
             self.comm_tail = create(self.TAIL_CTAS)
 
@@ -125,6 +125,14 @@ class DataParallel:
             L.check(L.load().db200_comm_register(self.comm, flat.data_ptr(), flat.numel() * flat.element_size(),
                                                  ctypes.byref(ok)), "comm_register")
             self.registered = True
+
+    def begin_overlap(self):
+        """Call right before the backward pass whose buckets are all-reduced on the fly: from here until wait() the
+        persistent kernels size their grids to (SM count - CTA cap), so the collective's CTAs and theirs fit side by
+        side (grids are sized on the host at launch time; forward / optimizer kernels keep all SMs)."""
+        if self.comm is not None and self._reserve:
+            from . import lib as L
+            L.check(L.load().db200_set_reserved_sms(self._reserve), "set_reserved_sms")
 
     def make_bucket_hook(self, flat):
         """Returns on_bucket_ready(start, end) for the engines' backward: async all-reduce(SUM) of flat[start:end],
@@ -170,6 +178,8 @@ class DataParallel:
             L.check(L.load().db200_bucket_allreduce_wait(self.comm, L.stream_ptr()), "bucket_allreduce_wait")
             if self.comm_tail is not None:
                 L.check(L.load().db200_bucket_allreduce_wait(self.comm_tail, L.stream_ptr()), "bucket_allreduce_wait")
+            if self._reserve:
+                L.check(L.load().db200_set_reserved_sms(0), "set_reserved_sms")
         for h in self.handles:
             h.wait()
         self.handles = []

@@ -151,6 +151,8 @@ def dalle_model_fn(features, labels, mode, params):
         for i in range(num_microbatches):
             model.forward(toks[i * mb:(i + 1) * mb])
             last = i == num_microbatches - 1
+            if last:
+                dp.begin_overlap()
             # loss = mean over the GLOBAL batch (models.py:353-354): every rank back-props local_sum / (B*S) and the
             # all-reduce SUMs the shard partials (mtf semantics)
             model.backward(1.0 / total_tokens_global, on_bucket_ready=hook if last else None)
@@ -260,6 +262,7 @@ def vae_model_fn(features, labels, mode, params):
         run(features, True)
         # CrossShardOptimizer: cross-replica MEAN of the gradients (model_fns_tf.py:61) = bucketed SUM all-reduce that
         # overlaps with the rest of backward (decoder, codebook, encoder ranges), then 1/N inside the Adam kernel
+        dp.begin_overlap()
         model.backward(on_bucket_ready=dp.make_bucket_hook(model.grads))
         dp.wait()
         spec.global_step += 1
