@@ -67,9 +67,21 @@ class DataParallel:
             # uninitialised unless somebody uses it (the data plane below does not)
             backend = backend or ("cpu:gloo,cuda:nccl" if cuda else "gloo")
             dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
-        if self.enabled and cuda and self.comm is None and os.environ.get("DB200_DP_BACKEND", "cabi") == "cabi":
-            self._create_comm()
+        # the NCCL communicators are created at first use (every rank reaches it at the same point of its first step),
+        # after the model function had the chance to size the CTA cap for its step (hint_tokens_per_gpu)
+        self._want_comm = bool(self.enabled and cuda and os.environ.get("DB200_DP_BACKEND", "cabi") == "cabi")
         return self
+
+    def hint_tokens_per_gpu(self, tokens):
+        """Sizes the CTA cap of the overlapped communicator (unless DB200_NCCL_MAX_CTAS is set): the gradient volume
+        is fixed by the model, the time to hide it behind shrinks with the per-GPU batch.  A long backward (weak
+        scaling, >= 16 k tokens per GPU) hides 287 MB behind 4 CTAs; a short one (strong scaling) needs more."""
+        if self.comm is None and "DB200_NCCL_MAX_CTAS" not in os.environ:
+            self.MAX_CTAS = 4 if tokens >= 16384 else 16
+
+    def _ensure_comm(self):
+        if getattr(self, "_want_comm", False) and self.comm is None:
+            self._create_comm()
 
     def _create_comm(self):
         from . import lib as L
@@ -108,6 +120,7 @@ class DataParallel:
     def _launch(self, t, exposed=False):
         """Asynchronous in-place SUM all-reduce of a contiguous fp32 / bf16 tensor (a slice of a flat buffer).
         exposed: nothing is left to overlap with — use the communicator without the CTA cap."""
+        self._ensure_comm()
         if self.comm is not None:
             from . import lib as L
             dt = {torch.float32: 0, torch.bfloat16: 1}[t.dtype]
@@ -119,6 +132,7 @@ class DataParallel:
 
     def register(self, flat):
         """ncclCommRegister of a long-lived flat buffer (best effort; once)."""
+        self._ensure_comm()
         if self.comm is not None and not self.registered:
             from . import lib as L
             ok = ctypes.c_int(0)
@@ -130,6 +144,7 @@ class DataParallel:
         """Call right before the backward pass whose buckets are all-reduced on the fly: from here until wait() the
         persistent kernels size their grids to (SM count - CTA cap), so the collective's CTAs and theirs fit side by
         side (grids are sized on the host at launch time; forward / optimizer kernels keep all SMs)."""
+        self._ensure_comm()
         if self.comm is not None and self._reserve:
             from . import lib as L
             L.check(L.load().db200_set_reserved_sms(self._reserve), "set_reserved_sms")
@@ -161,6 +176,7 @@ class DataParallel:
         if not self.enabled:
             return buf
         mine = buf[self.rank * count_per_rank:(self.rank + 1) * count_per_rank]
+        self._ensure_comm()
         if self.comm is not None:
             from . import lib as L
             dt = {torch.float32: 0, torch.bfloat16: 1}[buf.dtype]

@@ -143,6 +143,8 @@ def dalle_model_fn(features, labels, mode, params):
         # sum of per-token losses over all ranks (all-reduced with the gradients) / global token count
         return model.grads[model.aux_off:model.aux_off + 1]
 
+    dp.hint_tokens_per_gpu(local_batch * S)
+
     def train_op(features, labels):
         toks = assemble(features, labels)
         model.zero_grads()
