@@ -179,9 +179,6 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
     for (int c = 0; c < nchunk; ++c) {
       const int s = c % FT_NSTAGE;
       mbar_wait(sm.full(s), (uint32_t)((c / FT_NSTAGE) & 1));
-#ifdef DB200_F32CONV_CFENCE
-      fence_proxy_async_smem();   // A/B build: proxy fence on the consumer side, after the acquire of the producers' writes
-#endif
       tc_fence_after();
       const uint32_t sA = sm.stage(s), sB = sm.stage(s) + 3 * FT_A_PART;
       uint64_t ad[3], bd[3];
@@ -206,9 +203,7 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
       store_chunk(s, ra, rb);
       // the proxy fence compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it waits for every outstanding memory operation
       // of the thread, so the look-ahead loads are issued AFTER it (issued before, each chunk paid their L2 round trip)
-#ifndef DB200_F32CONV_CFENCE
       fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma (async proxy)
-#endif
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.full(s));
       if (c + 2 < nchunk) load_chunk(c + 2, ra, rb);
@@ -346,9 +341,6 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
     for (int c = 0; c < nchunk; ++c) {
       const int s = c % FT_NSTAGE;
       mbar_wait(sm.full(s), (uint32_t)((c / FT_NSTAGE) & 1));
-#ifdef DB200_F32CONV_CFENCE
-      fence_proxy_async_smem();
-#endif
       tc_fence_after();
       const uint32_t sA = sm.stage(s), sB = sm.stage(s) + 3 * FT_A_PART;
       uint64_t ad[3], bd[3];
@@ -369,9 +361,7 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
       const int s = c % FT_NSTAGE;
       if (c >= FT_NSTAGE) mbar_wait(sm.bar(s), (uint32_t)((c / FT_NSTAGE - 1) & 1));
       store_chunk(s, rp, rq);
-#ifndef DB200_F32CONV_CFENCE
       fence_proxy_async_smem();   // before the look-ahead loads (see the gather-GEMM kernel)
-#endif
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.full(s));
       if (c + 2 < nchunk) load_chunk(c + 2, rp, rq);
