@@ -201,12 +201,10 @@ conv_gemm_f32_tc_kernel(const ConvGemmParams p) {
       const int s = c % FT_NSTAGE;
       if (c >= FT_NSTAGE) mbar_wait(sm.bar(s), (uint32_t)((c / FT_NSTAGE - 1) & 1));
       store_chunk(s, ra, rb);
-      // the proxy fence compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it waits for every outstanding memory operation
-      // of the thread, so the look-ahead loads are issued AFTER it (issued before, each chunk paid their L2 round trip)
+      if (c + 2 < nchunk) load_chunk(c + 2, ra, rb);
       fence_proxy_async_smem();   // generic-proxy stores -> visible to tcgen05.mma (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.full(s));
-      if (c + 2 < nchunk) load_chunk(c + 2, ra, rb);
     };
     float4 ra0[8], rb0[4], ra1[8], rb1[4];
     load_chunk(0, ra0, rb0);
@@ -361,10 +359,10 @@ conv_wgrad_f32_tc_kernel(const ConvWgradParams p) {
       const int s = c % FT_NSTAGE;
       if (c >= FT_NSTAGE) mbar_wait(sm.bar(s), (uint32_t)((c / FT_NSTAGE - 1) & 1));
       store_chunk(s, rp, rq);
-      fence_proxy_async_smem();   // before the look-ahead loads (see the gather-GEMM kernel)
+      if (c + 2 < nchunk) load_chunk(c + 2, rp, rq);
+      fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(sm.full(s));
-      if (c + 2 < nchunk) load_chunk(c + 2, rp, rq);
     };
     float4 rp0[8], rq0[4], rp1[8], rq1[4];
     if (nchunk > 0) load_chunk(0, rp0, rq0);
