@@ -213,8 +213,8 @@ def test_bench_tokenizer_config_token_match_rate_and_near_tie_margins():
                          median_margin=margin.median().item())
         record(f"TOK 256px K512 {mode}", **out[mode])
     assert out["fp32"]["n_mismatch"] == 0                                     # token indices: bit-exact
-    # the split codebook product accumulates its partial products with fp32 reductions whose order varies from run to run,
-    # so a handful of near-ties flip differently each time (18-21 of 2048 observed); what matters is the margin test below
+    # 2 027 / 2 048 with every convolution (the first layer included, bf16-rounded weights) on tcgen05; what matters is
+    # that every flip is a near-tie of the fp32 logits (margin test below)
     assert out["bf16_tc"]["match"] >= 0.985
     assert out["bf16_tc"]["worst_mismatch_margin"] <= 0.1 * out["bf16_tc"]["median_margin"] + 1e-3
 
