@@ -224,6 +224,11 @@ def _dp_worker(rank, world, port, out):
     flat = torch.full((300,), float(rank + 1))
     hook = dp.make_bucket_hook(flat)
     # backward finishes buckets from the tail: [200,300), then [100,200); [0,100) is left un-reduced on purpose
+    dp.hint_tokens_per_gpu(40960)          # sizes the CTA cap of the (here absent) NCCL communicator: host logic only
+    assert dp.MAX_CTAS == 4 or "DB200_NCCL_MAX_CTAS" in os.environ
+    dp.hint_tokens_per_gpu(5120)
+    assert dp.MAX_CTAS == 16 or "DB200_NCCL_MAX_CTAS" in os.environ
+    dp.begin_overlap()                     # no C-ABI communicator on CPU: a no-op
     hook(200, 364)      # end beyond the buffer is clipped
     hook(100, 200)
     dp.wait()
